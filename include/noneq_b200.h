@@ -1,0 +1,230 @@
+/* noneq_b200.h -- C ABI of libnoneq_b200.so (sm_100a), the drop-in boundary of the
+ * noneq_opt ensemble hot path.
+ *
+ * The reference (mc2engel/noneq_opt) has no FFI: its hot path is reached through plain
+ * Python functions which trace into one XLA computation.  Each entry point below replaces
+ * the body of one of those functions (cited as file:line relative to the reference root);
+ * the Python package `noneq_opt_b200` keeps the reference signatures and calls these
+ * through ctypes (see INTEGRATION.md for the binding a maintainer of the reference adds).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless marked "host";
+ *     the library never allocates or frees caller-visible memory (workspaces are sized
+ *     by nq_*_workspace_bytes and passed in);
+ *   - every call enqueues on `stream` (a cudaStream_t passed as void*) and returns
+ *     without synchronising;
+ *   - return 0 on success, a negative NQ_ERR_* otherwise; nq_last_error() returns a
+ *     thread-local message for the last failure; no exceptions cross the ABI;
+ *   - re-entrant: no global mutable state apart from the thread-local error string;
+ *   - keys are raw uint32[2] threefry keys exactly as jax.random.PRNGKey / split
+ *     produce them (original, non-partitionable counter layout).
+ */
+#ifndef NONEQ_B200_H_
+#define NONEQ_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NQ_VERSION 100
+
+#define NQ_OK 0
+#define NQ_ERR_INVALID_ARGUMENT (-1)
+#define NQ_ERR_UNSUPPORTED (-2)
+#define NQ_ERR_CUDA (-3)
+#define NQ_ERR_WORKSPACE (-4)
+
+int nq_version(void);
+const char* nq_last_error(void);
+/* number of kernels this library has launched since load (all threads); bench.py's gpu_launches */
+uint64_t nq_launch_count(void);
+
+/* ------------------------------------------------------------------ random (jax.random) */
+/* jax.random.split(key, num)[first : first+count]  ->  out[count][2].
+ * Replaces jax.random.split at barrier_crossing.py:221,253; ising.py:283. */
+int nq_random_split(const uint32_t key[2] /*host*/, int64_t num, int64_t first, int64_t count,
+                    uint32_t* out, void* stream);
+/* jax.random.bits(key, (size,), uint32)[first : first+count] */
+int nq_random_bits(const uint32_t key[2] /*host*/, int64_t size, int64_t first, int64_t count,
+                   uint32_t* out, void* stream);
+/* jax.random.uniform(key,(size,),f32,lo,hi) / jax.random.normal(key,(size,),f32) slices */
+int nq_random_uniform(const uint32_t key[2] /*host*/, int64_t size, int64_t first, int64_t count,
+                      float lo, float hi, float* out, void* stream);
+int nq_random_normal(const uint32_t key[2] /*host*/, int64_t size, int64_t first, int64_t count,
+                     float* out, void* stream);
+
+/* ------------------------------------------------------------------ Langevin */
+#define NQ_POT_SPRING 0              /* potentials.py:47-52   V_spring(k_s)               */
+#define NQ_POT_BIOMOLECULE 1         /* potentials.py:27-35   V_biomolecule(...)          */
+#define NQ_POT_BIOMOLECULE_SHIFTED 2 /* potentials.py:37-45   V_biomolecule_shifted(...)  */
+
+#define NQ_SHIFT_FREE 0     /* jax_md.space.free():      R + dR            */
+#define NQ_SHIFT_PERIODIC 1 /* jax_md.space.periodic(b): mod(R + dR, box)  */
+
+#define NQ_MATH_STRICT 0 /* reference operation order, IEEE div/sqrt, accurate exp/log, no FMA */
+#define NQ_MATH_FAST 1   /* MUFU exp2/log2/rcp, FMA contraction allowed                       */
+
+typedef struct NqLangevinDesc {
+  int32_t potential;  /* NQ_POT_*   */
+  int32_t shift_kind; /* NQ_SHIFT_* */
+  int32_t math_mode;  /* NQ_MATH_*  */
+  int32_t reserved;
+  /* potential parameters, python floats of the reference's factory call */
+  double k_s, kappa_l, kappa_r, x_m, delta_E, beta;
+  /* brownian(energy, shift, dt, kT, gamma) + init_fn(mass)  barrier_crossing.py:28-75 */
+  double dt, kT, gamma, mass, box;
+  int64_t steps;     /* simulation_steps S            barrier_crossing.py:97 */
+  int64_t eq_steps;  /* Neq, at r0 = r_table[0]       barrier_crossing.py:115-121 */
+} NqLangevinDesc;
+
+/* moments[] layout written by the Langevin entry points (sums over the n trajectories of the call) */
+#define NQ_MOM_N 0
+#define NQ_MOM_W 1
+#define NQ_MOM_W2 2
+#define NQ_MOM_LOGP 3
+#define NQ_MOM_WLOGP 4
+#define NQ_MOM_EST 5
+#define NQ_MOM_COUNT 8
+
+size_t nq_langevin_workspace_bytes(int64_t n, int32_t D);
+
+/* run_brownian_opt (barrier_crossing.py:97-143) for n trajectories, given the trap table
+ * r_table[S+1] (MakeSchedule_chebyshev :145-151, built by the host) and the per-trajectory
+ * seeds (rows of jax.random.split(seed, B), :221).  The kernel performs the
+ * `key, split = random.split(key)` of :133 itself.
+ *   work[n]   = works.sum()      logp[n] = log_probs.sum()     x_final[n] = positions[-1]
+ *   positions : nullable, TIME-MAJOR [n_rec][n], n_rec = S/pos_stride + 1, row i = step i*pos_stride
+ *               (row 0 is the equilibrated start, :142)
+ *   step_works: nullable, time-major [S+1][n] (row 0 = 0, :141); step_logps: nullable [S][n]
+ *   moments   : nullable double[NQ_MOM_COUNT]                                               */
+int nq_langevin_forward(const NqLangevinDesc* desc /*host*/, const float* r_table,
+                        const float* x0, const uint32_t* seeds, int64_t n,
+                        float* work, float* logp, float* x_final,
+                        float* positions, int64_t pos_stride,
+                        float* step_works, float* step_logps,
+                        double* moments, void* workspace, size_t workspace_bytes, void* stream);
+
+/* estimate_gradient_boltzinit / _logP / _reparam / _REINFORCE_recordall
+ * (barrier_crossing.py:204-224, 262-333): one fused pass that also accumulates, per
+ * trajectory, A_j = sum_k dlogp_k/dr_k * phi[k-1][j] and B_j = sum_k dW/dr_k * phi[k-1][j]
+ * (k = 1..S-1; phi[S-1][D] = d r_table[1..S-1] / d variables, row-major) and reduces
+ *   grad_sums[0][j] = sum_n W_n A_nj   (log-prob / REINFORCE score term, :270)
+ *   grad_sums[1][j] = sum_n B_nj       (reparameterisation term, :271)
+ * over the n trajectories of this call (NOT divided by the batch size: the caller divides
+ * after summing over shards/ranks).  estimator[n] = logp*W + W (:212).                     */
+int nq_langevin_grad(const NqLangevinDesc* desc /*host*/, const float* r_table,
+                     const float* phi, int32_t D,
+                     const float* x0, const uint32_t* seeds, int64_t n,
+                     float* work, float* logp, float* estimator, float* x_final,
+                     double* grad_sums /*[2][D]*/, double* moments,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Checkpointed forward + replay ("adjoint") pair: the forward pass stores (x, rng) every
+ * `ckpt_every` steps; the replay pass regenerates each segment from its checkpoint and
+ * accumulates the gradient wrt EVERY trap position,
+ *   gbar[k] = sum_n ( lbar[n] * dlogp_{n,k}/dr_k + wbar[n] * dW_n/dr_k ),  k = 0..S
+ * for arbitrary per-trajectory cotangents (REINFORCE: lbar = W, wbar = 1).  This is the
+ * reverse pass of jax.grad through lax.scan / control_flow.checkpoint_scan
+ * (control_flow.py:16-31) for this integrator, where positions carry no derivative
+ * (stop_gradient, barrier_crossing.py:88).                                                 */
+size_t nq_langevin_ckpt_count(int64_t steps, int64_t ckpt_every);
+int nq_langevin_forward_ckpt(const NqLangevinDesc* desc /*host*/, const float* r_table,
+                             const float* x0, const uint32_t* seeds, int64_t n,
+                             int64_t ckpt_every,
+                             float* work, float* logp, float* x_final,
+                             float* ckpt_x /*[n_ckpt][n]*/, uint32_t* ckpt_rng /*[n_ckpt][2][n]*/,
+                             double* moments, void* workspace, size_t workspace_bytes, void* stream);
+int nq_langevin_replay(const NqLangevinDesc* desc /*host*/, const float* r_table,
+                       int64_t n, int64_t ckpt_every,
+                       const float* ckpt_x, const uint32_t* ckpt_rng,
+                       const float* lbar /*[n]*/, const float* wbar /*[n]*/,
+                       double* gbar /*[S+1]*/, void* workspace, size_t workspace_bytes, void* stream);
+
+/* run_brownian_stationary_trap (barrier_crossing.py:227-241 / simulate.py:101-115):
+ * S steps at constant r0; x_final[n] = traj[-1] (single_brownian_eqm :243-247);
+ * positions nullable time-major [S][n] (single_brownian_stiffness simulate.py:117-121).   */
+int nq_langevin_stationary(const NqLangevinDesc* desc /*host*/, float r0,
+                           const float* x0, const uint32_t* seeds, int64_t n,
+                           float* x_final, float* positions, void* stream);
+
+/* One apply_fn step (barrier_crossing.py:77-92 / simulate.py:82-97) for n independent states:
+ * rng[n][2] is split in place (`key, split = jax.random.split(state.rng)`), x[n] is advanced by
+ * one Euler-Maruyama step at trap position r0, log_prob[n] receives Normal.log_prob(dR).     */
+int nq_langevin_apply(const NqLangevinDesc* desc /*host*/, float r0, float* x, uint32_t* rng,
+                      float* log_prob, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------ Ising */
+#define NQ_ISING_NCLASS 10 /* (spin in {-1,+1}) x (neighbour sum in {-4,-2,0,2,4}) */
+/* class index c = 5*(s>0) + (nsum+4)/2 */
+
+/* per-(replica, sweep) float outputs, plane-major: out[f][r][t], t = 0..T-2 */
+#define NQ_IS_WORK 0
+#define NQ_IS_HEAT 1
+#define NQ_IS_FWD 2
+#define NQ_IS_REV 3
+#define NQ_IS_EP 4
+#define NQ_IS_MAG 5
+#define NQ_IS_ENERGY 6
+#define NQ_IS_NSUMMARY 7
+/* partial derivatives used by the gradient estimators (Appendix B.2 of SURVEY.md) */
+#define NQ_IS_DFWD_DH 0
+#define NQ_IS_DFWD_DL 1
+#define NQ_IS_DREV_DH 2
+#define NQ_IS_DREV_DL 3
+#define NQ_IS_NPARTIAL 4
+
+typedef struct NqIsingDesc {
+  int32_t L;          /* lattice side (2-D, periodic, even)          ising.py:99-106 */
+  int32_t T;          /* time_steps; T-1 sweeps                      ising.py:153-173 */
+  int64_t R;          /* replicas (rows of split(seed, batch_size),  ising.py:283)   */
+  int32_t spins0_broadcast; /* 1: spins0 holds ONE lattice shared by all replicas    */
+  int32_t reserved;
+} NqIsingDesc;
+
+size_t nq_ising_words_per_lattice(int32_t L); /* = L*L/32 (bit b of word w = site 32*w+b, row-major; 1 = spin +1) */
+size_t nq_ising_workspace_bytes(const NqIsingDesc* desc);
+
+/* simulate_ising (ising.py:153-173) for R replicas: T-1 x update (:129-150), each two
+ * masked_update half-sweeps (:109-126, odd-parity sites first :99-106), with
+ * seeds_t = split(seed_r, T-1)[t], (seed_even, seed_odd) = split(seed_t, 2) and the
+ * full-lattice uniform draw of distrax.Bernoulli reproduced counter-for-counter.
+ *   thr     [T-1][16] uint32 : acceptance thresholds ceil(sigmoid(logit_c) * 2^23) per class
+ *                              (entries >= NQ_ISING_NCLASS unused); flip iff (bits>>9) < thr
+ *   lut     [T-1][4][16] double : per class  logit, log_sigmoid(-logit), sigmoid(logit), spare
+ *   field, log_temp [T] float : the schedule tables (IsingParameters :14-16)
+ *   spins0  bit-packed [R or 1][L*L/32];  seeds [R][2]
+ *   spins_out bit-packed [R][L*L/32]  (final_state.spins)
+ *   summary [NQ_IS_NSUMMARY][R][T-1] float   (IsingSummary :33-40)
+ *   partials nullable [NQ_IS_NPARTIAL][R][T-1] float
+ *   counts  nullable [R][T-1][2][2][16] int32 : per half-sweep, [0]=active sites, [1]=flipped sites per class
+ *   states  nullable bit-packed [R][T-1][L*L/32]  (return_states=True :166-167)           */
+int nq_ising_run(const NqIsingDesc* desc /*host*/, const uint32_t* thr, const double* lut,
+                 const float* field, const float* log_temp,
+                 const uint32_t* spins0, const uint32_t* seeds,
+                 uint32_t* spins_out, float* summary, float* partials,
+                 int32_t* counts, uint32_t* states,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* random_spins(shape, p, seed) (ising.py:71-72) bit-packed: bit = uniform(seed)[i] < p */
+int nq_ising_random_spins(const uint32_t key[2] /*host*/, int32_t L, float p, uint32_t* out_bits,
+                          void* stream);
+/* pack / unpack between +-1 spins (int32 or float32 elements) and the bit-packed layout */
+int nq_ising_pack(const void* spins, int32_t is_float, int64_t n_sites, uint32_t* bits, void* stream);
+int nq_ising_unpack(const uint32_t* bits, int64_t n_sites, int32_t is_float, void* spins, void* stream);
+/* sum_neighbors / energy / magnetisation of bit-packed lattices: out[r] = {M, bond sum B} as int64[2] */
+int nq_ising_measure(const uint32_t* bits, int32_t L, int64_t R, int64_t* out_MB, void* stream);
+
+/* ------------------------------------------------------------------ calibration */
+/* issue-rate microbenchmark: runs `iters` dependent-chain iterations of
+ * instruction mix `which` on `blocks` x `threads`; elapsed SM cycles (max over blocks) -> host out.
+ * Used only by bench.py --calibrate and profiles/; not part of the hot path.               */
+int nq_microbench(int32_t which, int32_t blocks, int32_t threads, int32_t iters,
+                  uint64_t* out_cycles /*device [blocks]*/, uint32_t* sink /*device*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NONEQ_B200_H_ */

@@ -1,0 +1,100 @@
+// Issue-rate calibration for the instruction mixes the hot path is built from
+// ("first kernel PR must include a microbenchmark").  Not on the hot path.
+//
+// Each thread runs 8 independent dependency chains; one loop iteration issues kOps instructions
+// of the mix per chain-slot.  The host divides (threads * iters * ops_per_iter) by the elapsed SM
+// cycles to get thread-instructions / clk / SM for that mix.
+#include "nq_common.cuh"
+
+namespace nq {
+
+constexpr int kChains = 8;
+
+template <int WHICH>
+__device__ __forceinline__ void body(uint32_t (&a)[kChains], uint32_t (&b)[kChains], float (&f)[kChains]) {
+#pragma unroll
+  for (int c = 0; c < kChains; ++c) {
+    if (WHICH == 0) {  // LOP3 (alu)
+      asm volatile("xor.b32 %0, %0, %1;" : "+r"(a[c]) : "r"(b[c]));
+    } else if (WHICH == 1) {  // SHF (alu)
+      asm volatile("shf.l.wrap.b32 %0, %0, %0, 13;" : "+r"(a[c]));
+    } else if (WHICH == 2) {  // integer add (ptxas picks IADD3 or IMAD.IADD)
+      asm volatile("add.u32 %0, %0, %1;" : "+r"(a[c]) : "r"(b[c]));
+    } else if (WHICH == 3) {  // IMAD (fma pipe)
+      asm volatile("mad.lo.u32 %0, %0, %1, %1;" : "+r"(a[c]) : "r"(b[c]));
+    } else if (WHICH == 4) {  // FFMA
+      asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(f[c]) : "f"(__uint_as_float(b[c])));
+    } else if (WHICH == 5) {  // IMAD.WIDE
+      uint64_t w;
+      asm volatile("mul.wide.u32 %0, %1, 8192;" : "=l"(w) : "r"(a[c]));
+      a[c] = (uint32_t)w | (uint32_t)(w >> 32);
+    } else if (WHICH == 6) {  // one threefry round: add, rotate, xor
+      a[c] += b[c];
+      b[c] = rotl32(b[c], 13);
+      b[c] ^= a[c];
+    } else if (WHICH == 7) {  // MUFU.EX2
+      asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(f[c]));
+    } else if (WHICH == 8) {  // threefry round with the rotate done as IMAD.WIDE + LOP3
+      a[c] += b[c];
+      uint64_t w;
+      asm volatile("mul.wide.u32 %0, %1, 8192;" : "=l"(w) : "r"(b[c]));
+      b[c] = ((uint32_t)w | (uint32_t)(w >> 32)) ^ a[c];
+    } else if (WHICH == 9) {  // LOP3 + FFMA pair (dual-pipe issue)
+      asm volatile("xor.b32 %0, %0, %1;" : "+r"(a[c]) : "r"(b[c]));
+      asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(f[c]) : "f"(__uint_as_float(b[c])));
+    } else if (WHICH == 10) {  // LOP3 + IMAD pair
+      asm volatile("xor.b32 %0, %0, %1;" : "+r"(a[c]) : "r"(b[c]));
+      asm volatile("mad.lo.u32 %0, %0, %1, %1;" : "+r"(b[c]) : "r"(a[c]));
+    } else if (WHICH == 11) {  // full threefry2x32-20 block per chain (73 ops nominal)
+      uint32_t y0, y1;
+      threefry2x32(key_schedule(a[c], b[c]), a[c], b[c], y0, y1);
+      a[c] = y0;
+      b[c] = y1;
+    }
+  }
+}
+
+template <int WHICH>
+__global__ void microbench_kernel(int iters, unsigned long long* out_cycles, uint32_t* sink) {
+  uint32_t a[kChains], b[kChains];
+  float f[kChains];
+#pragma unroll
+  for (int c = 0; c < kChains; ++c) {
+    a[c] = threadIdx.x * 2654435761u + c;
+    b[c] = blockIdx.x * 40503u + c * 7u + 1u;
+    f[c] = 1.0f + 1e-3f * (float)((threadIdx.x + c) & 7);
+  }
+  __syncthreads();
+  const long long t0 = clock64();
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) body<WHICH>(a, b, f);
+  }
+  __syncthreads();
+  const long long t1 = clock64();
+  uint32_t acc = 0;
+#pragma unroll
+  for (int c = 0; c < kChains; ++c) acc ^= a[c] ^ b[c] ^ __float_as_uint(f[c]);
+  if (acc == 0x12345u) sink[0] = acc;
+  if (threadIdx.x == 0) out_cycles[blockIdx.x] = (unsigned long long)(t1 - t0);
+}
+
+}  // namespace nq
+
+using namespace nq;
+
+extern "C" int nq_microbench(int32_t which, int32_t blocks, int32_t threads, int32_t iters, uint64_t* out_cycles,
+                             uint32_t* sink, void* stream) {
+  NQ_CHECK_ARG(which >= 0 && which <= 11, "unknown microbenchmark %d", which);
+  NQ_CHECK_ARG(blocks >= 1 && threads >= 32 && threads <= 1024 && iters >= 1 && out_cycles && sink, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* oc = (unsigned long long*)out_cycles;
+#define NQ_MB(W) case W: microbench_kernel<W><<<blocks, threads, 0, st>>>(iters, oc, sink); break;
+  switch (which) {
+    NQ_MB(0) NQ_MB(1) NQ_MB(2) NQ_MB(3) NQ_MB(4) NQ_MB(5) NQ_MB(6) NQ_MB(7) NQ_MB(8) NQ_MB(9) NQ_MB(10) NQ_MB(11)
+  }
+#undef NQ_MB
+  NQ_LAUNCHED();
+  return NQ_OK;
+}
