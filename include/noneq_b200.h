@@ -158,7 +158,7 @@ int nq_langevin_apply(const NqLangevinDesc* desc /*host*/, float r0, float* x, u
 
 /* ------------------------------------------------------------------ Ising */
 #define NQ_ISING_NCLASS 10 /* (spin in {-1,+1}) x (neighbour sum in {-4,-2,0,2,4}) */
-/* class index c = 5*(s>0) + (nsum+4)/2 */
+/* class table slot = 8*(s>0) + (nsum+4)/2 ; slots 5-7 and 13-15 unused */
 
 /* per-(replica, sweep) float outputs, plane-major: out[f][r][t], t = 0..T-2 */
 #define NQ_IS_WORK 0
@@ -181,7 +181,8 @@ typedef struct NqIsingDesc {
   int32_t T;          /* time_steps; T-1 sweeps                      ising.py:153-173 */
   int64_t R;          /* replicas (rows of split(seed, batch_size),  ising.py:283)   */
   int32_t spins0_broadcast; /* 1: spins0 holds ONE lattice shared by all replicas    */
-  int32_t reserved;
+  int32_t sweep_key_mode;   /* 0: sweep t uses split(seed_r, T-1)[t-1] (simulate_ising :161);
+                               1: T must be 2 and the single sweep uses seed_r itself (update :132) */
 } NqIsingDesc;
 
 size_t nq_ising_words_per_lattice(int32_t L); /* = L*L/32 (bit b of word w = site 32*w+b, row-major; 1 = spin +1) */
@@ -193,7 +194,8 @@ size_t nq_ising_workspace_bytes(const NqIsingDesc* desc);
  * full-lattice uniform draw of distrax.Bernoulli reproduced counter-for-counter.
  *   thr     [T-1][16] uint32 : acceptance thresholds ceil(sigmoid(logit_c) * 2^23) per class
  *                              (entries >= NQ_ISING_NCLASS unused); flip iff (bits>>9) < thr
- *   lut     [T-1][4][16] double : per class  logit, log_sigmoid(-logit), sigmoid(logit), spare
+ *   lut     [T-1][4][16] double : per class  logit, log_sigmoid(-logit), log_sigmoid(logit) (the
+ *                              float32 values of the reference's arithmetic) and sigmoid(logit) (binary64)
  *   field, log_temp [T] float : the schedule tables (IsingParameters :14-16)
  *   spins0  bit-packed [R or 1][L*L/32];  seeds [R][2]
  *   spins_out bit-packed [R][L*L/32]  (final_state.spins)

@@ -29,7 +29,7 @@ class NqLangevinDesc(C.Structure):
 
 class NqIsingDesc(C.Structure):
   _fields_ = [('L', C.c_int32), ('T', C.c_int32), ('R', C.c_int64),
-              ('spins0_broadcast', C.c_int32), ('reserved', C.c_int32)]
+              ('spins0_broadcast', C.c_int32), ('sweep_key_mode', C.c_int32)]
 
 
 _P = C.c_void_p

@@ -1,0 +1,691 @@
+// Checkerboard Glauber sweeps of the 2-D periodic Ising model under a time-varying field and
+// temperature, with trajectory log-probabilities and their parameter derivatives (sm_100a).
+//
+// Replaces the XLA computation traced from the reference's
+//   masked_update / update / simulate_ising   noneq_opt/ising.py:109-173
+//   (sum_neighbors :75-83, energy :85-86, flip_logits :93-96, even_odd_masks :99-106)
+// and provides the per-sweep sufficient statistics from which IsingSummary (:33-40) and the
+// gradient estimators (:179-236, 294-599) are assembled.
+//
+// Design
+//   * the lattice is bit-packed (1 = spin +1) and lives in SHARED MEMORY for the whole
+//     trajectory, stored checkerboard-compressed: plane c holds the sites updated in
+//     half-sweep c (c = 0: (i+j) odd -- the reference's "even" mask; c = 1: (i+j) even), so
+//     a 32-bit word is 32 simultaneously-updatable sites and all four neighbours of a word
+//     are whole words of the other plane (one of them funnel-shifted by one site);
+//   * uniforms are jax's: site (i,j) of a half-sweep consumes counter i*L+j of
+//     threefry_2x32(half_key, iota(L*L)), whose counter pairing (p, p+L*L/2) makes ONE
+//     threefry block serve site (i,j) and site (i+L/2,j) -- same colour when L % 4 == 0 --
+//     so the half of the draw the reference discards is never generated;
+//   * acceptance is an integer compare (bits>>9) < thr[class] against a per-sweep table of
+//     ceil(sigmoid(logit)*2^23) for the 2x5 (spin, #up-neighbours) classes, so spin histories
+//     do not depend on device transcendentals;
+//   * neighbour counts are bit-sliced (full adders on 32 sites at a time); per-class counts of
+//     active and flipped sites come from popc and are reduced with redux.sync; every float
+//     summary is a fixed linear form of those integer counts, evaluated in binary64.
+#include <math.h>
+
+#include "nq_common.cuh"
+
+namespace nq {
+
+constexpr int kIsingClasses = 16;  // class = 8*(spin up) + (#up neighbours 0..4)
+
+// ------------------------------------------------------------------------------ bit helpers
+__host__ __device__ __forceinline__ uint32_t compact_even_bits(uint32_t x) {
+  x &= 0x55555555u;
+  x = (x | (x >> 1)) & 0x33333333u;
+  x = (x | (x >> 2)) & 0x0f0f0f0fu;
+  x = (x | (x >> 4)) & 0x00ff00ffu;
+  x = (x | (x >> 8)) & 0x0000ffffu;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t spread_to_even_bits(uint32_t x) {
+  x &= 0x0000ffffu;
+  x = (x | (x << 8)) & 0x00ff00ffu;
+  x = (x | (x << 4)) & 0x0f0f0f0fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  x = (x | (x << 1)) & 0x55555555u;
+  return x;
+}
+// 8 bits -> 8 nibbles (bit k -> bit 4k)
+__host__ __device__ __forceinline__ uint32_t spread8_to_nibbles(uint32_t v) {
+  v &= 0xffu;
+  v = (v | (v << 12)) & 0x000f000fu;
+  v = (v | (v << 6)) & 0x03030303u;
+  v = (v | (v << 3)) & 0x11111111u;
+  return v;
+}
+
+// row-major external word pair (sites 64w..64w+63 of row i) <-> the two colour planes
+__device__ __forceinline__ void split_colours(int row, uint32_t lo, uint32_t hi, uint32_t& c0, uint32_t& c1) {
+  const uint32_t even = compact_even_bits(lo) | (compact_even_bits(hi) << 16);
+  const uint32_t odd = compact_even_bits(lo >> 1) | (compact_even_bits(hi >> 1) << 16);
+  // colour 0 = (i+j) odd: odd j on even rows, even j on odd rows
+  c0 = (row & 1) ? even : odd;
+  c1 = (row & 1) ? odd : even;
+}
+__device__ __forceinline__ void merge_colours(int row, uint32_t c0, uint32_t c1, uint32_t& lo, uint32_t& hi) {
+  const uint32_t even = (row & 1) ? c0 : c1, odd = (row & 1) ? c1 : c0;
+  lo = spread_to_even_bits(even) | (spread_to_even_bits(odd) << 1);
+  hi = spread_to_even_bits(even >> 16) | (spread_to_even_bits(odd >> 16) << 1);
+}
+
+struct Planes {
+  uint32_t S, C0, C1, C2;
+};
+
+// number of up neighbours of 32 sites at once: 4 words -> 3 bit planes
+__device__ __forceinline__ void count_planes(uint32_t a, uint32_t b, uint32_t c, uint32_t d, Planes& p) {
+  const uint32_t s1 = a ^ b, k1 = a & b, s2 = c ^ d, k2 = c & d;
+  p.C0 = s1 ^ s2;
+  const uint32_t t = s1 & s2;
+  p.C1 = k1 ^ k2 ^ t;
+  p.C2 = (k1 & k2) | (t & (k1 ^ k2));
+}
+
+struct IsingShape {
+  int L, NW, T;     // NW = L/64 words per row per colour
+  long long R;
+  int broadcast0;
+  int direct_keys;
+};
+
+struct IsingIO {
+  const uint32_t* thr;    // [T-1][16]
+  const double* lut;      // [T-1][4][16]: logit, log_sigmoid(-logit), log_sigmoid(logit), sigmoid(logit)
+  const float* field;     // [T]
+  const float* log_temp;  // [T]
+  const uint32_t* spins0;
+  const uint32_t* seeds;  // [R][2]
+  uint32_t* spins_out;
+  float* summary;         // [7][R][T-1]
+  float* partials;        // [4][R][T-1] or null
+  int32_t* counts;        // [R][T-1][2][2][16] or null
+  uint32_t* states;       // [R][T-1][L*L/32] or null
+};
+
+// neighbour planes of word w of row r of colour c (reads the OTHER colour plane)
+__device__ __forceinline__ void load_planes(const uint32_t* lat, const IsingShape& sh, int c, int r, int w, Planes& p) {
+  const int L = sh.L, NW = sh.NW;
+  const uint32_t* own = lat + (size_t)c * L * NW;
+  const uint32_t* oth = lat + (size_t)(1 - c) * L * NW;
+  const int ru = r == 0 ? L - 1 : r - 1, rd = r == L - 1 ? 0 : r + 1;
+  const uint32_t up = oth[ru * NW + w], dn = oth[rd * NW + w], X = oth[r * NW + w];
+  uint32_t Xs;
+  if (((r & 1) == 0) == (c == 0)) {  // second in-row neighbour is site k+1
+    const uint32_t Xn = oth[r * NW + (w + 1 == NW ? 0 : w + 1)];
+    Xs = __funnelshift_r(X, Xn, 1);
+  } else {  // site k-1
+    const uint32_t Xp = oth[r * NW + (w == 0 ? NW - 1 : w - 1)];
+    Xs = __funnelshift_l(Xp, X, 1);
+  }
+  p.S = own[r * NW + w];
+  count_planes(up, dn, X, Xs, p);
+}
+
+// 8 sites -> nibble word of class indices (8*s + cnt), via the pre-shifted spread tables
+__device__ __forceinline__ uint32_t class_nibbles(const uint32_t* spread, const Planes& p, int q) {
+  const int sh = 8 * q;
+  return spread[3 * 256 + ((p.S >> sh) & 0xff)] | spread[2 * 256 + ((p.C2 >> sh) & 0xff)] |
+         spread[1 * 256 + ((p.C1 >> sh) & 0xff)] | spread[((p.C0 >> sh) & 0xff)];
+}
+
+__device__ __forceinline__ uint32_t thr_of(const uint32_t* thr_s, uint32_t packed4, int byte) {
+  const uint32_t off = __byte_perm(packed4, 0, 0x4440 | byte);  // 4*class, zero-extended
+  return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(thr_s) + off);
+}
+
+// per-class popcounts of active and flipped sites of one word
+__device__ __forceinline__ void histogram(const Planes& p, uint32_t F, int (&hA)[10], int (&hF)[10]) {
+  const uint32_t E[5] = {~(p.C2 | p.C1 | p.C0), ~p.C2 & ~p.C1 & p.C0, p.C1 & ~p.C0, p.C1 & p.C0, p.C2};
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const uint32_t up = E[k] & p.S, down = E[k] & ~p.S;
+    hA[k] += __popc(down);
+    hA[5 + k] += __popc(up);
+    hF[k] += __popc(down & F);
+    hF[5 + k] += __popc(up & F);
+  }
+}
+
+// One unit = word w of rows i and i+L/2 of colour c: 32 threefry blocks, 64 site updates.
+__device__ __forceinline__ void update_unit(uint32_t* lat, const IsingShape& sh, const uint32_t* spread,
+                                            const uint32_t* thr_s, const KeySchedule& ks, int c, int i, int w,
+                                            int (&hA)[10], int (&hF)[10]) {
+  const int L = sh.L, NW = sh.NW, i2 = i + L / 2;
+  Planes pa, pb;
+  load_planes(lat, sh, c, i, w, pa);
+  load_planes(lat, sh, c, i2, w, pb);
+  const int off = c == 0 ? 1 - (i & 1) : (i & 1);
+  const uint32_t cbase = (uint32_t)i * L + 2u * (32u * w) + off;
+  const uint32_t half = (uint32_t)L * L / 2;
+  uint32_t Fa = 0, Fb = 0;
+#pragma unroll 1
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t Na = class_nibbles(spread, pa, q), Nb = class_nibbles(spread, pb, q);
+    const uint32_t ea = (Na << 2) & 0x3C3C3C3Cu, oa = (Na >> 2) & 0x3C3C3C3Cu;
+    const uint32_t eb = (Nb << 2) & 0x3C3C3C3Cu, ob = (Nb >> 2) & 0x3C3C3C3Cu;
+    uint32_t fa = 0, fb = 0;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      const uint32_t ctr = cbase + 2u * (8u * q + s);
+      uint32_t y0, y1;
+      threefry2x32(ks, ctr, ctr + half, y0, y1);
+      const uint32_t ta = thr_of(thr_s, (s & 1) ? oa : ea, s >> 1);
+      const uint32_t tb = thr_of(thr_s, (s & 1) ? ob : eb, s >> 1);
+      fa |= ((y0 >> 9) < ta) ? (1u << s) : 0u;
+      fb |= ((y1 >> 9) < tb) ? (1u << s) : 0u;
+    }
+    Fa |= fa << (8 * q);
+    Fb |= fb << (8 * q);
+  }
+  uint32_t* own = lat + (size_t)c * L * NW;
+  own[i * NW + w] = pa.S ^ Fa;
+  own[i2 * NW + w] = pb.S ^ Fb;
+  histogram(pa, Fa, hA, hF);
+  histogram(pb, Fb, hA, hF);
+}
+
+// ------------------------------------------------------------------------------ summaries
+// class c10 in [0,10): spin = c10 >= 5 ? +1 : -1, #up-neighbours = c10 % 5; table slot = 8*(c10>=5) + c10%5
+__device__ __forceinline__ int slot_of(int c10) { return c10 >= 5 ? 8 + (c10 - 5) : c10; }
+
+// Integer sufficient statistics of one sweep -> the float outputs.  Executed by one full warp;
+// lane c < 10 owns class c and holds A[h], F[h] (active / flipped counts of its class in
+// half-sweep h).  M, B: spin sum and bond sum BEFORE the sweep; updated to AFTER.
+__device__ __forceinline__ void emit_summary(const int (&A)[2], const int (&F)[2], const IsingIO& io,
+                                             const IsingShape& sh, long long rep, int t, long long& M,
+                                             long long& B, int lane) {
+  const bool on = lane < 10;
+  const int c10 = on ? lane : 0;
+  const int slot = slot_of(c10);
+  const double* lut = io.lut + (size_t)(t - 1) * 4 * kIsingClasses;
+  const double ell = lut[slot], lsn = lut[kIsingClasses + slot], lsp = lut[2 * kIsingClasses + slot],
+               sig = lut[3 * kIsingClasses + slot];
+  const int s = c10 >= 5 ? 1 : -1;
+  const int nsum = 2 * (c10 % 5) - 4;
+  double fwd[2], rev[2], lF = 0.0, sAs = 0.0, lAs = 0.0;
+  int dM = 0, dB = 0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const double a = on ? (double)A[h] : 0.0, f = on ? (double)F[h] : 0.0;
+    fwd[h] = warp_sum((a - f) * lsn + f * lsp);  // sum_active (1-flip) log_sigmoid(-l) + flip log_sigmoid(l)
+    rev[h] = warp_sum(a * lsn);                  // reverse logits: -l on flipped sites, l elsewhere
+    lF += f * ell;
+    sAs += s * a * sig;
+    lAs += ell * a * sig;
+    if (on) {
+      dM += -2 * s * F[h];
+      dB += -2 * s * nsum * F[h];
+    }
+  }
+  lF = warp_sum(lF);
+  sAs = warp_sum(sAs);
+  lAs = warp_sum(lAs);
+  dM = __reduce_add_sync(0xffffffffu, dM);
+  dB = __reduce_add_sync(0xffffffffu, dB);
+
+  const double h_old = (double)io.field[t - 1], h_new = (double)io.field[t];
+  const double Md = (double)M, Bd = (double)B;
+  const long long M2 = M + dM, B2 = B + dB;
+  // energy(state) = -(B + h M)   (ising.py:85-86); f32 scalars are subtracted in f32 as in update() :143-144
+  const float e_init = (float)(-(Bd + h_old * Md));
+  const float e_mid = (float)(-(Bd + h_new * Md));
+  const float e_fin = (float)(-((double)B2 + h_new * (double)M2));
+  const float fwd32 = __fadd_rn((float)fwd[0], (float)fwd[1]);
+  const float rev32 = __fadd_rn((float)rev[0], (float)rev[1]);
+  const size_t RT = (size_t)sh.R * (sh.T - 1);
+  const size_t o = (size_t)rep * (sh.T - 1) + (t - 1);
+  float v = 0.f;
+  switch (lane) {
+    case NQ_IS_WORK: v = __fsub_rn(e_mid, e_init); break;
+    case NQ_IS_HEAT: v = __fsub_rn(e_mid, e_fin); break;
+    case NQ_IS_FWD: v = fwd32; break;
+    case NQ_IS_REV: v = rev32; break;
+    case NQ_IS_EP: v = __fsub_rn(fwd32, rev32); break;
+    case NQ_IS_MAG: v = (float)((double)M2 / ((double)sh.L * sh.L)); break;
+    case NQ_IS_ENERGY: v = e_fin; break;
+    default: break;
+  }
+  if (lane < NQ_IS_NSUMMARY) io.summary[lane * RT + o] = v;
+  if (io.partials && lane >= 8 && lane < 8 + NQ_IS_NPARTIAL) {
+    const double einv = exp(-(double)io.log_temp[t]);
+    const double sF = -0.5 * (double)dM;  // sum over flipped sites of s
+    double pv;
+    switch (lane - 8) {
+      case NQ_IS_DFWD_DH: pv = -2.0 * einv * (sF - sAs); break;
+      case NQ_IS_DFWD_DL: pv = -(lF - lAs); break;
+      case NQ_IS_DREV_DH: pv = 2.0 * einv * sAs; break;
+      default: pv = lAs; break;
+    }
+    io.partials[(lane - 8) * RT + o] = (float)pv;
+  }
+  if (io.counts && on) {
+    int32_t* cnt = io.counts + o * (2 * 2 * kIsingClasses);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      cnt[(h * 2 + 0) * kIsingClasses + slot] = A[h];
+      cnt[(h * 2 + 1) * kIsingClasses + slot] = F[h];
+    }
+  }
+  M = M2;
+  B = B2;
+}
+
+// per-sweep half keys: seed_t = split(seed_r, T-1)[t-1]; (seed_even, seed_odd) = split(seed_t, 2)
+__device__ __forceinline__ void sweep_keys(const KeySchedule& ks_rep, int t, int T, bool direct,
+                                           KeySchedule& k_first, KeySchedule& k_second) {
+  const uint64_t size = 2ull * (T - 1);
+  uint32_t s0 = ks_rep.ks0, s1 = ks_rep.ks1;
+  if (!direct) {
+    s0 = random_bits_at(ks_rep, 2ull * (t - 1), size);
+    s1 = random_bits_at(ks_rep, 2ull * (t - 1) + 1, size);
+  }
+  uint32_t e0, e1, o0, o1;
+  split2(s0, s1, e0, e1, o0, o1);
+  k_first = key_schedule(e0, e1);   // "even" mask = odd-parity sites, updated first  (ising.py:132-136)
+  k_second = key_schedule(o0, o1);
+}
+
+// ------------------------------------------------------------------------------ fast kernel
+// Shared memory: spread[4][256] | per team: lattice[2][L][NW], thr[2][16] | (CTA team) hist[2][2][2][16]
+template <bool WARP_TEAM>
+__global__ void __launch_bounds__(WARP_TEAM ? 128 : 1024) ising_fast_kernel(const IsingShape sh, const IsingIO io) {
+  extern __shared__ uint32_t smem[];
+  uint32_t* spread = smem;
+  const int L = sh.L, NW = sh.NW, T = sh.T;
+  const int lat_words = 2 * L * NW;
+  const int team_words = lat_words + 2 * kIsingClasses;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int team = WARP_TEAM ? warp : 0;
+  const int tid = WARP_TEAM ? lane : threadIdx.x;          // index within the team
+  const int tsize = WARP_TEAM ? 32 : blockDim.x;
+  const int nteams = WARP_TEAM ? blockDim.x / 32 : 1;
+  uint32_t* lat = smem + 4 * 256 + team * team_words;
+  uint32_t* thr_s = lat + lat_words;
+  int* hist_s = reinterpret_cast<int*>(smem + 4 * 256 + nteams * team_words);  // CTA team only
+
+  for (int v = threadIdx.x; v < 4 * 256; v += blockDim.x) spread[v] = spread8_to_nibbles(v & 255) << (v >> 8);
+  if (!WARP_TEAM)
+    for (int v = threadIdx.x; v < 2 * 2 * 2 * kIsingClasses; v += blockDim.x) hist_s[v] = 0;
+  __syncthreads();
+  const long long rep = (long long)blockIdx.x * nteams + team;
+  if (rep >= sh.R) return;  // whole team leaves together (warp-uniform / CTA-uniform)
+  auto team_sync = [&]() {
+    if (WARP_TEAM) __syncwarp(); else __syncthreads();
+  };
+
+  // ---- load the lattice (row-major bits -> colour planes)
+  const size_t ext_words = (size_t)L * L / 32;
+  const uint32_t* ext0 = io.spins0 + (sh.broadcast0 ? 0 : rep * ext_words);
+  for (int u = tid; u < L * NW; u += tsize) {
+    const int r = u / NW, w = u - r * NW;
+    uint32_t c0, c1;
+    split_colours(r, ext0[r * (L / 32) + 2 * w], ext0[r * (L / 32) + 2 * w + 1], c0, c1);
+    lat[u] = c0;
+    lat[L * NW + u] = c1;
+  }
+  if (tid < kIsingClasses && T > 1) thr_s[kIsingClasses + tid] = io.thr[tid];  // sweep 1 -> buffer 1
+  team_sync();
+
+  // ---- initial spin sum M and bond sum B (each bond joins a colour-0 and a colour-1 site)
+  long long M, B;
+  {
+    int hA[10], hF[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) hA[k] = hF[k] = 0;
+    int up = 0;
+    for (int u = tid; u < L * NW; u += tsize) {
+      const int r = u / NW, w = u - r * NW;
+      Planes p;
+      load_planes(lat, sh, 0, r, w, p);
+      histogram(p, 0u, hA, hF);
+      up += __popc(lat[u]) + __popc(lat[L * NW + u]);
+    }
+    int b = 0;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) b += (k >= 5 ? 1 : -1) * (2 * (k % 5) - 4) * hA[k];
+    up = __reduce_add_sync(0xffffffffu, up);
+    b = __reduce_add_sync(0xffffffffu, b);
+    if (!WARP_TEAM) {
+      int* tmp = hist_s + 2 * 2 * 2 * kIsingClasses;  // 2 scratch ints
+      if (threadIdx.x < 2) tmp[threadIdx.x] = 0;
+      __syncthreads();
+      if (lane == 0) { atomicAdd(&tmp[0], up); atomicAdd(&tmp[1], b); }
+      __syncthreads();
+      up = tmp[0];
+      b = tmp[1];
+    }
+    M = 2ll * up - (long long)L * L;
+    B = b;
+  }
+
+  const KeySchedule ks_rep = key_schedule(io.seeds[2 * rep], io.seeds[2 * rep + 1]);
+  const int units = (L / 2) * NW;
+  for (int t = 1; t < T; ++t) {
+    KeySchedule kh[2];
+    sweep_keys(ks_rep, t, T, sh.direct_keys != 0, kh[0], kh[1]);
+    const uint32_t* thr_cur = thr_s + (t & 1) * kIsingClasses;
+    if (tid < kIsingClasses && t + 1 < T) thr_s[((t + 1) & 1) * kIsingClasses + tid] = io.thr[(size_t)t * kIsingClasses + tid];
+    int At[2][10], Ft[2][10];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      int hA[10], hF[10];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) hA[k] = hF[k] = 0;
+      for (int u = tid; u < units; u += tsize) {
+        const int i = u / NW, w = u - i * NW;
+        update_unit(lat, sh, spread, thr_cur, kh[c], c, i, w, hA, hF);
+      }
+#pragma unroll
+      for (int k = 0; k < 10; ++k) {
+        At[c][k] = __reduce_add_sync(0xffffffffu, hA[k]);
+        Ft[c][k] = __reduce_add_sync(0xffffffffu, hF[k]);
+      }
+      if (!WARP_TEAM && lane == 0) {
+        int* hs = hist_s + ((t & 1) * 2 + c) * 2 * kIsingClasses;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+          if (At[c][k]) atomicAdd(&hs[k], At[c][k]);
+          if (Ft[c][k]) atomicAdd(&hs[kIsingClasses + k], Ft[c][k]);
+        }
+      }
+      team_sync();
+    }
+    if (io.states) {  // return_states=True: the lattice after this sweep, row-major bits
+      uint32_t* dst = io.states + ((size_t)rep * (T - 1) + (t - 1)) * ext_words;
+      for (int u = tid; u < L * NW; u += tsize) {
+        const int r = u / NW, w = u - r * NW;
+        uint32_t lo, hi;
+        merge_colours(r, lat[u], lat[L * NW + u], lo, hi);
+        dst[r * (L / 32) + 2 * w] = lo;
+        dst[r * (L / 32) + 2 * w + 1] = hi;
+      }
+      if (!WARP_TEAM) __syncthreads();  // the next sweep rewrites the lattice
+    }
+    if (WARP_TEAM || warp == 0) {
+      int a2[2], f2[2];
+      if (WARP_TEAM) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          a2[c] = f2[c] = 0;
+#pragma unroll
+          for (int k = 0; k < 10; ++k)
+            if (lane == k) { a2[c] = At[c][k]; f2[c] = Ft[c][k]; }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          int* hs = hist_s + ((t & 1) * 2 + c) * 2 * kIsingClasses;
+          a2[c] = lane < 10 ? hs[lane] : 0;
+          f2[c] = lane < 10 ? hs[kIsingClasses + lane] : 0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          int* hs = hist_s + ((t & 1) * 2 + c) * 2 * kIsingClasses;
+          if (lane < 10) { hs[lane] = 0; hs[kIsingClasses + lane] = 0; }
+        }
+      }
+      emit_summary(a2, f2, io, sh, rep, t, M, B, lane);
+    }
+  }
+  team_sync();
+  if (io.spins_out) {
+    uint32_t* dst = io.spins_out + (size_t)rep * ext_words;
+    for (int u = tid; u < L * NW; u += tsize) {
+      const int r = u / NW, w = u - r * NW;
+      uint32_t lo, hi;
+      merge_colours(r, lat[u], lat[L * NW + u], lo, hi);
+      dst[r * (L / 32) + 2 * w] = lo;
+      dst[r * (L / 32) + 2 * w + 1] = hi;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ generic kernel
+// Any even L: one CTA per replica, one spin per byte in shared memory, one threefry block per
+// updated site (the (p, p+L*L/2) partner may have the other colour when L/2 is odd).
+__global__ void __launch_bounds__(256) ising_generic_kernel(const IsingShape sh, const IsingIO io) {
+  extern __shared__ uint32_t smem[];
+  int* hist_s = reinterpret_cast<int*>(smem);               // [2][2][16]
+  int* scratch = hist_s + 2 * 2 * kIsingClasses;            // [2]
+  uint32_t* thr_s = reinterpret_cast<uint32_t*>(scratch + 2);  // [16]
+  signed char* sp = reinterpret_cast<signed char*>(thr_s + kIsingClasses);
+  const int L = sh.L, T = sh.T, N = L * L;
+  const long long rep = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t ext_words = ((size_t)N + 31) / 32;
+  const uint32_t* ext0 = io.spins0 + (sh.broadcast0 ? 0 : rep * ext_words);
+  for (int p = threadIdx.x; p < N; p += blockDim.x) sp[p] = ((ext0[p >> 5] >> (p & 31)) & 1u) ? 1 : -1;
+  if (threadIdx.x < 2) scratch[threadIdx.x] = 0;
+  __syncthreads();
+  auto nsum_at = [&](int i, int j) {
+    const int iu = i == 0 ? L - 1 : i - 1, id = i == L - 1 ? 0 : i + 1;
+    const int jl = j == 0 ? L - 1 : j - 1, jr = j == L - 1 ? 0 : j + 1;
+    return (int)sp[iu * L + j] + sp[id * L + j] + sp[i * L + jl] + sp[i * L + jr];
+  };
+  {
+    int m = 0, b = 0;
+    for (int p = threadIdx.x; p < N; p += blockDim.x) {
+      const int i = p / L, j = p - i * L;
+      m += sp[p];
+      if ((i + j) & 1) b += sp[p] * nsum_at(i, j);
+    }
+    m = __reduce_add_sync(0xffffffffu, m);
+    b = __reduce_add_sync(0xffffffffu, b);
+    if (lane == 0) { atomicAdd(&scratch[0], m); atomicAdd(&scratch[1], b); }
+  }
+  __syncthreads();
+  long long M = scratch[0], B = scratch[1];
+  const KeySchedule ks_rep = key_schedule(io.seeds[2 * rep], io.seeds[2 * rep + 1]);
+  for (int t = 1; t < T; ++t) {
+    KeySchedule kh[2];
+    sweep_keys(ks_rep, t, T, sh.direct_keys != 0, kh[0], kh[1]);
+    if (threadIdx.x < kIsingClasses) thr_s[threadIdx.x] = io.thr[(size_t)(t - 1) * kIsingClasses + threadIdx.x];
+    for (int v = threadIdx.x; v < 2 * 2 * kIsingClasses; v += blockDim.x) hist_s[v] = 0;
+    __syncthreads();
+    for (int c = 0; c < 2; ++c) {
+      const int want = c == 0 ? 1 : 0;  // parity of i+j updated in this half-sweep
+      for (int p = threadIdx.x; p < N; p += blockDim.x) {
+        const int i = p / L, j = p - i * L;
+        if (((i + j) & 1) != want) continue;
+        const int s = sp[p];
+        const int slot = (s > 0 ? 8 : 0) + (nsum_at(i, j) + 4) / 2;
+        const uint32_t bits = random_bits_at(kh[c], (uint64_t)p, (uint64_t)N);
+        const bool flip = (bits >> 9) < thr_s[slot];
+        atomicAdd(&hist_s[(c * 2 + 0) * kIsingClasses + slot], 1);
+        if (flip) {
+          atomicAdd(&hist_s[(c * 2 + 1) * kIsingClasses + slot], 1);
+          sp[p] = (signed char)(-s);
+        }
+      }
+      __syncthreads();
+    }
+    if (io.states) {
+      uint32_t* dst = io.states + ((size_t)rep * (T - 1) + (t - 1)) * ext_words;
+      for (int w = threadIdx.x; w < (int)ext_words; w += blockDim.x) {
+        uint32_t word = 0;
+        for (int b = 0; b < 32 && 32 * w + b < N; ++b) word |= (sp[32 * w + b] > 0 ? 1u : 0u) << b;
+        dst[w] = word;
+      }
+    }
+    if (warp == 0) {
+      int a2[2], f2[2];
+      for (int c = 0; c < 2; ++c) {
+        const int slot = slot_of(lane < 10 ? lane : 0);
+        a2[c] = lane < 10 ? hist_s[(c * 2 + 0) * kIsingClasses + slot] : 0;
+        f2[c] = lane < 10 ? hist_s[(c * 2 + 1) * kIsingClasses + slot] : 0;
+      }
+      emit_summary(a2, f2, io, sh, rep, t, M, B, lane);
+    }
+    __syncthreads();
+  }
+  if (io.spins_out) {
+    uint32_t* dst = io.spins_out + (size_t)rep * ext_words;
+    for (int w = threadIdx.x; w < (int)ext_words; w += blockDim.x) {
+      uint32_t word = 0;
+      for (int b = 0; b < 32 && 32 * w + b < N; ++b) word |= (sp[32 * w + b] > 0 ? 1u : 0u) << b;
+      dst[w] = word;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ utilities
+template <typename T>
+__global__ void pack_kernel(const T* spins, long long n_sites, uint32_t* bits) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w * 32 >= n_sites) return;
+  uint32_t word = 0;
+  for (int b = 0; b < 32 && w * 32 + b < n_sites; ++b) word |= (spins[w * 32 + b] > (T)0 ? 1u : 0u) << b;
+  bits[w] = word;
+}
+
+template <typename T>
+__global__ void unpack_kernel(const uint32_t* bits, long long n_sites, T* spins) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_sites) return;
+  spins[p] = ((bits[p >> 5] >> (p & 31)) & 1u) ? (T)1 : (T)-1;
+}
+
+// random_spins: 2 * (uniform(seed, (L*L,)) < p) - 1    (ising.py:71-72)
+__global__ void random_spins_kernel(uint32_t k0, uint32_t k1, long long n_sites, uint32_t thr, uint32_t* bits) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w * 32 >= n_sites) return;
+  const KeySchedule ks = key_schedule(k0, k1);
+  uint32_t word = 0;
+  for (int b = 0; b < 32 && w * 32 + b < n_sites; ++b)
+    word |= ((random_bits_at(ks, (uint64_t)(w * 32 + b), (uint64_t)n_sites) >> 9) < thr ? 1u : 0u) << b;
+  bits[w] = word;
+}
+
+// out[r] = {sum of spins, sum over bonds of s_i s_j}
+__global__ void measure_kernel(const uint32_t* bits, int L, long long R, long long* out) {
+  const long long rep = blockIdx.x;
+  const size_t ext_words = ((size_t)L * L + 31) / 32;
+  const uint32_t* x = bits + rep * ext_words;
+  auto spin = [&](int i, int j) { const int p = i * L + j; return ((x[p >> 5] >> (p & 31)) & 1u) ? 1 : -1; };
+  long long m = 0, b = 0;
+  for (int p = threadIdx.x; p < L * L; p += blockDim.x) {
+    const int i = p / L, j = p - i * L;
+    const int s = spin(i, j);
+    m += s;
+    b += s * (spin(i, j == L - 1 ? 0 : j + 1) + spin(i == L - 1 ? 0 : i + 1, j));
+  }
+  __shared__ long long acc[2];
+  if (threadIdx.x < 2) acc[threadIdx.x] = 0;
+  __syncthreads();
+  atomicAdd((unsigned long long*)&acc[0], (unsigned long long)m);
+  atomicAdd((unsigned long long*)&acc[1], (unsigned long long)b);
+  __syncthreads();
+  if (threadIdx.x < 2) out[2 * rep + threadIdx.x] = acc[threadIdx.x];
+}
+
+static bool fast_path(int L) { return L % 64 == 0; }
+static size_t fast_smem_bytes(int L, bool warp_team, int nteams) {
+  const size_t lat_words = 2 * (size_t)L * (L / 64);
+  size_t words = 4 * 256 + nteams * (lat_words + 2 * kIsingClasses);
+  if (!warp_team) words += 2 * 2 * 2 * kIsingClasses + 2;
+  return words * 4;
+}
+static size_t generic_smem_bytes(int L) {
+  return (2 * 2 * kIsingClasses + 2 + kIsingClasses) * 4 + (((size_t)L * L + 3) / 4) * 4;
+}
+
+}  // namespace nq
+
+using namespace nq;
+
+extern "C" size_t nq_ising_words_per_lattice(int32_t L) { return ((size_t)L * L + 31) / 32; }
+extern "C" size_t nq_ising_workspace_bytes(const NqIsingDesc*) { return 0; }
+
+extern "C" int nq_ising_run(const NqIsingDesc* desc, const uint32_t* thr, const double* lut, const float* field,
+                            const float* log_temp, const uint32_t* spins0, const uint32_t* seeds,
+                            uint32_t* spins_out, float* summary, float* partials, int32_t* counts, uint32_t* states,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  (void)workspace;
+  (void)workspace_bytes;
+  NQ_CHECK_ARG(desc != nullptr, "desc is null");
+  const int L = desc->L, T = desc->T;
+  if (L <= 0 || (L & 1)) {
+    set_error("All entries in `shape` must be even; got (%d, %d).", L, L);  // ising.py:101-103
+    return NQ_ERR_INVALID_ARGUMENT;
+  }
+  NQ_CHECK_ARG(T >= 1 && desc->R >= 1, "need T >= 1 and R >= 1 (got T=%d R=%lld)", T, (long long)desc->R);
+  NQ_CHECK_ARG(thr && lut && field && log_temp && spins0 && seeds && summary, "null required pointer");
+  NQ_CHECK_ARG((long long)L * L <= 0x7fffffffll, "lattice too large");
+  NQ_CHECK_ARG(desc->sweep_key_mode == 0 || (desc->sweep_key_mode == 1 && T == 2), "sweep_key_mode 1 needs T == 2");
+  IsingShape sh{L, L / 64, T, desc->R, desc->spins0_broadcast, desc->sweep_key_mode};
+  IsingIO io{thr, lut, field, log_temp, spins0, seeds, spins_out, summary, partials, counts, states};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (fast_path(L)) {
+    const bool warp_team = L <= 128;
+    const int nteams = warp_team ? 4 : 1;
+    const int units = (L / 2) * (L / 64);
+    const int threads = warp_team ? 32 * nteams : (units >= 1024 ? 1024 : ((units + 31) / 32) * 32);
+    const size_t smem = fast_smem_bytes(L, warp_team, nteams);
+    if (smem > 227 * 1024) {
+      set_error("L=%d needs %zu bytes of shared memory per replica (> 227 KB); the streamed large-lattice path is not built", L, smem);
+      return NQ_ERR_UNSUPPORTED;
+    }
+    const unsigned blocks = (unsigned)((desc->R + nteams - 1) / nteams);
+    if (warp_team) {
+      NQ_CUDA(cudaFuncSetAttribute(ising_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ising_fast_kernel<true><<<blocks, threads, smem, st>>>(sh, io);
+    } else {
+      NQ_CUDA(cudaFuncSetAttribute(ising_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ising_fast_kernel<false><<<blocks, threads, smem, st>>>(sh, io);
+    }
+  } else {
+    const size_t smem = generic_smem_bytes(L);
+    if (smem > 227 * 1024) {
+      set_error("generic path: L=%d does not fit shared memory; use a multiple of 64", L);
+      return NQ_ERR_UNSUPPORTED;
+    }
+    NQ_CUDA(cudaFuncSetAttribute(ising_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ising_generic_kernel<<<(unsigned)desc->R, 256, smem, st>>>(sh, io);
+  }
+  NQ_LAUNCHED();
+  return NQ_OK;
+}
+
+extern "C" int nq_ising_random_spins(const uint32_t key[2], int32_t L, float p, uint32_t* out_bits, void* stream) {
+  NQ_CHECK_ARG(key && out_bits && L > 0, "bad arguments");
+  const long long n = (long long)L * L;
+  // u < p  with u = m * 2^-23  <=>  m < ceil(p * 2^23)
+  double scaled = ceil((double)p * 8388608.0);
+  if (scaled < 0) scaled = 0;
+  if (scaled > 8388608.0) scaled = 8388608.0;
+  const long long words = (n + 31) / 32;
+  random_spins_kernel<<<(unsigned)((words + 127) / 128), 128, 0, (cudaStream_t)stream>>>(key[0], key[1], n, (uint32_t)scaled,
+                                                                                       out_bits);
+  NQ_LAUNCHED();
+  return NQ_OK;
+}
+
+extern "C" int nq_ising_pack(const void* spins, int32_t is_float, int64_t n_sites, uint32_t* bits, void* stream) {
+  NQ_CHECK_ARG(spins && bits && n_sites > 0, "bad arguments");
+  const long long words = (n_sites + 31) / 32;
+  const unsigned blocks = (unsigned)((words + 127) / 128);
+  if (is_float) pack_kernel<float><<<blocks, 128, 0, (cudaStream_t)stream>>>((const float*)spins, n_sites, bits);
+  else pack_kernel<int32_t><<<blocks, 128, 0, (cudaStream_t)stream>>>((const int32_t*)spins, n_sites, bits);
+  NQ_LAUNCHED();
+  return NQ_OK;
+}
+
+extern "C" int nq_ising_unpack(const uint32_t* bits, int64_t n_sites, int32_t is_float, void* spins, void* stream) {
+  NQ_CHECK_ARG(spins && bits && n_sites > 0, "bad arguments");
+  const unsigned blocks = (unsigned)((n_sites + 255) / 256);
+  if (is_float) unpack_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(bits, n_sites, (float*)spins);
+  else unpack_kernel<int32_t><<<blocks, 256, 0, (cudaStream_t)stream>>>(bits, n_sites, (int32_t*)spins);
+  NQ_LAUNCHED();
+  return NQ_OK;
+}
+
+extern "C" int nq_ising_measure(const uint32_t* bits, int32_t L, int64_t R, int64_t* out_MB, void* stream) {
+  NQ_CHECK_ARG(bits && out_MB && L > 0 && R > 0, "bad arguments");
+  measure_kernel<<<(unsigned)R, 256, 0, (cudaStream_t)stream>>>(bits, L, R, (long long*)out_MB);
+  NQ_LAUNCHED();
+  return NQ_OK;
+}

@@ -1,0 +1,211 @@
+"""GPU parity of the Ising path (csrc/ising.cu through the C ABI and the reference-shaped Python
+API) against the CPU oracle and the committed golden vectors.
+
+Spins are compared BIT-EXACTLY (same threefry uniforms, integer acceptance thresholds).  Float
+summaries: forward/reverse log-probs are exact sums of the oracle's float32 terms (tolerance 2
+float32 ulp of the sum); work / heat / energy are differences of O(L^2) float32 energy sums in the
+reference, whose own rounding noise is a few ulp of |E| -- the tolerance says so.  Gradients:
+1e-4 relative to the largest component (north star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ising_ref as I, jaxlike as J, parameterization_ref as P
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ising.npz'))
+FIELDS = I.IsingSummary._fields
+
+
+def rel(a, b):
+  a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+  return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def check_summary(got, ref, n_sites):
+  """got/ref: [7, ...] arrays in IsingSummary field order."""
+  got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+  e_scale = max(np.abs(ref[6]).max(), 2.0 * n_sites)
+  ulp_e = e_scale * 2.0 ** -23
+  for f, name in enumerate(FIELDS):
+    if name in ('work', 'dissipated_heat', 'energy'):
+      assert np.abs(got[f] - ref[f]).max() <= 4 * ulp_e, name
+    elif name == 'magnetization':
+      np.testing.assert_array_equal(got[f].astype(np.float32), ref[f].astype(np.float32))
+    else:
+      scale = max(np.abs(ref[2]).max(), np.abs(ref[3]).max())
+      assert np.abs(got[f] - ref[f]).max() <= 4 * scale * 2.0 ** -23, name
+
+
+def _schedule(weights):
+  from noneq_opt_b200 import ising, parameterization as p10n
+  return ising.IsingSchedule(
+      p10n.AddBaseline(p10n.ConstrainEndpoints(p10n.Chebyshev(weights[0]), 0., 0.), ising.log_temp_baseline()),
+      p10n.AddBaseline(p10n.ConstrainEndpoints(p10n.Chebyshev(weights[1]), 0., 0.), ising.field_baseline()))
+
+
+@pytest.mark.parametrize('name, L, T, R', [('L64', 64, 6, 3), ('L10', 10, 5, 3), ('L128', 128, 4, 2)])
+def test_golden_spin_histories_bit_exact(cuda, name, L, T, R):
+  from noneq_opt_b200 import ising
+  sched = _schedule(GOLD[name + '_weights'])
+  times = np.linspace(0, 1, T, dtype=np.float32)
+  params = sched(times)
+  np.testing.assert_array_equal(params.log_temp, GOLD[name + '_log_temp'])
+  np.testing.assert_array_equal(params.field, GOLD[name + '_field'])
+  seeds = J.split(J.PRNGKey(0), R)
+  final, (summary, states) = ising.simulate_ising(params, GOLD[name + '_spins0'], seeds, return_states=True)
+  assert final.spins.shape == (R, L, L) and states.spins.shape == (R, T - 1, L, L)
+  np.testing.assert_array_equal(final.spins.cpu().numpy(), GOLD[name + '_final'])
+  np.testing.assert_array_equal(states.spins.cpu().numpy(), GOLD[name + '_states'])
+  got = np.stack([getattr(summary, f).cpu().numpy() for f in FIELDS])        # [7, R, T-1]
+  check_summary(got, np.transpose(GOLD[name + '_summary'], (1, 0, 2)), L * L)
+  # single-replica call: same nesting as lax.scan over update (ising.py:153-173)
+  f1, s1 = ising.simulate_ising(params, GOLD[name + '_spins0'], seeds[1])
+  assert f1.spins.shape == (L, L) and s1.work.shape == (T - 1,)
+  np.testing.assert_array_equal(f1.spins.cpu().numpy(), GOLD[name + '_final'][1])
+
+
+@pytest.mark.parametrize('name, L, T, R', [('L64', 64, 6, 3), ('L10', 10, 5, 3), ('L128', 128, 4, 2)])
+@pytest.mark.parametrize('loss', ['work', 'entropy'])
+def test_golden_gradients(cuda, name, L, T, R, loss):
+  from noneq_opt_b200 import ising
+  sched = _schedule(GOLD[name + '_weights'])
+  times = np.linspace(0, 1, T, dtype=np.float32)
+  seeds = J.split(J.PRNGKey(0), R)
+  loss_fn = ising.total_work if loss == 'work' else ising.total_entropy_production
+  gold = GOLD[f'{name}_grad_{loss}']              # [R, 6*8 + 1]
+  grad, lp, rp, summary = ising.estimate_gradient_fwd_REINFORCE_track_terms(loss_fn)(
+      sched, times, GOLD[name + '_spins0'], seeds)
+  def flat(g):
+    return np.concatenate([g.log_temp.wrapped.wrapped.weights.cpu().numpy(),
+                           g.field.wrapped.wrapped.weights.cpu().numpy()], -1)
+  for got, sl in ((flat(grad), slice(0, 16)), (flat(lp), slice(16, 32)), (flat(rp), slice(32, 48))):
+    for r in range(R):
+      assert rel(got[r], gold[r, sl]) < 1e-4
+  g_rev, _ = ising.estimate_gradient_rev(loss_fn)(sched, times, GOLD[name + '_spins0'], seeds)
+  g_fwd, _ = ising.estimate_gradient_fwd(loss_fn)(sched, times, GOLD[name + '_spins0'], seeds)
+  np.testing.assert_allclose(flat(g_rev), flat(g_fwd), rtol=1e-4)        # tests/ising_test.py:129-145
+  np.testing.assert_allclose(flat(g_rev), flat(grad), rtol=1e-6)
+  g1, s1 = ising.estimate_gradient_rev(loss_fn)(sched, times, GOLD[name + '_spins0'], seeds[0])
+  assert g1.field.wrapped.wrapped.weights.shape == (8,) and s1.work.shape == (T - 1,)
+
+
+def test_random_spins_and_measures_bit_exact(cuda):
+  from noneq_opt_b200 import ising
+  for L in (10, 64, 256):
+    got = ising.random_spins([L, L], .5, J.PRNGKey(1)).cpu().numpy()
+    np.testing.assert_array_equal(got, I.random_spins((L, L), .5, J.PRNGKey(1)))
+  s = I.random_spins((64, 64), .3, J.PRNGKey(2))
+  np.testing.assert_array_equal(ising.sum_neighbors(s).cpu().numpy(), I.sum_neighbors(s))
+  st = ising.IsingState(s, ising.IsingParameters(np.float32(0.3), np.float32(-0.7)))
+  np.testing.assert_allclose(float(ising.energy(st)), I.energy(s, -0.7), rtol=1e-6)
+  np.testing.assert_allclose(ising.flip_logits(s, st.params).cpu().numpy(), I.flip_logits(s, 0.3, -0.7), rtol=1e-6)
+
+
+@pytest.mark.parametrize('L', [256, 64])
+@pytest.mark.parametrize('field', [-1.0, 0.5])
+@pytest.mark.parametrize('temperature', [float(np.exp(-1.)), float(np.exp(1.))])
+def test_detailed_balance_and_entropy_production(cuda, L, field, temperature):
+  """tests/ising_test.py:71-109 re-expressed against the new API; also bit-exact vs the oracle."""
+  from noneq_opt_b200 import ising
+  init_seed, sim_seed = J.split(J.PRNGKey(0))
+  params = ising.IsingParameters(np.log(np.float32(temperature)), np.float32(field))
+  s0 = ising.random_spins([L, L], .5, init_seed)
+  state0 = ising.IsingState(s0, params)
+  lp0 = -float(ising.energy(state0)) / temperature
+  state1, summ = ising.update(state0, params, sim_seed)
+  lp1 = -float(ising.energy(state1)) / temperature
+  np.testing.assert_allclose(lp0 + float(summ.forward_log_prob), lp1 + float(summ.reverse_log_prob), rtol=5e-4)
+  np.testing.assert_allclose(float(summ.dissipated_heat), float(summ.entropy_production) * temperature, rtol=1e-4,
+                             atol=1e-3)
+  s1_o, summ_o = I.update(s0.cpu().numpy(), (params.log_temp, field), (params.log_temp, field), sim_seed)
+  np.testing.assert_array_equal(state1.spins.cpu().numpy(), s1_o)
+  check_summary(np.array([float(getattr(summ, f)) for f in FIELDS]), np.array([getattr(summ_o, f) for f in FIELDS]), L * L)
+
+
+@pytest.mark.parametrize('L, field, temperature, expected', [(64, 0., 1e6, .5), (256, 3., .2, 1.), (64, -4., .5, 0.)])
+def test_statistics(cuda, L, field, temperature, expected):
+  from noneq_opt_b200 import ising
+  init_seed, sim_seed = J.split(J.PRNGKey(0), 2)
+  s0 = ising.random_spins([L, L], .5, init_seed)
+  params = ising.IsingParameters(np.full(1000, np.log(temperature), np.float32), np.full(1000, field, np.float32))
+  state, _ = ising.simulate_ising(params, s0, sim_seed)
+  np.testing.assert_allclose(float(((state.spins + 1) / 2).float().mean()), expected, atol=.05)
+
+
+def test_counts_and_partials_match_oracle_trace(cuda):
+  from noneq_opt_b200 import ising
+  L, T = 64, 5
+  lt, h = GOLD['L64_log_temp'][:T], GOLD['L64_field'][:T]
+  s0 = I.random_spins((L, L), .5, J.PRNGKey(3))
+  seed = J.PRNGKey(9)
+  trace = []
+  I.simulate_ising(lt, h, s0, seed, trace=trace)
+  _, _, spins, _, _, seeds, broadcast, bits = ising._prepare(ising.IsingParameters(lt, h), s0, seed)
+  run = ising._run_kernel(lt, h, bits, broadcast, seeds, L, want_partials=True, want_counts=True)
+  counts = run.counts.cpu().numpy()[0]            # [T-1, half, active/flipped, 16]
+  for t in range(1, T):
+    tr = trace[t - 1]
+    cur = tr['spins_before']
+    for half in range(2):
+      mask = tr['masks'][half].astype(bool)
+      slot = 8 * (cur > 0) + (I.sum_neighbors(cur) + 4) // 2
+      np.testing.assert_array_equal(counts[t - 1, half, 0], np.bincount(slot[mask], minlength=16))
+      np.testing.assert_array_equal(counts[t - 1, half, 1], np.bincount(slot[mask & (tr['flips'][half] > 0)], minlength=16))
+      cur = tr['spins_mid'] if half == 0 else tr['spins_after']
+  cf = I.closed_form_gradient('total_work', lt, h, np.eye(T), np.eye(T), s0, seed)
+  part = run.partials.cpu().numpy()[:, 0]
+  assert rel(part[0], cf['per_step']['dfwd_dh'][1:]) < 1e-5
+  assert rel(part[1], cf['per_step']['dfwd_dl'][1:]) < 1e-5
+
+
+def test_training_step_runs(cuda):
+  """tests/ising_test.py:148-175: 20 Adam steps stay finite; batch 32, 11 time steps."""
+  from noneq_opt_b200 import ising, optimizers, parameterization as p10n, random as nqr, tree
+  for loss_fn in (ising.total_work, ising.total_entropy_production):
+    for mode in ('fwd', 'rev'):
+      schedule = ising.IsingSchedule(log_temp=p10n.Constant(1.), field=p10n.Chebyshev(np.ones(8, np.float32)))
+      opt = optimizers.adam(1e-3)
+      state = opt.init_fn(schedule)
+      step_fn = ising.get_train_step(opt, -np.ones([10, 10], np.float32), 32, 11, loss_fn, mode)
+      seed = J.PRNGKey(0)
+      for step in range(20):
+        seed, split = nqr.split_host(seed)
+        state, summary = step_fn(state, step, split)
+      assert summary.work.shape == (32, 10)
+      for leaf in tree.tree_leaves(state):
+        assert np.isfinite(np.asarray(leaf)).all()
+  out = ising.get_train_step_REINFORCE_track_terms(opt, -np.ones([10, 10], np.float32), 8, 5, ising.total_work, 'fwd')(
+      opt.init_fn(schedule), 0, J.PRNGKey(1))
+  assert len(out) == 5
+
+
+def test_config4_lattice_properties_and_one_sweep_parity(cuda):
+  """configs[3] lattice size (1024^2, shared-memory resident, CTA per replica): a short run is
+  bit-exact vs the oracle, and the running energy agrees with a from-scratch measurement."""
+  from noneq_opt_b200 import ising
+  L, T, R = 1024, 3, 2
+  s0 = I.random_spins((L, L), .5, J.PRNGKey(1))
+  lt = np.log(np.array([2.5, 2.3, 2.1], np.float32))
+  h = np.array([-0.2, 0.0, 0.2], np.float32)
+  seeds = J.split(J.PRNGKey(0), R)
+  final, summary = ising.simulate_ising(ising.IsingParameters(lt, h), s0, seeds)
+  fin_o, summ_o = I.simulate_ising(lt, h, s0, seeds[1])
+  np.testing.assert_array_equal(final.spins[1].cpu().numpy(), fin_o)
+  got = np.stack([getattr(summary, f)[1].cpu().numpy() for f in FIELDS])
+  check_summary(got, np.stack([getattr(summ_o, f) for f in FIELDS]), L * L)
+  e_meas = float(ising.energy(ising.IsingState(final.spins[0], ising.IsingParameters(lt[-1], h[-1]))))
+  np.testing.assert_allclose(float(summary.energy[0, -1]), e_meas, rtol=1e-6)
+
+
+def test_shape_errors(cuda):
+  from noneq_opt_b200 import ising
+  p = ising.IsingParameters(np.zeros(3, np.float32), np.zeros(3, np.float32))
+  with pytest.raises(ValueError):
+    ising.simulate_ising(p, -np.ones((9, 9), np.int32), J.PRNGKey(0))
+  with pytest.raises(ValueError):
+    ising.simulate_ising(p, -np.ones((8, 8), np.int32), J.PRNGKey(0), checkpoint_every=5)
+  with pytest.raises(NotImplementedError):
+    ising.simulate_ising(p, -np.ones((8,), np.int32), J.PRNGKey(0))
