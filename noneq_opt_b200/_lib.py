@@ -15,6 +15,8 @@ NQ_SHIFT_FREE, NQ_SHIFT_PERIODIC = 0, 1
 NQ_MATH_STRICT, NQ_MATH_FAST = 0, 1
 NQ_MOM_COUNT = 8
 NQ_IS_NSUMMARY, NQ_IS_NPARTIAL = 7, 4
+(NQ_IS_WORK, NQ_IS_HEAT, NQ_IS_FWD, NQ_IS_REV, NQ_IS_EP, NQ_IS_MAG, NQ_IS_ENERGY) = range(7)
+(NQ_IS_DFWD_DH, NQ_IS_DFWD_DL, NQ_IS_DREV_DH, NQ_IS_DREV_DL) = range(4)
 
 
 class NqLangevinDesc(C.Structure):

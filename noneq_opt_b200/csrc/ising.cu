@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(WARP_TEAM ? 128 : 1024) ising_fast_kernel(cons
   uint32_t* spread = smem;
   const int L = sh.L, NW = sh.NW, T = sh.T;
   const int lat_words = 2 * L * NW;
-  const int team_words = lat_words + 2 * kIsingClasses;
+  const int team_words = lat_words + 2 * kIsingClasses + (WARP_TEAM ? 2 * 2 * 2 * kIsingClasses : 0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int team = WARP_TEAM ? warp : 0;
   const int tid = WARP_TEAM ? lane : threadIdx.x;          // index within the team
@@ -304,7 +304,9 @@ __global__ void __launch_bounds__(WARP_TEAM ? 128 : 1024) ising_fast_kernel(cons
   const int nteams = WARP_TEAM ? blockDim.x / 32 : 1;
   uint32_t* lat = smem + 4 * 256 + team * team_words;
   uint32_t* thr_s = lat + lat_words;
-  int* hist_s = reinterpret_cast<int*>(smem + 4 * 256 + nteams * team_words);  // CTA team only
+  // per-sweep class histograms [parity][half][active|flipped][16]: per team (warp teams) or per CTA
+  int* hist_s = WARP_TEAM ? reinterpret_cast<int*>(thr_s + 2 * kIsingClasses)
+                          : reinterpret_cast<int*>(smem + 4 * 256 + nteams * team_words);
 
   for (int v = threadIdx.x; v < 4 * 256; v += blockDim.x) spread[v] = spread8_to_nibbles(v & 255) << (v >> 8);
   if (!WARP_TEAM)
@@ -383,12 +385,17 @@ __global__ void __launch_bounds__(WARP_TEAM ? 128 : 1024) ising_fast_kernel(cons
         At[c][k] = __reduce_add_sync(0xffffffffu, hA[k]);
         Ft[c][k] = __reduce_add_sync(0xffffffffu, hF[k]);
       }
-      if (!WARP_TEAM && lane == 0) {
+      if (lane == 0) {
         int* hs = hist_s + ((t & 1) * 2 + c) * 2 * kIsingClasses;
 #pragma unroll
         for (int k = 0; k < 10; ++k) {
-          if (At[c][k]) atomicAdd(&hs[k], At[c][k]);
-          if (Ft[c][k]) atomicAdd(&hs[kIsingClasses + k], Ft[c][k]);
+          if (WARP_TEAM) {
+            hs[k] = At[c][k];
+            hs[kIsingClasses + k] = Ft[c][k];
+          } else {
+            if (At[c][k]) atomicAdd(&hs[k], At[c][k]);
+            if (Ft[c][k]) atomicAdd(&hs[kIsingClasses + k], Ft[c][k]);
+          }
         }
       }
       team_sync();
@@ -406,22 +413,15 @@ __global__ void __launch_bounds__(WARP_TEAM ? 128 : 1024) ising_fast_kernel(cons
     }
     if (WARP_TEAM || warp == 0) {
       int a2[2], f2[2];
-      if (WARP_TEAM) {
+      if (WARP_TEAM) __syncwarp();
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          a2[c] = f2[c] = 0;
-#pragma unroll
-          for (int k = 0; k < 10; ++k)
-            if (lane == k) { a2[c] = At[c][k]; f2[c] = Ft[c][k]; }
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          int* hs = hist_s + ((t & 1) * 2 + c) * 2 * kIsingClasses;
-          a2[c] = lane < 10 ? hs[lane] : 0;
-          f2[c] = lane < 10 ? hs[kIsingClasses + lane] : 0;
-        }
-        __syncwarp();
+      for (int c = 0; c < 2; ++c) {
+        int* hs = hist_s + ((t & 1) * 2 + c) * 2 * kIsingClasses;
+        a2[c] = lane < 10 ? hs[lane] : 0;
+        f2[c] = lane < 10 ? hs[kIsingClasses + lane] : 0;
+      }
+      __syncwarp();
+      if (!WARP_TEAM) {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           int* hs = hist_s + ((t & 1) * 2 + c) * 2 * kIsingClasses;
@@ -585,7 +585,7 @@ __global__ void measure_kernel(const uint32_t* bits, int L, long long R, long lo
 static bool fast_path(int L) { return L % 64 == 0; }
 static size_t fast_smem_bytes(int L, bool warp_team, int nteams) {
   const size_t lat_words = 2 * (size_t)L * (L / 64);
-  size_t words = 4 * 256 + nteams * (lat_words + 2 * kIsingClasses);
+  size_t words = 4 * 256 + nteams * (lat_words + 2 * kIsingClasses + (warp_team ? 2 * 2 * 2 * kIsingClasses : 0));
   if (!warp_team) words += 2 * 2 * 2 * kIsingClasses + 2;
   return words * 4;
 }

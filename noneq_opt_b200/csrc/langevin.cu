@@ -19,7 +19,9 @@
 namespace nq {
 
 constexpr int kTile = 128;     // steps staged per shared-memory tile
-constexpr int kThreads = 128;  // trajectories per CTA
+constexpr int kThreads = 64;   // trajectories per CTA (small CTAs balance 1e5 trajectories over 148 SMs)
+// resident CTAs per SM the register budget is held to, so that config 2 (1563 CTAs) is one wave
+constexpr int min_blocks(int DP) { return DP <= 8 ? 16 : (DP <= 16 ? 11 : (DP <= 24 ? 8 : 6)); }
 
 struct LangevinConsts {
   int potential, shift_kind;
@@ -173,7 +175,7 @@ struct LangevinIO {
 
 // NV layout of a partial row: [0..7] moments, [8 .. 8+DP) logP grads, [8+DP .. 8+2DP) reparam grads
 template <int POT, bool FAST, int DP, bool RECORD>
-__global__ void __launch_bounds__(kThreads) langevin_kernel(const LangevinConsts c, const LangevinIO io) {
+__global__ void __launch_bounds__(kThreads, min_blocks(DP)) langevin_kernel(const LangevinConsts c, const LangevinIO io) {
   constexpr bool GRAD = DP > 0;
   constexpr int DPS = GRAD ? DP : 4;
   __shared__ float r_s[kTile + 1];
