@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""Benchmark of the noneq_opt ensemble hot path on B200 (driver contract: one JSON line on stdout).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the CPU arm (oracle port, all host threads)
+
+Headline workload (BASELINE.json configs[1]): barrier_crossing -- double well with moving trap,
+100 000 trajectories x 10 000 steps, forward + gradient of the REINFORCE work objective wrt the 13
+Chebyshev protocol coefficients.  One "step" = one such gradient evaluation per GPU (1e9
+trajectory-steps); with N GPUs every rank runs its own 100 000-trajectory slice of the global batch
+(weak scaling) and ONE NCCL all-reduce combines the gradient and work moments.
+
+Also reported in the same line (`ising`): spin-updates/s of the Glauber sweep at configs[2]
+(64x64 x 4096 replicas x 1000 sweeps, with the REINFORCE gradient) and configs[3] (1024x1024
+bit-packed x 256 replicas; throughput per sweep is independent of T, the bench runs 100 sweeps).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# ---- config 2: barrier_crossing
+KT = 4.183
+BETA = 1.0 / KT
+X_M = 14.0
+KAPPA = 21.3863 / (BETA * X_M ** 2)
+K_TRAP = 1.5
+GAMMA = KT / 1e7
+DT = 1e-8
+C2_COEFFS = np.array([2.00000000e+01, 1.99599600e+01, -2.63245988e-15, 8.41484236e-16, 0.00000000e+00,
+                      -7.47209997e-15, -1.69086360e-14, 1.27892999e-14, 3.02606960e-15, -6.05805446e-15,
+                      -6.36600761e-16, -5.53701086e-15, -1.14938537e-14], np.float32)
+C2_B, C2_S = 100_000, 10_000
+INSTR_PER_TRAJ_STEP = 326.0      # 3 threefry blocks (219 INT) + ~75 FP32 + ~6 SFU + 2*13 FFMA
+INSTR_PER_SPIN_UPDATE = 47.0     # half a threefry block (36.5) + ~10 logic/compare/popc
+ISSUE_PEAK = 148 * 128 * 1.965e9  # thread-instructions/s at max SM clock
+L2_FLUSH_BYTES = 256 << 20
+
+
+def measured_peaks():
+  try:
+    return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+  except Exception:
+    return None
+
+
+class ClockSampler:
+  """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+  Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+       'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+       'clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, index):
+    self.index, self.rows, self.proc = index, [], None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                    '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                   stderr=subprocess.DEVNULL, text=True)
+      self.thread = threading.Thread(target=self._read, daemon=True)
+      self.thread.start()
+    except Exception:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append([c.strip() for c in line.split(',')])
+
+  def stop(self):
+    if self.proc is None:
+      return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+    time.sleep(0.12)
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=5)
+    except Exception:
+      self.proc.kill()
+    sm, mx, reasons, power = [], [], set(), []
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    for r in self.rows:
+      try:
+        sm.append(float(r[0])); mx.append(float(r[1])); power.append(float(r[2]))
+        for nm, v in zip(names, r[3:7]):
+          if v.lower().startswith('active'):
+            reasons.add(nm)
+      except Exception:
+        pass
+    if not sm:
+      return dict(sm_mhz=None, sm_max_mhz=None, reasons=['no samples'])
+    busy = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] or sm
+    return dict(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                samples=len(sm), power_w_max=float(max(power)))
+
+
+# =============================================================================== reference arm
+def run_reference(args):
+  """The reference's CPU implementation of the path.  JAX cannot be installed in this image, so this
+  is the oracle PORT (oracle/c, OpenMP on all host threads), on a bounded sample of config 2."""
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  from oracle import c_oracle, jaxlike as J, langevin_ref as L
+  pot = L.V_biomolecule_shifted(KAPPA, KAPPA, X_M, 0., K_TRAP, BETA)
+  r, phi = L.make_schedule_chebyshev(C2_S, C2_COEFFS, 0., 40.)
+  n = 1024
+  seeds = J.split(J.PRNGKey(0), C2_B)[:n]
+  x0 = np.zeros(n, np.float32)
+  times = []
+  for i in range(args.warmup + args.steps):
+    t0 = time.perf_counter()
+    c_oracle.langevin(pot, r, phi, x0, seeds, C2_S, 0, DT, KT, GAMMA, 1.0)
+    if i >= args.warmup:
+      times.append(time.perf_counter() - t0)
+  ms = 1e3 * float(np.mean(times))
+  value = n * C2_S / (ms * 1e-3)
+  cores = c_oracle.max_threads()
+  line = dict(impl='reference', metric='langevin_traj_steps_per_s', value=value, unit='traj-steps/s',
+              n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True,
+              scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+              config=workload_config(args.gpus),
+              cpu_baseline=dict(value=value, unit='traj-steps/s', cores=cores, kind='port',
+                                sample=f'{n} of {C2_B} trajectories x {C2_S} steps per step, C/OpenMP oracle port '
+                                       '(JAX itself is not installable here)'),
+              e2e=dict(value=value, unit='traj-steps/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+  print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+  return dict(workload='barrier_crossing: V_biomolecule_shifted double well + moving trap, '
+                       f'{C2_B} trajectories/GPU x {C2_S} steps, forward + REINFORCE work gradient wrt 13 Chebyshev coeffs',
+              trajectories_per_gpu=C2_B, steps_per_trajectory=C2_S, coefficients=13, kT=KT, dt=DT,
+              parallelism=f'ensemble-sharded x{n_gpus} + 1 allreduce', l2='flushed between timed iterations '
+              f'({L2_FLUSH_BYTES >> 20} MiB write); working set is registers + 24 B/trajectory')
+
+
+# =============================================================================== native arm
+def run_native(args):
+  import torch
+  import torch.distributed as dist
+  from noneq_opt_b200 import _lib, barrier_crossing as bc, distributed as nqd, random as nqr, space
+  rank, ws = nqd.init_from_env('nccl')
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  torch.cuda.set_device(local)
+  dev = torch.device('cuda', local)
+  lib = _lib.lib()   # raises when the extension is missing: no fallback
+  bc.set_math_mode(args.math)
+  _, shift = space.free()
+  pot = bc.V_biomolecule_shifted(KAPPA, KAPPA, X_M, 0., K_TRAP, BETA)
+  B_global = C2_B * ws
+  first, count = nqd.shard_range(B_global, rank, ws)
+  seed = nqr.PRNGKey(0)
+  flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+  # ---- device-resident inputs (the `value` leg): seeds, start positions, tables already in HBM
+  seeds = nqr.split(seed, B_global, first=first, count=count)
+  # Boltzmann start: 1000 stationary-trap steps at r0 = 0 with the SAME dt/kT/gamma
+  eq_key = nqr.split_host(seed, 3)[1]
+  x0 = bc._stationary_final(pot, np.zeros((1, 1), np.float32), 0.0, shift, nqr.split(eq_key, B_global, first, count),
+                            1000, DT, KT, GAMMA).reshape(-1).contiguous()
+  r_np, phi_np = bc._schedule_and_jacobian(np.arange(C2_S + 1), C2_COEFFS, 0., 40.)
+  r_dev = torch.from_numpy(r_np).to(dev)
+  phi_dev = torch.from_numpy(phi_np).to(dev)
+
+  def step_resident():
+    out = bc._simulate(pot, shift, r_dev, phi_dev, x0, seeds, C2_S, 0, DT, KT, 1.0, GAMMA)
+    if ws > 1:
+      gs, mom = nqd.allreduce_sums([out['grad_sums'], out['moments']])
+    else:
+      gs, mom = out['grad_sums'], out['moments']
+    return (gs[0] + gs[1]) / B_global, mom
+
+  # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+  coeffs_host = torch.from_numpy(C2_COEFFS.copy()).pin_memory()
+  x0_host = x0.cpu().pin_memory()
+  out_host = dict(grad=torch.empty(13, dtype=torch.float32).pin_memory(),
+                  work=torch.empty(count, dtype=torch.float32).pin_memory(),
+                  logp=torch.empty(count, dtype=torch.float32).pin_memory(),
+                  est=torch.empty(count, dtype=torch.float32).pin_memory())
+  grad_fn = nqd.langevin_gradient_sharded(B_global, pot, 0., 40., 0, shift, C2_S, DT, KT, 1.0, GAMMA)
+  h2d = coeffs_host.numel() * 4 + x0_host.numel() * 4 + 8
+  d2h = sum(t.numel() * 4 for t in out_host.values())
+
+  def step_e2e():
+    coeffs = coeffs_host.to(dev, non_blocking=True)
+    xs = x0_host.to(dev, non_blocking=True)
+    grad, aux = grad_fn(coeffs, xs, seed)
+    out_host['grad'].copy_(grad, non_blocking=True)
+    out_host['work'].copy_(aux['local']['work'], non_blocking=True)
+    out_host['logp'].copy_(aux['local']['logp'], non_blocking=True)
+    out_host['est'].copy_(aux['local']['estimator'], non_blocking=True)
+    torch.cuda.synchronize()
+    return out_host['grad']
+
+  def timed(fn, steps, warmup, sample_clocks=False):
+    for _ in range(warmup):
+      fn()
+    torch.cuda.synchronize()
+    if ws > 1:
+      dist.barrier()
+    sampler = ClockSampler(local) if sample_clocks else None
+    if sampler:
+      sampler.start()
+    launches0 = lib.nq_launch_count()
+    total_ms, result = 0.0, None
+    for _ in range(steps):
+      flush.fill_(1)                       # L2 flush between timed iterations (not timed)
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record()
+      result = fn()
+      e1.record()
+      torch.cuda.synchronize()
+      total_ms += e0.elapsed_time(e1)
+    launches = lib.nq_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if ws > 1:
+      dist.barrier()
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)     # max over ranks
+    return float(t.item()) / steps, launches, clocks, result
+
+  ms, launches, clocks, (grad, mom) = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
+  units = float(B_global) * C2_S
+  value = units / (ms * 1e-3)
+  ms_e2e, _, _, grad_e2e = timed(step_e2e, max(3, args.steps // 2), 2)
+  e2e_value = units / (ms_e2e * 1e-3)
+
+  line = None
+  if rank == 0:
+    per_gpu = value / ws
+    peaks = measured_peaks()
+    hbm_peak = peaks['hbm_gbs'] if peaks else 6650.0
+    alg_bytes = 24.0 * C2_B + 4.0 * (C2_S + 1) + 4.0 * 13 * (C2_S - 1)
+    roofline = dict(
+        bound='issue', kernel='langevin_kernel<BIOMOLECULE_SHIFTED, DP=16>',
+        achieved=per_gpu * INSTR_PER_TRAJ_STEP / 1e12, peak=ISSUE_PEAK / 1e12, unit='Tinstr/s (thread-instructions)',
+        frac=per_gpu * INSTR_PER_TRAJ_STEP / ISSUE_PEAK,
+        note='instruction-issue bound (3 threefry2x32-20 blocks per step): 326 thread-instr/traj-step (SURVEY 8d) x '
+             'measured traj-steps/s per GPU / (148 SM x 128 lanes x 1.965 GHz); not HBM- or tensor-bound',
+        traffic=None,
+        hbm=dict(bound='hbm', achieved=alg_bytes / (ms * 1e-3) / 1e9, peak=hbm_peak, unit='GB/s',
+                 frac=alg_bytes / (ms * 1e-3) / 1e9 / hbm_peak,
+                 peak_source='MEASURED_PEAKS.json (of measured)' if peaks else 'fallback',
+                 algorithmic_bytes_per_launch=alg_bytes))
+    line = dict(metric='langevin_traj_steps_per_s', value=value, unit='traj-steps/s', n_gpus=ws, steps=args.steps,
+                warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='f32', data='synthetic', config=workload_config(ws), math_mode=args.math,
+                per_gpu=per_gpu, target_per_gpu=1e11, clocks=clocks, gpu_launches=int(launches),
+                e2e=dict(value=e2e_value, unit='traj-steps/s', ms_per_step=ms_e2e, h2d_bytes_per_step=h2d,
+                         d2h_bytes_per_step=d2h, api='noneq_opt_b200.distributed.langevin_gradient_sharded '
+                         '(= barrier_crossing.estimate_gradient_boltzinit per rank)'),
+                roofline=roofline,
+                check=dict(mean_work=float(mom[1] / mom[0]), grad0=float(grad[0]), grad0_e2e=float(grad_e2e[0])))
+
+  # ---- secondary: Ising spin-updates/s (rank-local replicas; no collective on the data path)
+  ising_res = None if args.no_ising else bench_ising(args, dev, rank, ws)
+  if rank == 0:
+    line['ising'] = ising_res
+    if ws == 1 and not args.no_cpu:
+      line['cpu_baseline'] = cpu_baseline()
+    print(json.dumps(line), flush=True)
+  if ws > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def bench_ising(args, dev, rank, ws):
+  import torch
+  import torch.distributed as dist
+  from noneq_opt_b200 import ising, parameterization as p10n, random as nqr
+  out = {}
+
+  def schedule(D, weights):
+    return ising.IsingSchedule(
+        p10n.AddBaseline(p10n.ConstrainEndpoints(p10n.Chebyshev(weights[0]), 0., 0.), ising.log_temp_baseline(0.69, 10, 1)),
+        p10n.AddBaseline(p10n.ConstrainEndpoints(p10n.Chebyshev(weights[1]), 0., 0.), ising.field_baseline(-1, 1)))
+
+  def timed(fn, steps, warmup):
+    for _ in range(warmup):
+      fn()
+    torch.cuda.synchronize()
+    if ws > 1:
+      dist.barrier()
+    total = 0.0
+    for _ in range(steps):
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record()
+      fn()
+      e1.record()
+      torch.cuda.synchronize()
+      total += e0.elapsed_time(e1)
+    t = torch.tensor([total], dtype=torch.float64, device=dev)
+    if ws > 1:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) / steps
+
+  # config 3: 64x64, 4096 replicas/GPU, T = 1001, REINFORCE gradient of total entropy production
+  L, R, T = 64, 4096, 1001
+  w = (0.1 * np.random.RandomState(0).normal(size=(2, 16))).astype(np.float32)
+  sched = schedule(16, w)
+  times = np.linspace(0, 1, T, dtype=np.float32)
+  spins0 = -torch.ones((L, L), dtype=torch.float32, device=dev)
+  first, count = rank * R, R
+  seeds = nqr.split(nqr.PRNGKey(0), R * ws, first=first, count=count)
+  est = ising.estimate_gradient_rev(ising.total_entropy_production)
+  ms = timed(lambda: est(sched, times, spins0, seeds), 3, 1)
+  upd = float(R * ws) * (T - 1) * L * L
+  out['c3_64x64_4096rep_1000sweeps_grad'] = dict(spin_updates_per_s=upd / (ms * 1e-3), ms_per_step=ms,
+                                                 per_gpu=upd / ws / (ms * 1e-3),
+                                                 roofline_frac_issue=upd / ws / (ms * 1e-3) * INSTR_PER_SPIN_UPDATE / ISSUE_PEAK)
+  # config 4: 1024x1024 bit-packed, 256 replicas/GPU; 100 sweeps per step (throughput is per sweep)
+  L, R, T = 1024, 256, 101
+  sched0 = schedule(16, np.zeros((2, 16), np.float32))
+  times = np.linspace(0, 1, T, dtype=np.float32)
+  params = sched0(times)
+  spins0 = ising.random_spins([L, L], 0.5, nqr.PRNGKey(1))
+  seeds = nqr.split(nqr.PRNGKey(0), R * ws, first=rank * R, count=R)
+  log_temp, field, spins, L_, batched, seeds_t, broadcast, bits = ising._prepare(params, spins0, seeds)
+  ms = timed(lambda: ising._run_kernel(log_temp, field, bits, broadcast, seeds_t, L), 2, 1)
+  upd = float(R * ws) * (T - 1) * L * L
+  peaks = measured_peaks()
+  hbm_peak = peaks['hbm_gbs'] if peaks else 6650.0
+  out['c4_1024x1024_256rep'] = dict(spin_updates_per_s=upd / (ms * 1e-3), ms_per_step=ms, sweeps_per_step=T - 1,
+                                    per_gpu=upd / ws / (ms * 1e-3),
+                                    roofline_frac_issue=upd / ws / (ms * 1e-3) * INSTR_PER_SPIN_UPDATE / ISSUE_PEAK,
+                                    hbm_gbs_if_streamed=upd / ws / (ms * 1e-3) * 0.375 / 1e9,
+                                    hbm_frac_if_streamed=upd / ws / (ms * 1e-3) * 0.375 / 1e9 / hbm_peak,
+                                    note='lattice is shared-memory resident for the whole trajectory: HBM is touched '
+                                         'only at start/end (0.375 B/update is the streamed-design figure of SURVEY 8d)')
+  out['unit'] = 'spin-updates/s'
+  out['target_per_gpu'] = 1e11
+  return out
+
+
+def cpu_baseline():
+  """Oracle port (C/OpenMP) on a bounded sample of config 2, timed on this box's host cores."""
+  from oracle import c_oracle, jaxlike as J, langevin_ref as L
+  pot = L.V_biomolecule_shifted(KAPPA, KAPPA, X_M, 0., K_TRAP, BETA)
+  r, phi = L.make_schedule_chebyshev(C2_S, C2_COEFFS, 0., 40.)
+  n = 2048
+  seeds = J.split(J.PRNGKey(0), C2_B)[:n]
+  c_oracle.langevin(pot, r, phi, np.zeros(64, np.float32), seeds[:64], C2_S, 0, DT, KT, GAMMA, 1.0)   # warm
+  t0 = time.perf_counter()
+  c_oracle.langevin(pot, r, phi, np.zeros(n, np.float32), seeds, C2_S, 0, DT, KT, GAMMA, 1.0)
+  dt = time.perf_counter() - t0
+  return dict(value=n * C2_S / dt, unit='traj-steps/s', cores=c_oracle.max_threads(), kind='port',
+              sample=f'{n} of {C2_B} trajectories x {C2_S} steps (config 2 slice), {dt:.1f} s of C/OpenMP oracle port; '
+                     'the reference itself (JAX-CPU) is not installable in this image')
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=10)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+  ap.add_argument('--math', default=os.environ.get('NQ_MATH_MODE', 'strict'), choices=['strict', 'fast'])
+  ap.add_argument('--no-ising', action='store_true')
+  ap.add_argument('--no-cpu', action='store_true')
+  args = ap.parse_args()
+  if args.impl == 'reference':
+    run_reference(args)
+  else:
+    run_native(args)
+
+
+if __name__ == '__main__':
+  main()
