@@ -135,7 +135,7 @@ int nq_langevin_forward_ckpt(const NqLangevinDesc* desc /*host*/, const float* r
                              const float* x0, const uint32_t* seeds, int64_t n,
                              int64_t ckpt_every,
                              float* work, float* logp, float* x_final,
-                             float* ckpt_x /*[n_ckpt][n]*/, uint32_t* ckpt_rng /*[n_ckpt][2][n]*/,
+                             float* ckpt_x /*[n_ckpt][n]*/, uint32_t* ckpt_rng /*[n_ckpt][4][n]: chain key + pending sub-key*/,
                              double* moments, void* workspace, size_t workspace_bytes, void* stream);
 int nq_langevin_replay(const NqLangevinDesc* desc /*host*/, const float* r_table,
                        int64_t n, int64_t ckpt_every,

@@ -23,12 +23,14 @@ from __future__ import annotations
 
 import collections
 import ctypes as C
+import functools
 import os
 
 import numpy as np
 import torch
 
 from . import _lib
+from . import control_flow
 from . import parameterization as p10n
 from . import random as nqrandom
 from .potentials import V_biomolecule, V_biomolecule_shifted, V_spring, as_energy  # noqa: F401
@@ -130,17 +132,40 @@ def MakeSchedule_chebyshev(timevec, coeffs, r0_init, r0_final):
   return vals
 
 
-def _schedule_and_jacobian(timevec, coeffs, r0_init, r0_final):
-  tv = np.asarray(timevec)[1:-1]
+@functools.lru_cache(maxsize=16)
+def _chebyshev_grid_basis(n_times: int, n_coeffs: int):
+  """Monic Chebyshev basis on the reference's scaled step grid ((k-1)/(S-2), k = 1..S-1); it does
+  not depend on the coefficients, so it is built once per (S, D)."""
+  tv = np.arange(n_times)[1:-1]
   scaled = ((tv - 1).astype(np.float32) / np.float32(tv[-1] - 1)).astype(np.float32)
+  basis = p10n.Chebyshev(np.zeros(n_coeffs, np.float32)).basis(scaled)
+  basis.setflags(write=False)
+  return scaled, basis
+
+
+def _schedule_and_jacobian(timevec, coeffs, r0_init, r0_final):
+  timevec = np.asarray(timevec)
   if isinstance(coeffs, p10n.Parameterization):
-    proto = coeffs
+    tv = timevec[1:-1]
+    scaled = ((tv - 1).astype(np.float32) / np.float32(tv[-1] - 1)).astype(np.float32)
+    inner, jac = coeffs(scaled), coeffs.jacobian(scaled)
   else:
     if isinstance(coeffs, torch.Tensor):
       coeffs = coeffs.detach().cpu().numpy()
-    proto = p10n.Chebyshev(np.asarray(coeffs, np.float32))
-  vals = np.concatenate([[np.float32(r0_init)], proto(scaled), [np.float32(r0_final)]]).astype(np.float32)
-  return vals, proto.jacobian(scaled)
+    w = np.asarray(coeffs, np.float32)
+    contiguous = timevec.ndim == 1 and timevec[0] == 0 and timevec[-1] == len(timevec) - 1
+    if contiguous and w.ndim == 1:
+      _, jac = _chebyshev_grid_basis(len(timevec), w.shape[0])
+      inner = np.zeros(jac.shape[0], np.float32)
+      for j in range(w.shape[0]):        # same float32 summation order as Chebyshev.__call__
+        inner = (inner + (w[j] * jac[:, j]).astype(np.float32)).astype(np.float32)
+    else:
+      tv = timevec[1:-1]
+      scaled = ((tv - 1).astype(np.float32) / np.float32(tv[-1] - 1)).astype(np.float32)
+      proto = p10n.Chebyshev(w)
+      inner, jac = proto(scaled), proto.jacobian(scaled)
+  vals = np.concatenate([[np.float32(r0_init)], inner, [np.float32(r0_final)]]).astype(np.float32)
+  return vals, jac
 
 
 def make_trap_fxn(timevec, coeffs, r0_init, r0_final):
@@ -373,3 +398,71 @@ single_estimate_boltzinit_logP, estimate_gradient_boltzinit_logP = _estimator_fa
 single_estimate_boltzinit_reparam, estimate_gradient_boltzinit_reparam = _estimator_factory('reparam')
 (single_estimate_boltzinit_REINFORCE_recordall,
  estimate_gradient_boltzinit_REINFORCE_recordall) = _estimator_factory('reinforce')
+
+
+# ------------------------------------------------------------------------------ checkpoint + replay
+def forward_checkpointed(energy_fn, coeffs, init_pos, seeds, r0_init, r0_final, Neq, shift, simulation_steps,
+                         dt, temperature, mass, gamma, checkpoint_every):
+  """Forward pass that stores one (x, rng) carry per block of `checkpoint_every` steps -- the memory
+  profile of `control_flow.checkpoint_scan` (control_flow.py:16-31) for this integrator.  Returns the
+  trajectory totals plus an opaque `tape` for `replay_vjp`."""
+  control_flow.check_divides(int(simulation_steps), int(checkpoint_every))
+  device = _lib.require_cuda()
+  S, K = int(simulation_steps), int(checkpoint_every)
+  seeds = nqrandom.as_key_tensor(seeds, device).reshape(-1, 2)
+  n = seeds.shape[0]
+  x0 = _dev_f32(init_pos, device).reshape(-1)
+  if x0.numel() == 1:
+    x0 = x0.expand(n).contiguous()
+  r, phi = _schedule_and_jacobian(np.arange(S + 1), coeffs, r0_init, r0_final)
+  lib = _lib.lib()
+  desc = _desc(energy_fn, shift, S, Neq, dt, temperature, mass, gamma)
+  r_dev = _dev_f32(r, device)
+  n_ckpt = lib.nq_langevin_ckpt_count(S, K)
+  ckpt_x = torch.empty((n_ckpt, n), dtype=torch.float32, device=device)
+  ckpt_rng = torch.empty((n_ckpt, 4, n), dtype=torch.int32, device=device)
+  ws_bytes = lib.nq_langevin_workspace_bytes(n, 0)
+  ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+  out = dict(work=torch.empty(n, dtype=torch.float32, device=device),
+             logp=torch.empty(n, dtype=torch.float32, device=device),
+             x_final=torch.empty(n, dtype=torch.float32, device=device),
+             moments=torch.zeros(_lib.NQ_MOM_COUNT, dtype=torch.float64, device=device))
+  _lib.check(lib.nq_langevin_forward_ckpt(C.byref(desc), _lib.ptr(r_dev), _lib.ptr(x0), _lib.ptr(seeds), n, K,
+                                          _lib.ptr(out['work']), _lib.ptr(out['logp']), _lib.ptr(out['x_final']),
+                                          _lib.ptr(ckpt_x), _lib.ptr(ckpt_rng), _lib.ptr(out['moments']),
+                                          _lib.ptr(ws), ws_bytes, _lib.stream_arg()))
+  out['tape'] = dict(desc=desc, r_dev=r_dev, phi=phi, ckpt_x=ckpt_x, ckpt_rng=ckpt_rng, K=K, S=S, n=n)
+  return out
+
+
+def replay_vjp(tape, lbar, wbar):
+  """Reverse ("adjoint") pass: regenerate every block from its checkpoint and return
+  gbar[k] = sum_n lbar_n dlogp_n/dr_k + wbar_n dW_n/dr_k for k = 0..S (float64 CUDA tensor)."""
+  device = tape['r_dev'].device
+  lbar = _dev_f32(lbar, device).reshape(-1)
+  wbar = _dev_f32(wbar, device).reshape(-1)
+  gbar = torch.empty(tape['S'] + 1, dtype=torch.float64, device=device)
+  _lib.check(_lib.lib().nq_langevin_replay(C.byref(tape['desc']), _lib.ptr(tape['r_dev']), tape['n'], tape['K'],
+                                           _lib.ptr(tape['ckpt_x']), _lib.ptr(tape['ckpt_rng']), _lib.ptr(lbar),
+                                           _lib.ptr(wbar), _lib.ptr(gbar), None, 0, _lib.stream_arg()))
+  return gbar
+
+
+def estimate_gradient_boltzinit_checkpointed(batch_size, energy_fn, r0_init, r0_final, Neq, shift, simulation_steps,
+                                             dt, temperature, mass, gamma, checkpoint_every, term='reinforce'):
+  """estimate_gradient_boltzinit (:216-224) as forward-with-checkpoints + replay: the two-pass
+  reverse-mode structure of jax.grad through a checkpointed scan.  Same result as the fused
+  single-pass estimator; useful for arbitrary per-trajectory cotangents via `replay_vjp`."""
+  w_logp, w_rep = _TERMS[term]
+
+  def _estimate_gradient(coeffs, init_pos, seed):
+    seeds = nqrandom.split(seed, batch_size)
+    fwd = forward_checkpointed(energy_fn, coeffs, init_pos, seeds, r0_init, r0_final, Neq, shift, simulation_steps,
+                               dt, temperature, mass, gamma, checkpoint_every)
+    # objective = logp * stop_grad(W) + W :  d/dlogp = W,  d/dW = 1
+    gbar = replay_vjp(fwd['tape'], w_logp * fwd['work'], torch.full_like(fwd['work'], w_rep))
+    phi = torch.from_numpy(np.asarray(fwd['tape']['phi'], np.float64)).to(gbar.device)
+    grad = ((gbar[1:-1] @ phi) / batch_size).to(torch.float32)
+    W, lp = fwd['work'], fwd['logp']
+    return grad, (w_logp * lp * W + w_rep * W, (None, lp, W)), gbar
+  return _estimate_gradient

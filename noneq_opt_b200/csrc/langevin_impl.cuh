@@ -1,0 +1,504 @@
+// Batched overdamped-Langevin integrator with per-step work / log-prob accumulation, the fused
+// REINFORCE / log-prob / reparameterisation gradient moments, and the checkpoint + replay
+// ("adjoint") pair (sm_100a).  Kernel templates; instantiated per potential in langevin_pot*.cu.
+//
+// Replaces the XLA computation traced from the reference's
+//   brownian / apply_fn              noneq_opt/barrier_crossing.py:28-94
+//   run_brownian_opt (lax.scan)      noneq_opt/barrier_crossing.py:97-143
+//   estimate_gradient_boltzinit*     noneq_opt/barrier_crossing.py:204-224, 262-333
+//   run_brownian_stationary_trap     noneq_opt/barrier_crossing.py:227-241
+//
+// Design: one thread per trajectory; position, threefry key chain, work / log-prob sums and the
+// 2*D gradient accumulators live in registers for the whole trajectory.  The trap table r[k] and
+// the protocol Jacobian phi[k][:] are staged tile by tile into shared memory and read as
+// warp-uniform broadcasts.  The key chain does not depend on the positions, so it is software
+// pipelined one step ahead: each iteration hashes the pending sub-key (the normal draw of this
+// step) and splits the next key at the same time -- three independent threefry2x32-20 blocks in
+// flight per thread.  HBM traffic is ~24 B per *trajectory*; the kernel is bound by instruction
+// issue.
+#pragma once
+#include <math.h>
+
+#include "nq_common.cuh"
+
+namespace nq {
+
+constexpr int kTile = 128;    // steps staged per shared-memory tile
+constexpr int kThreads = 64;  // trajectories per CTA (small CTAs balance 1e5 trajectories over 148 SMs)
+// resident CTAs per SM the register budget is held to, so that config 2 (1563 CTAs) is one wave
+constexpr int min_blocks(int D) { return D <= 8 ? 16 : (D <= 16 ? 11 : (D <= 24 ? 8 : 6)); }
+
+struct LangevinConsts {
+  int potential, shift_kind;
+  float hk, k_s, inv_beta, cl, cr, bde, xm, two_xm;
+  float nu, dt, sigma, inv_sigma, log_norm, box;
+  float ca;     // nu*dt*k_s/sigma : d logp_k / d r_k = z_k * ca
+  float nudt;   // nu*dt (fast mode only)
+  long long S, Neq;
+};
+
+int make_langevin_consts(const NqLangevinDesc* d, LangevinConsts* c);
+
+// ------------------------------------------------------------------------------ device math
+// STRICT (FAST=false): the reference's operation order with one binary32 rounding per operation
+// (__f*_rn intrinsics are never contracted), IEEE division/sqrt, accurate expf/logf/log1pf.
+// FAST: FMA contraction, MUFU exp2/log2/rcp, work increment in its algebraic form.
+template <bool FAST> __device__ __forceinline__ float fmul(float a, float b) { return FAST ? a * b : __fmul_rn(a, b); }
+template <bool FAST> __device__ __forceinline__ float fadd(float a, float b) { return FAST ? a + b : __fadd_rn(a, b); }
+template <bool FAST> __device__ __forceinline__ float fsub(float a, float b) { return FAST ? a - b : __fsub_rn(a, b); }
+template <bool FAST> __device__ __forceinline__ float fexp(float a) { return FAST ? __expf(a) : expf(a); }
+template <bool FAST> __device__ __forceinline__ float flog(float a) { return FAST ? __logf(a) : logf(a); }
+template <bool FAST> __device__ __forceinline__ float fdiv(float a, float b) { return FAST ? __fdividef(a, b) : __fdiv_rn(a, b); }
+
+// a / y for a constant y with r = RN(1/y): one Newton correction in FMA arithmetic returns the
+// correctly rounded quotient (Markstein) -- 3 instructions instead of the IEEE division sequence.
+__device__ __forceinline__ float div_by_const(float a, float y, float r) {
+  const float q = __fmul_rn(a, r);
+  const float e = __fmaf_rn(-q, y, a);
+  return __fmaf_rn(e, r, q);
+}
+
+// energy pieces shared between increment_work (:123-124) and the force (:60,68)
+template <int POT, bool FAST>
+struct Landscape {
+  float ul, ur, A, B, sAB;
+  __device__ __forceinline__ void eval(const LangevinConsts& c, float x) {
+    if (POT == NQ_POT_SPRING) return;
+    if (POT == NQ_POT_BIOMOLECULE) {
+      ul = fadd<FAST>(x, c.xm);
+      ur = fsub<FAST>(x, c.xm);
+    } else {
+      ul = x;
+      ur = fsub<FAST>(x, c.two_xm);
+    }
+    const float a = fmul<FAST>(c.cl, fmul<FAST>(ul, ul));
+    const float v = fadd<FAST>(fmul<FAST>(c.cr, fmul<FAST>(ur, ur)), c.bde);
+    A = fexp<FAST>(a);
+    B = fexp<FAST>(-v);
+    sAB = fadd<FAST>(A, B);
+  }
+  __device__ __forceinline__ float Em(const LangevinConsts& c) const {
+    return POT == NQ_POT_SPRING ? 0.f : fmul<FAST>(-c.inv_beta, flog<FAST>(sAB));
+  }
+  // dEm/dx in the order of jax's VJP rules (log: g/x, exp: g*ans, x**2: g*(2x))
+  __device__ __forceinline__ float dEm(const LangevinConsts& c) const {
+    if (POT == NQ_POT_SPRING) return 0.f;
+    const float g = fdiv<FAST>(-c.inv_beta, sAB);
+    const float ga = fmul<FAST>(g, A), gb = fmul<FAST>(g, B);
+    const float dxa = fmul<FAST>(fmul<FAST>(ga, c.cl), fmul<FAST>(2.0f, ul));
+    const float dxb = fmul<FAST>(fmul<FAST>(-gb, c.cr), fmul<FAST>(2.0f, ur));
+    return fadd<FAST>(dxa, dxb);
+  }
+};
+
+template <bool FAST>
+__device__ __forceinline__ float spring_energy(const LangevinConsts& c, float x, float r) {
+  const float u = fsub<FAST>(x, r);
+  return fmul<FAST>(c.hk, fmul<FAST>(u, u));
+}
+
+// dW = E(x; r_cur) - E(x; r_prev), position BEFORE the kick (:123-124, 128)
+template <int POT, bool FAST>
+__device__ __forceinline__ float work_increment(const LangevinConsts& c, const Landscape<POT, FAST>& land, float x,
+                                                float r_prev, float r_cur) {
+  if (FAST) {  // (k_s/2) [(x-r1)^2 - (x-r0)^2] = (k_s/2) (r0 - r1) (2x - r0 - r1); the landscape term cancels
+    return c.hk * (r_prev - r_cur) * ((x - r_prev) + (x - r_cur));
+  }
+  if (POT == NQ_POT_SPRING) return __fsub_rn(spring_energy<false>(c, x, r_cur), spring_energy<false>(c, x, r_prev));
+  const float em = land.Em(c);
+  return __fsub_rn(__fadd_rn(em, spring_energy<false>(c, x, r_cur)), __fadd_rn(em, spring_energy<false>(c, x, r_prev)));
+}
+
+__device__ __forceinline__ float py_mod(float x, float box) {
+  float r = fmodf(x, box);
+  if (r != 0.f && ((r < 0.f) != (box < 0.f))) r += box;
+  return r;
+}
+
+// The software-pipelined key chain of one trajectory.  Invariant at the top of step k:
+// (k0, k1) is the chain key AFTER the split of step k, (s0, s1) the sub-key step k samples with.
+struct RngPipe {
+  uint32_t k0, k1, s0, s1;
+  // state.rng -> pipeline (performs the split of the first step)
+  __device__ __forceinline__ void prime(uint32_t r0, uint32_t r1) { split2(r0, r1, k0, k1, s0, s1); }
+  // bits for this step's normal draw; advances the chain by one step
+  __device__ __forceinline__ uint32_t next() {
+    uint32_t bits, unused, n0, n1, t0, t1;
+    threefry2x32(key_schedule(s0, s1), 0u, 0u, bits, unused);  // normal(split, [1,1,1]) :88
+    split2(k0, k1, n0, n1, t0, t1);                            // key, split = split(state.rng) of the NEXT step :79
+    k0 = n0; k1 = n1; s0 = t0; s1 = t1;
+    return bits;
+  }
+};
+
+// One apply_fn (barrier_crossing.py:77-92) given the landscape already evaluated at x and the raw
+// bits of this step's normal draw.  Returns dR; updates x; writes z (standardised noise) and lp.
+template <int POT, bool FAST>
+__device__ __forceinline__ float brownian_apply(const LangevinConsts& c, const Landscape<POT, FAST>& land, float& x,
+                                                uint32_t bits, float r, float& z, float& lp) {
+  const float u = fsub<FAST>(x, r);
+  const float dEs = fmul<FAST>(c.hk, fmul<FAST>(2.0f, u));
+  const float F = POT == NQ_POT_SPRING ? -dEs : -fadd<FAST>(land.dEm(c), dEs);
+  const float mean = FAST ? F * c.nudt : __fmul_rn(__fmul_rn(F, c.nu), c.dt);
+  const float xi = normal_from_bits<FAST>(bits);
+  const float dR = fadd<FAST>(fmul<FAST>(xi, c.sigma), mean);  // sampled * scale + loc
+  if (FAST) {
+    z = xi;  // (dR - mean) / sigma in exact arithmetic
+  } else {  // x/scale - loc/scale, each quotient correctly rounded (tfp normal.py _log_prob)
+    z = __fsub_rn(div_by_const(dR, c.sigma, c.inv_sigma), div_by_const(mean, c.sigma, c.inv_sigma));
+  }
+  lp = fsub<FAST>(fmul<FAST>(-0.5f, fmul<FAST>(z, z)), c.log_norm);
+  x = fadd<FAST>(x, dR);
+  if (c.shift_kind == NQ_SHIFT_PERIODIC) x = py_mod(x, c.box);
+  return dR;
+}
+
+// ------------------------------------------------------------------------------ main kernel
+struct LangevinIO {
+  const float* r_table;  // [S+1]
+  const float* phi;      // [S-1][D] or null
+  const float* x0;       // [n]
+  const uint32_t* seeds; // [n][2]
+  float* work;           // [n]
+  float* logp;           // [n]
+  float* estimator;      // [n] or null
+  float* x_final;        // [n] or null
+  float* positions;      // time-major [n_rec][n] or null
+  long long pos_stride;
+  float* step_works;     // [S+1][n] or null
+  float* step_logps;     // [S][n] or null
+  float* ckpt_x;         // [n_ckpt][n] or null
+  uint32_t* ckpt_rng;    // [n_ckpt][4][n] or null
+  long long ckpt_every;
+  double* partials;      // [gridDim.x][NV] block partial sums
+  long long n;
+  int D;
+};
+
+constexpr int pad4(int D) { return (D + 3) / 4 * 4; }
+
+// NV layout of a partial row: [0..7] moments, [8 .. 8+DPS) logP grads, [8+DPS .. 8+2DPS) reparam grads
+template <int POT, bool FAST, int D, bool RECORD>
+__global__ void __launch_bounds__(kThreads, min_blocks(D)) langevin_kernel(const LangevinConsts c, const LangevinIO io) {
+  constexpr bool GRAD = D > 0;
+  constexpr int DA = GRAD ? D : 1;            // accumulators per term
+  constexpr int DPS = GRAD ? pad4(D) : 4;     // padded row length in shared memory
+  __shared__ float r_s[kTile + 1];
+  __shared__ __align__(16) float phi_s[GRAD ? kTile * DPS : 4];
+  __shared__ double red_s[kThreads / 32][8 + 2 * DPS];
+
+  const long long gid = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const bool live = gid < io.n;
+  const long long idx = live ? gid : io.n - 1;
+
+  float x = io.x0[idx];
+  RngPipe rng;
+  {
+    // key, split = random.split(key); init(split, ...)     barrier_crossing.py:133,138
+    uint32_t n0, n1, r0, r1;
+    split2(io.seeds[2 * idx], io.seeds[2 * idx + 1], n0, n1, r0, r1);
+    rng.prime(r0, r1);
+  }
+  Landscape<POT, FAST> land;
+  float z, lp;
+  {
+    const float r_eq = io.r_table[0];
+    for (long long e = 0; e < c.Neq; ++e) {  // equilibrate :115-121
+      land.eval(c, x);
+      brownian_apply<POT, FAST>(c, land, x, rng.next(), r_eq, z, lp);
+    }
+  }
+  if (RECORD && io.positions && live) io.positions[gid] = x;      // positions[0] = x_eq  :142
+  if (RECORD && io.step_works && live) io.step_works[gid] = 0.f;  // works[0] = 0        :141
+
+  double W = 0.0, LP = 0.0;
+  float gA[DA], gB[DA];
+#pragma unroll
+  for (int j = 0; j < DA; ++j) gA[j] = gB[j] = 0.f;
+
+  for (long long t0 = 1; t0 <= c.S; t0 += kTile) {
+    const int len = (int)min((long long)kTile, c.S - t0 + 1);
+    __syncthreads();
+    for (int i = threadIdx.x; i <= len; i += kThreads) r_s[i] = io.r_table[t0 - 1 + i];
+    if (GRAD) {
+      // phi row for step k is k-1 (k = 1..S-1); step S (fixed end point) contributes nothing
+      for (int i = threadIdx.x; i < len * DPS; i += kThreads) {
+        const int row = i / DPS, col = i - row * DPS;
+        const long long k = t0 + row;
+        phi_s[i] = (col < io.D && k <= c.S - 1) ? io.phi[(k - 1) * io.D + col] : 0.f;  // io.D <= D (template)
+      }
+    }
+    __syncthreads();
+    float Wt = 0.f, LPt = 0.f;
+#pragma unroll 1
+    for (int i = 0; i < len; ++i) {
+      if (RECORD && io.ckpt_x) {  // checkpoint BEFORE step k = t0+i when (k-1) % ckpt_every == 0
+        const long long k = t0 + i;
+        if ((k - 1) % io.ckpt_every == 0 && live) {
+          const long long q = (k - 1) / io.ckpt_every;
+          io.ckpt_x[q * io.n + gid] = x;
+          uint32_t* dst = io.ckpt_rng + q * 4 * io.n + gid;
+          dst[0] = rng.k0; dst[io.n] = rng.k1; dst[2 * io.n] = rng.s0; dst[3 * io.n] = rng.s1;
+        }
+      }
+      const float r_prev = r_s[i], r_cur = r_s[i + 1];
+      land.eval(c, x);
+      const float dW = work_increment<POT, FAST>(c, land, x, r_prev, r_cur);
+      const float dR = brownian_apply<POT, FAST>(c, land, x, rng.next(), r_cur, z, lp);
+      Wt += dW;
+      if (FAST && !RECORD) {
+        LPt = fmaf(z, z, LPt);  // sum of z^2; turned into the log-prob sum at the end of the tile
+      } else {
+        LPt += lp;
+      }
+      if (GRAD) {
+        // d logp_k / d r_k = z * ca and d W / d r_k = k_s * dR: the constant factors are applied
+        // once, after the trajectory
+        const float a = z, b = dR;
+        const float4* row = reinterpret_cast<const float4*>(phi_s + i * DPS);
+#pragma unroll
+        for (int q = 0; q < DPS / 4; ++q) {
+          const float4 p = row[q];
+          const float pv[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (4 * q + e < D) {
+              gA[4 * q + e] = fmaf(a, pv[e], gA[4 * q + e]);
+              gB[4 * q + e] = fmaf(b, pv[e], gB[4 * q + e]);
+            }
+          }
+        }
+      }
+      if (RECORD && live) {
+        const long long k = t0 + i;
+        if (io.step_works) io.step_works[k * io.n + gid] = dW;
+        if (io.step_logps) io.step_logps[(k - 1) * io.n + gid] = lp;
+        if (io.positions && (k % io.pos_stride) == 0) io.positions[(k / io.pos_stride) * io.n + gid] = x;
+      }
+    }
+    W += (double)Wt;   // two-level accumulation: f32 within a tile, binary64 across tiles
+    if (FAST && !RECORD) {
+      LP += -0.5 * (double)LPt - (double)len * (double)c.log_norm;
+    } else {
+      LP += (double)LPt;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < DA; ++j) {
+    gA[j] *= c.ca;
+    gB[j] *= c.k_s;
+  }
+
+  const float Wf = (float)W, LPf = (float)LP;
+  const float est = __fadd_rn(__fmul_rn(LPf, Wf), Wf);  // tot_log_prob * sg(total_work) + total_work  :212
+  if (live) {
+    io.work[gid] = Wf;
+    io.logp[gid] = LPf;
+    if (io.estimator) io.estimator[gid] = est;
+    if (io.x_final) io.x_final[gid] = x;
+  }
+
+  // ---- block reduction of moments and gradient sums (binary64, fixed order => deterministic)
+  const double m = live ? 1.0 : 0.0;
+  const double Wd = (double)Wf, Ld = (double)LPf;
+  constexpr int NV = 8 + 2 * DPS;
+  double v[NV];
+  v[NQ_MOM_N] = m;
+  v[NQ_MOM_W] = m * Wd;
+  v[NQ_MOM_W2] = m * Wd * Wd;
+  v[NQ_MOM_LOGP] = m * Ld;
+  v[NQ_MOM_WLOGP] = m * Wd * Ld;
+  v[NQ_MOM_EST] = m * (double)est;
+  v[6] = 0.0;
+  v[7] = 0.0;
+#pragma unroll
+  for (int j = 0; j < DPS; ++j) {
+    v[8 + j] = (GRAD && j < D) ? m * Wd * (double)gA[j < DA ? j : 0] : 0.0;
+    v[8 + DPS + j] = (GRAD && j < D) ? m * (double)gB[j < DA ? j : 0] : 0.0;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    const double s = warp_sum(v[q]);
+    if (lane == 0) red_s[warp][q] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) s += red_s[w][threadIdx.x];
+    io.partials[(long long)blockIdx.x * NV + threadIdx.x] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------ replay ("adjoint")
+// One thread per (trajectory, segment): regenerate the segment from its checkpoint and accumulate
+//   gbar[k] += lbar_n * dlogp_{n,k}/dr_k + wbar_n * dW_n/dr_k     for every step k of the segment.
+// d logp_k/d r_k = z_k * ca ; d W/d r_k = k_s (x_k - x_{k-1}) for 1 <= k <= S-1,
+// d W/d r_S = -dE/dr(x_{S-1}; r_S) = k_s (x_{S-1} - r_S), d W/d r_0 = -k_s (x_0 - r_0)... the two end
+// points are fixed by the schedule (barrier_crossing.py:149-150) but reported for completeness.
+struct ReplayIO {
+  const float* r_table;
+  const float* ckpt_x;
+  const uint32_t* ckpt_rng;
+  const float* lbar;
+  const float* wbar;
+  double* gbar;  // [S+1]
+  long long n, ckpt_every, n_ckpt;
+};
+
+template <int POT, bool FAST>
+__global__ void __launch_bounds__(128) replay_kernel(const LangevinConsts c, const ReplayIO io) {
+  extern __shared__ double acc_s[];  // [ckpt_every + 1]
+  const long long q = blockIdx.y;    // segment
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = gid < io.n;
+  const long long idx = live ? gid : io.n - 1;
+  const long long k_first = q * io.ckpt_every + 1;
+  const int len = (int)min(io.ckpt_every, c.S - k_first + 1);
+  for (int i = threadIdx.x; i <= len; i += blockDim.x) acc_s[i] = 0.0;
+  __syncthreads();
+  float x = io.ckpt_x[q * io.n + idx];
+  RngPipe rng;
+  {
+    const uint32_t* src = io.ckpt_rng + q * 4 * io.n + idx;
+    rng.k0 = src[0]; rng.k1 = src[io.n]; rng.s0 = src[2 * io.n]; rng.s1 = src[3 * io.n];
+  }
+  const float lb = live ? io.lbar[idx] : 0.f, wb = live ? io.wbar[idx] : 0.f;
+  Landscape<POT, FAST> land;
+  float z, lp;
+  const int lane = threadIdx.x & 31;
+  for (int i = 0; i < len; ++i) {
+    const long long k = k_first + i;
+    const float r_prev = io.r_table[k - 1], r_cur = io.r_table[k];
+    const float x_before = x;
+    land.eval(c, x);
+    const float dR = brownian_apply<POT, FAST>(c, land, x, rng.next(), r_cur, z, lp);
+    // dW_k = E(x_{k-1}; r_k) - E(x_{k-1}; r_{k-1}):  d/dr_k = -k_s (x_{k-1} - r_k), d/dr_{k-1} = +k_s (x_{k-1} - r_{k-1})
+    double g_cur = (double)lb * (double)(z * c.ca) - (double)wb * (double)(c.k_s * (x_before - r_cur));
+    double g_prev = (double)wb * (double)(c.k_s * (x_before - r_prev));
+    (void)dR;
+    g_cur = warp_sum(g_cur);
+    g_prev = warp_sum(g_prev);
+    if (lane == 0) {
+      atomicAdd(&acc_s[i + 1], g_cur);
+      atomicAdd(&acc_s[i], g_prev);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i <= len; i += blockDim.x) {
+    const double v = acc_s[i];
+    if (v != 0.0) atomicAdd(&io.gbar[k_first - 1 + i], v);
+  }
+}
+
+// stationary trap: same integrator, constant r0, no work bookkeeping
+template <int POT, bool FAST>
+__global__ void __launch_bounds__(kThreads) stationary_kernel(const LangevinConsts c, float r0, const float* x0,
+                                                              const uint32_t* seeds, long long n, float* x_final,
+                                                              float* positions) {
+  const long long gid = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (gid >= n) return;
+  float x = x0[gid];
+  RngPipe rng;
+  {
+    uint32_t n0, n1, r0k, r1k;
+    split2(seeds[2 * gid], seeds[2 * gid + 1], n0, n1, r0k, r1k);  // :228
+    rng.prime(r0k, r1k);
+  }
+  Landscape<POT, FAST> land;
+  float z, lp;
+  for (long long s = 0; s < c.S; ++s) {
+    land.eval(c, x);
+    brownian_apply<POT, FAST>(c, land, x, rng.next(), r0, z, lp);
+    if (positions) positions[s * n + gid] = x;
+  }
+  if (x_final) x_final[gid] = x;
+}
+
+// a single apply_fn step on caller-held state (the state's rng is split in place)
+template <int POT, bool FAST>
+__global__ void __launch_bounds__(kThreads) apply_kernel(const LangevinConsts c, float r0, float* x_io, uint32_t* rng_io,
+                                                         float* log_prob, long long n) {
+  const long long gid = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (gid >= n) return;
+  float x = x_io[gid];
+  uint32_t n0, n1, s0, s1, bits, unused;
+  split2(rng_io[2 * gid], rng_io[2 * gid + 1], n0, n1, s0, s1);
+  threefry2x32(key_schedule(s0, s1), 0u, 0u, bits, unused);
+  Landscape<POT, FAST> land;
+  float z, lp;
+  land.eval(c, x);
+  brownian_apply<POT, FAST>(c, land, x, bits, r0, z, lp);
+  x_io[gid] = x;
+  rng_io[2 * gid] = n0;
+  rng_io[2 * gid + 1] = n1;
+  if (log_prob) log_prob[gid] = lp;
+}
+
+// per-potential launchers (defined in langevin_pot*.cu through NQ_DEFINE_POT_LAUNCHERS)
+using MainLauncher = int (*)(const LangevinConsts&, const LangevinIO&, int blocks, bool fast, bool record, cudaStream_t);
+using ReplayLauncher = int (*)(const LangevinConsts&, const ReplayIO&, dim3 grid, size_t smem, bool fast, cudaStream_t);
+using StationaryLauncher = int (*)(const LangevinConsts&, float r0, const float*, const uint32_t*, long long, float*,
+                                   float*, int blocks, bool fast, cudaStream_t);
+using ApplyLauncher = int (*)(const LangevinConsts&, float r0, float*, uint32_t*, float*, long long, int blocks,
+                              bool fast, cudaStream_t);
+
+#define NQ_MAIN_CASE(POT, DD)                                                                          \
+  case DD:                                                                                             \
+    if (fast) langevin_kernel<POT, true, DD, false><<<blocks, kThreads, 0, st>>>(c, io);               \
+    else langevin_kernel<POT, false, DD, false><<<blocks, kThreads, 0, st>>>(c, io);                   \
+    break;
+
+#define NQ_DEFINE_POT_LAUNCHERS(POT, NAME)                                                             \
+  int NAME##_main(const LangevinConsts& c, const LangevinIO& io, int blocks, bool fast, bool record,   \
+                  cudaStream_t st) {                                                                   \
+    if (io.D == 0) {                                                                                   \
+      if (record) {                                                                                    \
+        if (fast) langevin_kernel<POT, true, 0, true><<<blocks, kThreads, 0, st>>>(c, io);             \
+        else langevin_kernel<POT, false, 0, true><<<blocks, kThreads, 0, st>>>(c, io);                 \
+      } else {                                                                                         \
+        if (fast) langevin_kernel<POT, true, 0, false><<<blocks, kThreads, 0, st>>>(c, io);            \
+        else langevin_kernel<POT, false, 0, false><<<blocks, kThreads, 0, st>>>(c, io);                \
+      }                                                                                                \
+      return 0;                                                                                        \
+    }                                                                                                  \
+    switch (io.D <= 13 && io.D > 12 ? 13 : pad4(io.D)) {                                               \
+      NQ_MAIN_CASE(POT, 4) NQ_MAIN_CASE(POT, 8) NQ_MAIN_CASE(POT, 12) NQ_MAIN_CASE(POT, 13)            \
+      NQ_MAIN_CASE(POT, 16) NQ_MAIN_CASE(POT, 20) NQ_MAIN_CASE(POT, 24) NQ_MAIN_CASE(POT, 28)          \
+      NQ_MAIN_CASE(POT, 32)                                                                            \
+      default: return -1;                                                                              \
+    }                                                                                                  \
+    return 0;                                                                                          \
+  }                                                                                                    \
+  int NAME##_replay(const LangevinConsts& c, const ReplayIO& io, dim3 grid, size_t smem, bool fast,    \
+                    cudaStream_t st) {                                                                 \
+    if (fast) replay_kernel<POT, true><<<grid, 128, smem, st>>>(c, io);                                \
+    else replay_kernel<POT, false><<<grid, 128, smem, st>>>(c, io);                                    \
+    return 0;                                                                                          \
+  }                                                                                                    \
+  int NAME##_stationary(const LangevinConsts& c, float r0, const float* x0, const uint32_t* seeds,     \
+                        long long n, float* xf, float* pos, int blocks, bool fast, cudaStream_t st) {  \
+    if (fast) stationary_kernel<POT, true><<<blocks, kThreads, 0, st>>>(c, r0, x0, seeds, n, xf, pos); \
+    else stationary_kernel<POT, false><<<blocks, kThreads, 0, st>>>(c, r0, x0, seeds, n, xf, pos);     \
+    return 0;                                                                                          \
+  }                                                                                                    \
+  int NAME##_apply(const LangevinConsts& c, float r0, float* x, uint32_t* rng, float* lp, long long n, \
+                   int blocks, bool fast, cudaStream_t st) {                                           \
+    if (fast) apply_kernel<POT, true><<<blocks, kThreads, 0, st>>>(c, r0, x, rng, lp, n);              \
+    else apply_kernel<POT, false><<<blocks, kThreads, 0, st>>>(c, r0, x, rng, lp, n);                  \
+    return 0;                                                                                          \
+  }
+
+#define NQ_DECLARE_POT_LAUNCHERS(NAME)                                                                 \
+  int NAME##_main(const LangevinConsts&, const LangevinIO&, int, bool, bool, cudaStream_t);            \
+  int NAME##_replay(const LangevinConsts&, const ReplayIO&, dim3, size_t, bool, cudaStream_t);         \
+  int NAME##_stationary(const LangevinConsts&, float, const float*, const uint32_t*, long long, float*, \
+                        float*, int, bool, cudaStream_t);                                              \
+  int NAME##_apply(const LangevinConsts&, float, float*, uint32_t*, float*, long long, int, bool, cudaStream_t);
+
+NQ_DECLARE_POT_LAUNCHERS(pot_spring)
+NQ_DECLARE_POT_LAUNCHERS(pot_biomolecule)
+NQ_DECLARE_POT_LAUNCHERS(pot_shifted)
+
+}  // namespace nq

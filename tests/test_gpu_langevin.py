@@ -229,3 +229,43 @@ def test_rejects_unknown_callables_and_bad_sizes(cuda):
     bc.run_brownian_opt(bc.V_spring(1.), np.zeros(3), np.zeros((1, 1)), 0., 1., 0, lambda R, dR: R + dR, J.PRNGKey(0), 10)
   with pytest.raises(ValueError):
     bc.run_brownian_opt(bc.V_spring(1.), np.zeros(3), np.zeros((5, 1, 1)), 0., 1., 0, shift, J.split(J.PRNGKey(0), 4), 10)
+
+
+@pytest.mark.parametrize('term', ['reinforce', 'logP', 'reparam'])
+def test_checkpoint_replay_adjoint_equals_fused_gradient(cuda, term):
+  """The two-pass forward-with-checkpoints + replay kernels give the fused estimator's gradient."""
+  from noneq_opt_b200 import barrier_crossing as bc, space
+  _, shift = space.free()
+  B, S, K = 192, 600, 50
+  pot = bc.V_biomolecule_shifted(KAPPA, KAPPA, XM, 0., 1.5, BETA)
+  coeffs = np.array([20., 19.5, 0.5, -0.3, 0.2], np.float32)
+  x0 = np.zeros((B, 1, 1), np.float32)
+  args = (pot, 0., 40., 5, shift, S, 1e-8, KT, 1.0, KT / 1e7)
+  fused = dict(reinforce=bc.estimate_gradient_boltzinit, logP=bc.estimate_gradient_boltzinit_logP,
+               reparam=bc.estimate_gradient_boltzinit_reparam)[term](B, *args)
+  g_fused, (_, (_, lp, w)) = fused(coeffs, x0, J.PRNGKey(11))
+  g_ckpt, (_, (_, lp2, w2)), gbar = bc.estimate_gradient_boltzinit_checkpointed(B, *args, checkpoint_every=K, term=term)(
+      coeffs, x0, J.PRNGKey(11))
+  assert torch.equal(w, w2) and torch.equal(lp, lp2)          # same forward trajectory, bit for bit
+  assert rel(g_ckpt.cpu().numpy(), g_fused.cpu().numpy()) < 1e-5
+  assert gbar.shape == (S + 1,)
+  with pytest.raises(ValueError):
+    bc.estimate_gradient_boltzinit_checkpointed(B, *args, checkpoint_every=7)(coeffs, x0, J.PRNGKey(11))
+
+
+def test_replay_per_step_gradient_vs_oracle(cuda):
+  from noneq_opt_b200 import barrier_crossing as bc, random as nqr, space
+  _, shift = space.free()
+  B, S, K = 64, 120, 30
+  pot_g, pot_o = bc.V_spring(1.3), L.V_spring(1.3)
+  coeffs = np.array([7.5, 2.5, 0.1], np.float32)
+  seeds = nqr.split(J.PRNGKey(2), B)
+  fwd = bc.forward_checkpointed(pot_g, coeffs, np.full(B, 5., np.float32), seeds, 5., 10., 4, shift, S, 1e-2, 1.0, 1.0,
+                                1.0, K)
+  gbar = bc.replay_vjp(fwd['tape'], fwd['work'], torch.ones_like(fwd['work'])).cpu().numpy()
+  o = L.estimate_gradient(pot_o, coeffs, np.full(B, 5., np.float32), J.PRNGKey(2), 5., 10., 4, S, 1e-2, 1.0, 1.0, 1.0)
+  sc = o['traj']['sc']
+  z = o['traj']['dR'] / sc.sigma - o['traj']['mean'] / sc.sigma
+  a = z / sc.sigma * sc.nu * sc.dt * np.float32(1.3)
+  expect = (o['total_work'][:, None].astype(np.float64) * a + 1.3 * o['traj']['dR']).sum(0)   # k = 1..S
+  assert rel(gbar[1:S], expect[:S - 1]) < 1e-5
