@@ -18,7 +18,7 @@ STAMP = os.path.join(HERE, 'csrc', '.build_stamp')
 SOURCES = ['core.cu', 'langevin.cu', 'langevin_pot_spring.cu', 'langevin_pot_biomolecule.cu', 'langevin_pot_shifted.cu',
            'ising.cu', 'microbench.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
-              '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
+              '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr'] + os.environ.get('NQ_EXTRA_NVCC_FLAGS', '').split()
 
 
 def _nvcc():

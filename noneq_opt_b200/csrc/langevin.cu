@@ -42,6 +42,7 @@ int make_langevin_consts(const NqLangevinDesc* d, LangevinConsts* c) {
   c->box = (float)d->box;
   c->ca = (float)((double)nu * (double)c->dt * (double)c->k_s / (double)c->sigma);
   c->nudt = (float)((double)nu * (double)c->dt);
+  c->one = 1u;
   c->S = d->steps;
   c->Neq = d->eq_steps;
   return NQ_OK;

@@ -19,10 +19,18 @@
 #pragma once
 #include <math.h>
 
+#ifndef NQ_TF_FORCE_IMAD
+#define NQ_TF_FORCE_IMAD 0
+#endif
+
 #include "nq_common.cuh"
 
 namespace nq {
 
+#ifndef NQ_LANGEVIN_UNROLL
+#define NQ_LANGEVIN_UNROLL 1
+#endif
+constexpr int kUnroll = NQ_LANGEVIN_UNROLL;
 constexpr int kTile = 128;    // steps staged per shared-memory tile
 constexpr int kThreads = 64;  // trajectories per CTA (small CTAs balance 1e5 trajectories over 148 SMs)
 // resident CTAs per SM the register budget is held to, so that config 2 (1563 CTAs) is one wave
@@ -34,6 +42,7 @@ struct LangevinConsts {
   float nu, dt, sigma, inv_sigma, log_norm, box;
   float ca;     // nu*dt*k_s/sigma : d logp_k / d r_k = z_k * ca
   float nudt;   // nu*dt (fast mode only)
+  uint32_t one;  // = 1 at run time: a multiplier ptxas cannot fold, used to place integer adds on the FMA pipe
   long long S, Neq;
 };
 
@@ -109,6 +118,19 @@ __device__ __forceinline__ float work_increment(const LangevinConsts& c, const L
   return __fsub_rn(__fadd_rn(em, spring_energy<false>(c, x, r_cur)), __fadd_rn(em, spring_energy<false>(c, x, r_prev)));
 }
 
+// Shared-memory reads through an explicit 32-bit shared-window address: keeps the per-iteration
+// generic->shared address arithmetic (S2UR/ULEA/UMOV, ~9 issue slots per step) out of the hot loop.
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
 __device__ __forceinline__ float py_mod(float x, float box) {
   float r = fmodf(x, box);
   if (r != 0.f && ((r < 0.f) != (box < 0.f))) r += box;
@@ -122,10 +144,18 @@ struct RngPipe {
   // state.rng -> pipeline (performs the split of the first step)
   __device__ __forceinline__ void prime(uint32_t r0, uint32_t r1) { split2(r0, r1, k0, k1, s0, s1); }
   // bits for this step's normal draw; advances the chain by one step
-  __device__ __forceinline__ uint32_t next() {
+  __device__ __forceinline__ uint32_t next(uint32_t one = 1u) {
     uint32_t bits, unused, n0, n1, t0, t1;
+#if NQ_TF_FORCE_IMAD
+    threefry2x32_mad(key_schedule(s0, s1), 0u, 0u, bits, unused, one);
+    const KeySchedule ks = key_schedule(k0, k1);
+    threefry2x32_mad(ks, 0u, 2u, n0, t0, one);
+    threefry2x32_mad(ks, 1u, 3u, n1, t1, one);
+#else
+    (void)one;
     threefry2x32(key_schedule(s0, s1), 0u, 0u, bits, unused);  // normal(split, [1,1,1]) :88
     split2(k0, k1, n0, n1, t0, t1);                            // key, split = split(state.rng) of the NEXT step :79
+#endif
     k0 = n0; k1 = n1; s0 = t0; s1 = t1;
     return bits;
   }
@@ -230,8 +260,10 @@ __global__ void __launch_bounds__(kThreads, min_blocks(D)) langevin_kernel(const
     }
     __syncthreads();
     float Wt = 0.f, LPt = 0.f;
-#pragma unroll 1
-    for (int i = 0; i < len; ++i) {
+    uint32_t r_addr = (uint32_t)__cvta_generic_to_shared(r_s);
+    uint32_t phi_addr = (uint32_t)__cvta_generic_to_shared(phi_s);
+#pragma unroll kUnroll
+    for (int i = 0; i < len; ++i, r_addr += 4, phi_addr += 4 * DPS) {
       if (RECORD && io.ckpt_x) {  // checkpoint BEFORE step k = t0+i when (k-1) % ckpt_every == 0
         const long long k = t0 + i;
         if ((k - 1) % io.ckpt_every == 0 && live) {
@@ -241,10 +273,10 @@ __global__ void __launch_bounds__(kThreads, min_blocks(D)) langevin_kernel(const
           dst[0] = rng.k0; dst[io.n] = rng.k1; dst[2 * io.n] = rng.s0; dst[3 * io.n] = rng.s1;
         }
       }
-      const float r_prev = r_s[i], r_cur = r_s[i + 1];
+      const float r_prev = lds_f32(r_addr), r_cur = lds_f32(r_addr + 4);
       land.eval(c, x);
       const float dW = work_increment<POT, FAST>(c, land, x, r_prev, r_cur);
-      const float dR = brownian_apply<POT, FAST>(c, land, x, rng.next(), r_cur, z, lp);
+      const float dR = brownian_apply<POT, FAST>(c, land, x, rng.next(c.one), r_cur, z, lp);
       Wt += dW;
       if (FAST && !RECORD) {
         LPt = fmaf(z, z, LPt);  // sum of z^2; turned into the log-prob sum at the end of the tile
@@ -255,10 +287,9 @@ __global__ void __launch_bounds__(kThreads, min_blocks(D)) langevin_kernel(const
         // d logp_k / d r_k = z * ca and d W / d r_k = k_s * dR: the constant factors are applied
         // once, after the trajectory
         const float a = z, b = dR;
-        const float4* row = reinterpret_cast<const float4*>(phi_s + i * DPS);
 #pragma unroll
         for (int q = 0; q < DPS / 4; ++q) {
-          const float4 p = row[q];
+          const float4 p = lds_f32x4(phi_addr + 16 * q);
           const float pv[4] = {p.x, p.y, p.z, p.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
