@@ -1,6 +1,8 @@
 // Host side of the Langevin entry points of include/noneq_b200.h: descriptor -> kernel constants
 // (float32, reference operation order), argument checks, kernel dispatch, deterministic final
 // reduction.  Kernels: langevin_impl.cuh.
+#include <stdlib.h>
+
 #include "langevin_impl.cuh"
 
 namespace nq {
@@ -43,6 +45,20 @@ int make_langevin_consts(const NqLangevinDesc* d, LangevinConsts* c) {
   c->ca = (float)((double)nu * (double)c->dt * (double)c->k_s / (double)c->sigma);
   c->nudt = (float)((double)nu * (double)c->dt);
   c->one = 1u;
+  {
+    const int R[8] = {13, 15, 26, 6, 17, 29, 16, 24};
+    for (int j = 0; j < 8; ++j) c->pow2[j] = 1u << R[j];
+  }
+  {
+    const double log2e = 1.4426950408889634, nudt = (double)nu * (double)c->dt;
+    const double ib = d->potential == NQ_POT_SPRING ? 0.0 : 1.0 / d->beta;
+    c->f_cl2 = (float)((double)c->cl * log2e);
+    c->f_ncr2 = (float)(-(double)c->cr * log2e);
+    c->f_nbde2 = (float)(-(double)c->bde * log2e);
+    c->f_clm = (float)(nudt * ib * 2.0 * (double)c->cl);
+    c->f_crm = (float)(nudt * ib * 2.0 * (double)c->cr);
+    c->f_cu = (float)(2.0 * (double)c->hk * nudt);
+  }
   c->S = d->steps;
   c->Neq = d->eq_steps;
   return NQ_OK;
@@ -65,6 +81,7 @@ __global__ void langevin_finalize_kernel(const double* partials, int nblocks, in
 
 struct PotLaunchers {
   MainLauncher main;
+  PersistentLauncher persistent;
   ReplayLauncher replay;
   StationaryLauncher stationary;
   ApplyLauncher apply;
@@ -72,16 +89,35 @@ struct PotLaunchers {
 
 static PotLaunchers launchers(int potential) {
   switch (potential) {
-    case NQ_POT_SPRING: return {pot_spring_main, pot_spring_replay, pot_spring_stationary, pot_spring_apply};
+    case NQ_POT_SPRING: return {pot_spring_main, pot_spring_persistent, pot_spring_replay, pot_spring_stationary, pot_spring_apply};
     case NQ_POT_BIOMOLECULE:
-      return {pot_biomolecule_main, pot_biomolecule_replay, pot_biomolecule_stationary, pot_biomolecule_apply};
-    default: return {pot_shifted_main, pot_shifted_replay, pot_shifted_stationary, pot_shifted_apply};
+      return {pot_biomolecule_main, pot_biomolecule_persistent, pot_biomolecule_replay, pot_biomolecule_stationary, pot_biomolecule_apply};
+    default: return {pot_shifted_main, pot_shifted_persistent, pot_shifted_replay, pot_shifted_stationary, pot_shifted_apply};
   }
 }
 
 // template D actually launched for a requested D (see NQ_DEFINE_POT_LAUNCHERS)
 static int kernel_D(int D) { return D == 0 ? 0 : (D == 13 ? 13 : pad4(D)); }
 static int partial_row(int D) { return 8 + 2 * (D > 0 ? pad4(kernel_D(D)) : 4); }
+
+// Dynamic (persistent) scheduling pays when a static launch would leave SM sub-partitions unevenly
+// loaded for a long run: at least a few CTAs per SM and at least two chunks of steps.
+constexpr long long kChunkSteps = 512;
+static bool use_persistent(long long n, long long S, bool record) {
+  // Measured on B200 at config 2: 11.04 ms vs 11.17 ms for the static launch (+1 %), i.e. the
+  // load imbalance it removes is mostly eaten by the per-chunk hand-off.  Kept as an opt-in
+  // (NQ_PERSISTENT=1) and covered by tests; the static single-wave launch is the default.
+  const char* env = getenv("NQ_PERSISTENT");
+  const bool enabled = env != nullptr && env[0] == '1';
+  return enabled && !record && n >= 148ll * kThreads * 2 && S >= 2 * kChunkSteps;
+}
+static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+static size_t persistent_bytes(long long n, int D) {
+  const long long groups = (n + kThreads - 1) / kThreads;
+  const long long n_chunks_max = 1 << 16;  // callers size the workspace without knowing S: bound the ring by n
+  (void)n_chunks_max;
+  return align256((size_t)state_words(kernel_D(D)) * groups * kThreads * 4) + align256((size_t)(groups + 2) * 4);
+}
 
 static int run(const NqLangevinDesc* desc, const LangevinIO& io_in, double* moments, double* grad_sums,
                void* workspace, size_t workspace_bytes, cudaStream_t st) {
@@ -96,18 +132,61 @@ static int run(const NqLangevinDesc* desc, const LangevinIO& io_in, double* mome
   const bool fast = desc->math_mode == NQ_MATH_FAST;
   const int blocks = (int)((io.n + kThreads - 1) / kThreads);
   const int NV = partial_row(io.D);
-  const size_t need = (size_t)blocks * NV * sizeof(double);
+  const bool record = io.positions || io.step_works || io.step_logps || io.ckpt_x;
+  const bool persistent = use_persistent(io.n, c.S, record);
+  const size_t part_bytes = align256((size_t)blocks * NV * sizeof(double));
+  const size_t ring_bytes = persistent ? align256((size_t)blocks * ((c.S + kChunkSteps - 1) / kChunkSteps) * 4) : 0;
+  size_t need = part_bytes + (persistent ? persistent_bytes(io.n, io.D) : 0);
+  bool persistent_ok = persistent;
+  int* ring = nullptr;
+  if (persistent) {
+    // the ring (4 B per work item) does not fit the S-independent workspace bound when S is huge: fall back
+    if (workspace_bytes >= need + ring_bytes) {
+      ring = (int*)((char*)workspace + need);
+      need += ring_bytes;
+    } else {
+      persistent_ok = false;
+      need = part_bytes;
+    }
+  }
   if (workspace_bytes < need || workspace == nullptr) {
     set_error("workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
     return NQ_ERR_WORKSPACE;
   }
   io.partials = (double*)workspace;
-  const bool record = io.positions || io.step_works || io.step_logps || io.ckpt_x;
   if (record) NQ_CHECK_ARG(io.D == 0, "per-step recording is only available on the forward entry points");
   if (io.positions) NQ_CHECK_ARG(io.pos_stride >= 1, "pos_stride must be >= 1");
   if (io.ckpt_x) NQ_CHECK_ARG(io.ckpt_rng && io.ckpt_every >= 1, "checkpointing needs ckpt_rng and ckpt_every >= 1");
-  rc = launchers(c.potential).main(c, io, blocks, fast, record, st);
-  NQ_CHECK_ARG(rc == 0, "no kernel for D=%d", io.D);
+  if (persistent_ok) {
+    PersistentCtl ctl;
+    char* base = (char*)workspace + part_bytes;
+    ctl.groups = blocks;
+    ctl.npad = (long long)blocks * kThreads;
+    ctl.chunk = kChunkSteps;
+    ctl.n_chunks = (c.S + kChunkSteps - 1) / kChunkSteps;
+    ctl.state = (uint32_t*)base;
+    const size_t state_bytes = align256((size_t)state_words(kernel_D(io.D)) * ctl.npad * 4);
+    ctl.head = (unsigned int*)(base + state_bytes);
+    ctl.tail = ctl.head + 1;
+    ctl.progress = (int*)(ctl.head + 2);
+    ctl.ring = ring;
+    persistent_init_kernel<<<64, 256, 0, st>>>(ctl);
+    NQ_LAUNCHED();
+    int occ = 0, sms = 0, dev = 0;
+    NQ_CUDA(cudaGetDevice(&dev));
+    NQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    rc = launchers(c.potential).persistent(c, io, ctl, 0, fast, st, &occ);
+    NQ_CHECK_ARG(rc == 0 && occ > 0, "no persistent kernel for D=%d", io.D);
+    // fewer resident CTAs than chains, the same number on every SM
+    long long per_sm = blocks / sms;
+    if (per_sm > occ) per_sm = occ;
+    if (per_sm < 1) per_sm = 1;
+    rc = launchers(c.potential).persistent(c, io, ctl, (int)(per_sm * sms), fast, st, nullptr);
+    NQ_CHECK_ARG(rc == 0, "no persistent kernel for D=%d", io.D);
+  } else {
+    rc = launchers(c.potential).main(c, io, blocks, fast, record, st);
+    NQ_CHECK_ARG(rc == 0, "no kernel for D=%d", io.D);
+  }
   NQ_LAUNCHED();
   if (moments || grad_sums) {
     langevin_finalize_kernel<<<1, 128, 0, st>>>(io.partials, blocks, NV, (NV - 8) / 2, io.D, moments, grad_sums);
@@ -130,7 +209,8 @@ extern "C" size_t nq_langevin_workspace_bytes(int64_t n, int32_t D) {
   if (D < 0) D = 0;
   if (D > 32) D = 32;
   const size_t blocks = (size_t)((n + kThreads - 1) / kThreads);
-  return blocks * partial_row(D) * sizeof(double);
+  // + ring of work items for up to 256 chunks of kChunkSteps steps (S <= 131072); longer runs use the static kernel
+  return align256(blocks * partial_row(D) * sizeof(double)) + persistent_bytes(n, D) + align256(blocks * 256 * 4);
 }
 
 extern "C" int nq_langevin_forward(const NqLangevinDesc* desc, const float* r_table, const float* x0,

@@ -22,6 +22,9 @@
 #ifndef NQ_TF_FORCE_IMAD
 #define NQ_TF_FORCE_IMAD 0
 #endif
+#ifndef NQ_TF_WIDE_MASK
+#define NQ_TF_WIDE_MASK 0
+#endif
 
 #include "nq_common.cuh"
 
@@ -42,7 +45,10 @@ struct LangevinConsts {
   float nu, dt, sigma, inv_sigma, log_norm, box;
   float ca;     // nu*dt*k_s/sigma : d logp_k / d r_k = z_k * ca
   float nudt;   // nu*dt (fast mode only)
+  uint32_t pow2[8];  // 2^{13,15,26,6,17,29,16,24}: run-time multipliers for the IMAD.WIDE rotates
   uint32_t one;  // = 1 at run time: a multiplier ptxas cannot fold, used to place integer adds on the FMA pipe
+  // FAST-math constants (see fast_mean): log2(e)-scaled exponents, (nu dt / beta)-scaled force terms
+  float f_cl2, f_ncr2, f_nbde2, f_clm, f_crm, f_cu;
   long long S, Neq;
 };
 
@@ -144,9 +150,15 @@ struct RngPipe {
   // state.rng -> pipeline (performs the split of the first step)
   __device__ __forceinline__ void prime(uint32_t r0, uint32_t r1) { split2(r0, r1, k0, k1, s0, s1); }
   // bits for this step's normal draw; advances the chain by one step
-  __device__ __forceinline__ uint32_t next(uint32_t one = 1u) {
+  __device__ __forceinline__ uint32_t next(uint32_t one = 1u, const uint32_t* pow2 = nullptr) {
+    (void)pow2;
     uint32_t bits, unused, n0, n1, t0, t1;
-#if NQ_TF_FORCE_IMAD
+#if NQ_TF_WIDE_MASK
+    threefry2x32_wide<NQ_TF_WIDE_MASK>(key_schedule(s0, s1), 0u, 0u, bits, unused, pow2);
+    const KeySchedule ks = key_schedule(k0, k1);
+    threefry2x32_wide<NQ_TF_WIDE_MASK>(ks, 0u, 2u, n0, t0, pow2);
+    threefry2x32_wide<NQ_TF_WIDE_MASK>(ks, 1u, 3u, n1, t1, pow2);
+#elif NQ_TF_FORCE_IMAD
     threefry2x32_mad(key_schedule(s0, s1), 0u, 0u, bits, unused, one);
     const KeySchedule ks = key_schedule(k0, k1);
     threefry2x32_mad(ks, 0u, 2u, n0, t0, one);
@@ -183,6 +195,91 @@ __device__ __forceinline__ float brownian_apply(const LangevinConsts& c, const L
   return dR;
 }
 
+// ------------------------------------------------------------------------------ FAST-math step
+// The same step with the algebra refactored for instruction count: constants
+// pre-multiplied on the host (log2 e into the exponents, nu*dt/beta into the force), MUFU
+// ex2/lg2/rcp/rsq without denormal fix-ups, sqrt(2) folded into the erfinv coefficients, FMA
+// everywhere.  Agrees with the STRICT step to ~1e-7 per step; not bit-faithful to the reference's
+// operation order.
+__device__ __forceinline__ float ex2_approx(float a) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+__device__ __forceinline__ float lg2_approx(float a) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float a) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+__device__ __forceinline__ float rsq_approx(float a) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+
+// sqrt(2) * erfinv(u) with Giles' polynomials (coefficients pre-scaled by sqrt(2))
+__device__ __forceinline__ float normal_from_bits_fast(uint32_t bits) {
+  const float f = __uint_as_float((bits >> 9) | 0x3F800000u);        // [1, 2)
+  const float u = fmaxf(-0.99999994f, fmaf(2.0f, f, -3.0f));          // uniform on (-1, 1)
+  const float lg = lg2_approx(fmaf(-u, u, 1.0f));                     // log2(1 - u^2)
+  constexpr float S2 = 1.41421356237309504880f;
+  float p;
+  if (lg > -7.2134752044448170f) {                                    // w = -ln(1-u^2) < 5
+    const float w = fmaf(lg, -0.69314718055994531f, -2.5f);
+    p = S2 * 2.81022636e-08f;
+    p = fmaf(p, w, S2 * 3.43273939e-07f);
+    p = fmaf(p, w, S2 * -3.5233877e-06f);
+    p = fmaf(p, w, S2 * -4.39150654e-06f);
+    p = fmaf(p, w, S2 * 0.00021858087f);
+    p = fmaf(p, w, S2 * -0.00125372503f);
+    p = fmaf(p, w, S2 * -0.00417768164f);
+    p = fmaf(p, w, S2 * 0.246640727f);
+    p = fmaf(p, w, S2 * 1.50140941f);
+  } else {
+    const float w0 = lg * -0.69314718055994531f;
+    const float w = fmaf(w0, rsq_approx(w0), -3.0f);                  // sqrt(w) - 3
+    p = S2 * -0.000200214257f;
+    p = fmaf(p, w, S2 * 0.000100950558f);
+    p = fmaf(p, w, S2 * 0.00134934322f);
+    p = fmaf(p, w, S2 * -0.00367342844f);
+    p = fmaf(p, w, S2 * 0.00573950773f);
+    p = fmaf(p, w, S2 * -0.0076224613f);
+    p = fmaf(p, w, S2 * 0.00943887047f);
+    p = fmaf(p, w, S2 * 1.00167406f);
+    p = fmaf(p, w, S2 * 2.83297682f);
+  }
+  return p * u;
+}
+
+// mean displacement F*nu*dt at x for trap centre r
+template <int POT>
+__device__ __forceinline__ float fast_mean(const LangevinConsts& c, float x, float r) {
+  const float u = x - r;
+  if (POT == NQ_POT_SPRING) return -c.f_cu * u;
+  const float ul = POT == NQ_POT_BIOMOLECULE ? x + c.xm : x;
+  const float ur = POT == NQ_POT_BIOMOLECULE ? x - c.xm : x - c.two_xm;
+  const float A = ex2_approx(c.f_cl2 * (ul * ul));                    // exp(cl ul^2)
+  const float B = ex2_approx(fmaf(c.f_ncr2, ur * ur, c.f_nbde2));     // exp(-(cr ur^2 + beta dE))
+  // -dEm/dx * nu dt = (nu dt / beta) (2 cl A ul - 2 cr B ur) / (A + B)
+  const float num = fmaf(c.f_clm, A * ul, -c.f_crm * (B * ur));
+  return fmaf(-c.f_cu, u, num * rcp_approx(A + B));
+}
+
+template <int POT>
+__device__ __forceinline__ float fast_step(const LangevinConsts& c, float& x, uint32_t bits, float r, float& z) {
+  const float mean = fast_mean<POT>(c, x, r);
+  z = normal_from_bits_fast(bits);
+  const float dR = fmaf(z, c.sigma, mean);
+  x += dR;
+  if (c.shift_kind == NQ_SHIFT_PERIODIC) x = py_mod(x, c.box);
+  return dR;
+}
+
 // ------------------------------------------------------------------------------ main kernel
 struct LangevinIO {
   const float* r_table;  // [S+1]
@@ -208,48 +305,79 @@ struct LangevinIO {
 constexpr int pad4(int D) { return (D + 3) / 4 * 4; }
 
 // NV layout of a partial row: [0..7] moments, [8 .. 8+DPS) logP grads, [8+DPS .. 8+2DPS) reparam grads
+// Steps [k_begin, k_end] of the 64 trajectories of group `block`.  first: initialise from x0 / seeds
+// (+ equilibration); otherwise restore the carry from `state`.  last: write the outputs and the
+// group's partial sums; otherwise save the carry.  state layout: [word][npad] (coalesced).
+constexpr int state_words(int D) { return 9 + 2 * (D > 0 ? D : 1); }
+
 template <int POT, bool FAST, int D, bool RECORD>
-__global__ void __launch_bounds__(kThreads, min_blocks(D)) langevin_kernel(const LangevinConsts c, const LangevinIO io) {
+__device__ __forceinline__ void langevin_chunk(const LangevinConsts& c, const LangevinIO& io, long long block,
+                                               long long k_begin, long long k_end, bool first, bool last,
+                                               uint32_t* state, long long npad) {
   constexpr bool GRAD = D > 0;
   constexpr int DA = GRAD ? D : 1;            // accumulators per term
   constexpr int DPS = GRAD ? pad4(D) : 4;     // padded row length in shared memory
   __shared__ float r_s[kTile + 1];
+  __shared__ __align__(16) float4 tab_s[FAST ? kTile : 1];  // FAST: (r_k, a_k, b_k, -) with dW_k = a_k x + b_k
   __shared__ __align__(16) float phi_s[GRAD ? kTile * DPS : 4];
   __shared__ double red_s[kThreads / 32][8 + 2 * DPS];
 
-  const long long gid = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const long long gid = block * kThreads + threadIdx.x;
   const bool live = gid < io.n;
   const long long idx = live ? gid : io.n - 1;
 
-  float x = io.x0[idx];
+  float x;
   RngPipe rng;
-  {
-    // key, split = random.split(key); init(split, ...)     barrier_crossing.py:133,138
-    uint32_t n0, n1, r0, r1;
-    split2(io.seeds[2 * idx], io.seeds[2 * idx + 1], n0, n1, r0, r1);
-    rng.prime(r0, r1);
-  }
-  Landscape<POT, FAST> land;
-  float z, lp;
-  {
-    const float r_eq = io.r_table[0];
-    for (long long e = 0; e < c.Neq; ++e) {  // equilibrate :115-121
-      land.eval(c, x);
-      brownian_apply<POT, FAST>(c, land, x, rng.next(), r_eq, z, lp);
-    }
-  }
-  if (RECORD && io.positions && live) io.positions[gid] = x;      // positions[0] = x_eq  :142
-  if (RECORD && io.step_works && live) io.step_works[gid] = 0.f;  // works[0] = 0        :141
-
   double W = 0.0, LP = 0.0;
   float gA[DA], gB[DA];
+  Landscape<POT, FAST> land;
+  float z, lp;
+  if (first) {
+    x = io.x0[idx];
+    {
+      // key, split = random.split(key); init(split, ...)     barrier_crossing.py:133,138
+      uint32_t n0, n1, r0, r1;
+      split2(io.seeds[2 * idx], io.seeds[2 * idx + 1], n0, n1, r0, r1);
+      rng.prime(r0, r1);
+    }
+    const float r_eq = io.r_table[0];
+    for (long long e = 0; e < c.Neq; ++e) {  // equilibrate :115-121
+      if (FAST) {
+        fast_step<POT>(c, x, rng.next(), r_eq, z);
+      } else {
+        land.eval(c, x);
+        brownian_apply<POT, FAST>(c, land, x, rng.next(), r_eq, z, lp);
+      }
+    }
+    if (RECORD && io.positions && live) io.positions[gid] = x;      // positions[0] = x_eq  :142
+    if (RECORD && io.step_works && live) io.step_works[gid] = 0.f;  // works[0] = 0        :141
 #pragma unroll
-  for (int j = 0; j < DA; ++j) gA[j] = gB[j] = 0.f;
+    for (int j = 0; j < DA; ++j) gA[j] = gB[j] = 0.f;
+  } else {
+    const uint32_t* sp = state + idx;
+    x = __uint_as_float(sp[0]);
+    rng.k0 = sp[npad]; rng.k1 = sp[2 * npad]; rng.s0 = sp[3 * npad]; rng.s1 = sp[4 * npad];
+    W = __hiloint2double((int)sp[6 * npad], (int)sp[5 * npad]);
+    LP = __hiloint2double((int)sp[8 * npad], (int)sp[7 * npad]);
+#pragma unroll
+    for (int j = 0; j < DA; ++j) {
+      gA[j] = __uint_as_float(sp[(9 + j) * npad]);
+      gB[j] = __uint_as_float(sp[(9 + DA + j) * npad]);
+    }
+  }
 
-  for (long long t0 = 1; t0 <= c.S; t0 += kTile) {
-    const int len = (int)min((long long)kTile, c.S - t0 + 1);
+  for (long long t0 = k_begin; t0 <= k_end; t0 += kTile) {
+    const int len = (int)min((long long)kTile, k_end - t0 + 1);
     __syncthreads();
     for (int i = threadIdx.x; i <= len; i += kThreads) r_s[i] = io.r_table[t0 - 1 + i];
+    if (FAST) {
+      // dW_k = (k_s/2)[(x-r_k)^2 - (x-r_{k-1})^2] = a_k x + b_k,  a_k = k_s (r_{k-1} - r_k),  b_k = -a_k (r_{k-1} + r_k)/2
+      for (int i = threadIdx.x; i < len; i += kThreads) {
+        const float r0 = io.r_table[t0 - 1 + i], r1 = io.r_table[t0 + i];
+        const float a = 2.0f * c.hk * (r0 - r1);
+        tab_s[i] = make_float4(r1, a, -0.5f * a * (r0 + r1), 0.f);
+      }
+    }
     if (GRAD) {
       // phi row for step k is k-1 (k = 1..S-1); step S (fixed end point) contributes nothing
       for (int i = threadIdx.x; i < len * DPS; i += kThreads) {
@@ -262,8 +390,9 @@ __global__ void __launch_bounds__(kThreads, min_blocks(D)) langevin_kernel(const
     float Wt = 0.f, LPt = 0.f;
     uint32_t r_addr = (uint32_t)__cvta_generic_to_shared(r_s);
     uint32_t phi_addr = (uint32_t)__cvta_generic_to_shared(phi_s);
+    uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(tab_s);
 #pragma unroll kUnroll
-    for (int i = 0; i < len; ++i, r_addr += 4, phi_addr += 4 * DPS) {
+    for (int i = 0; i < len; ++i, r_addr += 4, phi_addr += 4 * DPS, tab_addr += 16) {
       if (RECORD && io.ckpt_x) {  // checkpoint BEFORE step k = t0+i when (k-1) % ckpt_every == 0
         const long long k = t0 + i;
         if ((k - 1) % io.ckpt_every == 0 && live) {
@@ -273,10 +402,18 @@ __global__ void __launch_bounds__(kThreads, min_blocks(D)) langevin_kernel(const
           dst[0] = rng.k0; dst[io.n] = rng.k1; dst[2 * io.n] = rng.s0; dst[3 * io.n] = rng.s1;
         }
       }
-      const float r_prev = lds_f32(r_addr), r_cur = lds_f32(r_addr + 4);
-      land.eval(c, x);
-      const float dW = work_increment<POT, FAST>(c, land, x, r_prev, r_cur);
-      const float dR = brownian_apply<POT, FAST>(c, land, x, rng.next(c.one), r_cur, z, lp);
+      float dW, dR;
+      if (FAST) {
+        const float4 tab = lds_f32x4(tab_addr);
+        dW = fmaf(tab.y, x, tab.z);
+        dR = fast_step<POT>(c, x, rng.next(c.one, c.pow2), tab.x, z);
+        if (RECORD) lp = fmaf(-0.5f * z, z, -c.log_norm);
+      } else {
+        const float r_prev = lds_f32(r_addr), r_cur = lds_f32(r_addr + 4);
+        land.eval(c, x);
+        dW = work_increment<POT, FAST>(c, land, x, r_prev, r_cur);
+        dR = brownian_apply<POT, FAST>(c, land, x, rng.next(c.one, c.pow2), r_cur, z, lp);
+      }
       Wt += dW;
       if (FAST && !RECORD) {
         LPt = fmaf(z, z, LPt);  // sum of z^2; turned into the log-prob sum at the end of the tile
@@ -313,6 +450,21 @@ __global__ void __launch_bounds__(kThreads, min_blocks(D)) langevin_kernel(const
     } else {
       LP += (double)LPt;
     }
+  }
+  if (!last) {
+    if (live) {
+      uint32_t* sp = state + gid;
+      sp[0] = __float_as_uint(x);
+      sp[npad] = rng.k0; sp[2 * npad] = rng.k1; sp[3 * npad] = rng.s0; sp[4 * npad] = rng.s1;
+      sp[5 * npad] = (uint32_t)__double2loint(W); sp[6 * npad] = (uint32_t)__double2hiint(W);
+      sp[7 * npad] = (uint32_t)__double2loint(LP); sp[8 * npad] = (uint32_t)__double2hiint(LP);
+#pragma unroll
+      for (int j = 0; j < DA; ++j) {
+        sp[(9 + j) * npad] = __float_as_uint(gA[j]);
+        sp[(9 + DA + j) * npad] = __float_as_uint(gB[j]);
+      }
+    }
+    return;
   }
 #pragma unroll
   for (int j = 0; j < DA; ++j) {
@@ -358,7 +510,87 @@ __global__ void __launch_bounds__(kThreads, min_blocks(D)) langevin_kernel(const
     double s = 0.0;
 #pragma unroll
     for (int w = 0; w < kThreads / 32; ++w) s += red_s[w][threadIdx.x];
-    io.partials[(long long)blockIdx.x * NV + threadIdx.x] = s;
+    io.partials[block * NV + threadIdx.x] = s;
+  }
+}
+
+template <int POT, bool FAST, int D, bool RECORD>
+__global__ void __launch_bounds__(kThreads, min_blocks(D)) langevin_kernel(const LangevinConsts c, const LangevinIO io) {
+  langevin_chunk<POT, FAST, D, RECORD>(c, io, blockIdx.x, 1, c.S, true, true, nullptr, 0);
+}
+
+// Persistent variant with a FIFO ready-queue of trajectory groups ("chains").  With 1e5
+// trajectories there are 3125 warps for 592 SM sub-partitions: a static launch leaves some with 6
+// warps and some with 5 for the whole run (makespan 6 units for an average of 5.28).  Here fewer
+// CTAs than chains are resident (the same number on every SM); each CTA pops a chain, advances it
+// by one chunk of steps, saves the carry and pushes the chain back, so chains rotate over all SMs
+// and every sub-partition carries the same load all the time.
+//   ring[t]  : chain id served by pop ticket t (-1 until published); tickets 0..groups-1 are
+//              pre-filled, every completed non-final chunk publishes one more entry;
+//   n_items  = groups * n_chunks tickets in total, so a pop on an unpublished entry always has a
+//              running chunk that will publish it: waits terminate.
+struct PersistentCtl {
+  unsigned int* head;        // pop tickets handed out
+  unsigned int* tail;        // push tickets handed out (starts at groups)
+  int* ring;                 // [groups * n_chunks]
+  int* progress;             // [groups] chunks completed
+  uint32_t* state;           // [state_words][npad]
+  long long groups, npad, chunk, n_chunks;
+};
+
+static __global__ void persistent_init_kernel(PersistentCtl ctl) {
+  const long long n_items = ctl.groups * ctl.n_chunks;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += (long long)gridDim.x * blockDim.x) {
+    ctl.ring[i] = i < ctl.groups ? (int)i : -1;
+    if (i < ctl.groups) ctl.progress[i] = 0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *ctl.head = 0u;
+    *ctl.tail = (unsigned int)ctl.groups;
+  }
+}
+
+template <int POT, bool FAST, int D>
+__global__ void __launch_bounds__(kThreads, min_blocks(D)) langevin_persistent_kernel(const LangevinConsts c,
+                                                                                      const LangevinIO io,
+                                                                                      const PersistentCtl ctl) {
+  __shared__ int chain_s, chunk_s;
+  const unsigned long long n_items = (unsigned long long)ctl.groups * ctl.n_chunks;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int t = atomicAdd(ctl.head, 1u);
+      int g = -2;
+      if (t < n_items) {
+        volatile int* slot = ctl.ring + t;
+        unsigned int spins = 0;
+        while ((g = *slot) < 0) {
+          __nanosleep(100);
+          if (++spins > (1u << 25)) __trap();  // > 3 s: a scheduling bug must fail loudly, never hang the GPU
+        }
+        __threadfence();
+        chunk_s = ctl.progress[g];
+      }
+      chain_s = g;
+    }
+    __syncthreads();
+    const long long g = chain_s;
+    if (g < 0) return;
+    const long long ch = chunk_s;
+    const long long k_begin = ch * ctl.chunk + 1;
+    const long long k_end = min(c.S, (ch + 1) * ctl.chunk);
+    const bool last = ch == ctl.n_chunks - 1;
+    langevin_chunk<POT, FAST, D, false>(c, io, g, k_begin, k_end, ch == 0, last, ctl.state, ctl.npad);
+    if (!last) {
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        ctl.progress[g] = (int)ch + 1;
+        __threadfence();
+        const unsigned int s = atomicAdd(ctl.tail, 1u);
+        atomicExch(ctl.ring + s, (int)g);
+      }
+    }
   }
 }
 
@@ -403,12 +635,15 @@ __global__ void __launch_bounds__(128) replay_kernel(const LangevinConsts c, con
     const long long k = k_first + i;
     const float r_prev = io.r_table[k - 1], r_cur = io.r_table[k];
     const float x_before = x;
-    land.eval(c, x);
-    const float dR = brownian_apply<POT, FAST>(c, land, x, rng.next(), r_cur, z, lp);
+    if (FAST) {
+      fast_step<POT>(c, x, rng.next(), r_cur, z);
+    } else {
+      land.eval(c, x);
+      brownian_apply<POT, FAST>(c, land, x, rng.next(), r_cur, z, lp);
+    }
     // dW_k = E(x_{k-1}; r_k) - E(x_{k-1}; r_{k-1}):  d/dr_k = -k_s (x_{k-1} - r_k), d/dr_{k-1} = +k_s (x_{k-1} - r_{k-1})
     double g_cur = (double)lb * (double)(z * c.ca) - (double)wb * (double)(c.k_s * (x_before - r_cur));
     double g_prev = (double)wb * (double)(c.k_s * (x_before - r_prev));
-    (void)dR;
     g_cur = warp_sum(g_cur);
     g_prev = warp_sum(g_prev);
     if (lane == 0) {
@@ -440,8 +675,12 @@ __global__ void __launch_bounds__(kThreads) stationary_kernel(const LangevinCons
   Landscape<POT, FAST> land;
   float z, lp;
   for (long long s = 0; s < c.S; ++s) {
-    land.eval(c, x);
-    brownian_apply<POT, FAST>(c, land, x, rng.next(), r0, z, lp);
+    if (FAST) {
+      fast_step<POT>(c, x, rng.next(), r0, z);
+    } else {
+      land.eval(c, x);
+      brownian_apply<POT, FAST>(c, land, x, rng.next(), r0, z, lp);
+    }
     if (positions) positions[s * n + gid] = x;
   }
   if (x_final) x_final[gid] = x;
@@ -459,8 +698,13 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const LangevinConsts c,
   threefry2x32(key_schedule(s0, s1), 0u, 0u, bits, unused);
   Landscape<POT, FAST> land;
   float z, lp;
-  land.eval(c, x);
-  brownian_apply<POT, FAST>(c, land, x, bits, r0, z, lp);
+  if (FAST) {
+    fast_step<POT>(c, x, bits, r0, z);
+    lp = fmaf(-0.5f * z, z, -c.log_norm);
+  } else {
+    land.eval(c, x);
+    brownian_apply<POT, FAST>(c, land, x, bits, r0, z, lp);
+  }
   x_io[gid] = x;
   rng_io[2 * gid] = n0;
   rng_io[2 * gid + 1] = n1;
@@ -469,6 +713,8 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const LangevinConsts c,
 
 // per-potential launchers (defined in langevin_pot*.cu through NQ_DEFINE_POT_LAUNCHERS)
 using MainLauncher = int (*)(const LangevinConsts&, const LangevinIO&, int blocks, bool fast, bool record, cudaStream_t);
+using PersistentLauncher = int (*)(const LangevinConsts&, const LangevinIO&, const PersistentCtl&, int blocks, bool fast,
+                                   cudaStream_t, int* max_blocks_per_sm);
 using ReplayLauncher = int (*)(const LangevinConsts&, const ReplayIO&, dim3 grid, size_t smem, bool fast, cudaStream_t);
 using StationaryLauncher = int (*)(const LangevinConsts&, float r0, const float*, const uint32_t*, long long, float*,
                                    float*, int blocks, bool fast, cudaStream_t);
@@ -479,6 +725,16 @@ using ApplyLauncher = int (*)(const LangevinConsts&, float r0, float*, uint32_t*
   case DD:                                                                                             \
     if (fast) langevin_kernel<POT, true, DD, false><<<blocks, kThreads, 0, st>>>(c, io);               \
     else langevin_kernel<POT, false, DD, false><<<blocks, kThreads, 0, st>>>(c, io);                   \
+    break;
+
+// occ != nullptr: only report resident CTAs per SM (no launch)
+#define NQ_PERSIST_CASE(POT, DD)                                                                       \
+  case DD:                                                                                             \
+    if (occ) {                                                                                         \
+      if (fast) cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, langevin_persistent_kernel<POT, true, DD>, kThreads, 0);  \
+      else cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, langevin_persistent_kernel<POT, false, DD>, kThreads, 0);      \
+    } else if (fast) langevin_persistent_kernel<POT, true, DD><<<blocks, kThreads, 0, st>>>(c, io, ctl); \
+    else langevin_persistent_kernel<POT, false, DD><<<blocks, kThreads, 0, st>>>(c, io, ctl);          \
     break;
 
 #define NQ_DEFINE_POT_LAUNCHERS(POT, NAME)                                                             \
@@ -498,6 +754,16 @@ using ApplyLauncher = int (*)(const LangevinConsts&, float r0, float*, uint32_t*
       NQ_MAIN_CASE(POT, 4) NQ_MAIN_CASE(POT, 8) NQ_MAIN_CASE(POT, 12) NQ_MAIN_CASE(POT, 13)            \
       NQ_MAIN_CASE(POT, 16) NQ_MAIN_CASE(POT, 20) NQ_MAIN_CASE(POT, 24) NQ_MAIN_CASE(POT, 28)          \
       NQ_MAIN_CASE(POT, 32)                                                                            \
+      default: return -1;                                                                              \
+    }                                                                                                  \
+    return 0;                                                                                          \
+  }                                                                                                    \
+  int NAME##_persistent(const LangevinConsts& c, const LangevinIO& io, const PersistentCtl& ctl,       \
+                        int blocks, bool fast, cudaStream_t st, int* occ) {                            \
+    switch (io.D == 0 ? 0 : (io.D <= 13 && io.D > 12 ? 13 : pad4(io.D))) {                             \
+      NQ_PERSIST_CASE(POT, 0) NQ_PERSIST_CASE(POT, 4) NQ_PERSIST_CASE(POT, 8) NQ_PERSIST_CASE(POT, 12) \
+      NQ_PERSIST_CASE(POT, 13) NQ_PERSIST_CASE(POT, 16) NQ_PERSIST_CASE(POT, 20)                       \
+      NQ_PERSIST_CASE(POT, 24) NQ_PERSIST_CASE(POT, 28) NQ_PERSIST_CASE(POT, 32)                       \
       default: return -1;                                                                              \
     }                                                                                                  \
     return 0;                                                                                          \
@@ -523,6 +789,8 @@ using ApplyLauncher = int (*)(const LangevinConsts&, float r0, float*, uint32_t*
 
 #define NQ_DECLARE_POT_LAUNCHERS(NAME)                                                                 \
   int NAME##_main(const LangevinConsts&, const LangevinIO&, int, bool, bool, cudaStream_t);            \
+  int NAME##_persistent(const LangevinConsts&, const LangevinIO&, const PersistentCtl&, int, bool,    \
+                        cudaStream_t, int*);                                                          \
   int NAME##_replay(const LangevinConsts&, const ReplayIO&, dim3, size_t, bool, cudaStream_t);         \
   int NAME##_stationary(const LangevinConsts&, float, const float*, const uint32_t*, long long, float*, \
                         float*, int, bool, cudaStream_t);                                              \

@@ -13,6 +13,7 @@ import torch
 from oracle import jaxlike as J, langevin_ref as L
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'langevin.npz'))
 POS_RTOL = 1e-5
 GRAD_RTOL = 1e-4
@@ -269,3 +270,65 @@ def test_replay_per_step_gradient_vs_oracle(cuda):
   a = z / sc.sigma * sc.nu * sc.dt * np.float32(1.3)
   expect = (o['total_work'][:, None].astype(np.float64) * a + 1.3 * o['traj']['dR']).sum(0)   # k = 1..S
   assert rel(gbar[1:S], expect[:S - 1]) < 1e-5
+
+
+def test_fast_math_mode_parity_is_statistical(cuda):
+  """NQ_MATH_FAST refactors the step algebra (MUFU, FMA, folded constants): every step differs from
+  the reference order at the 1e-7 level and double-well trajectories amplify that while they sit
+  on the barrier top, so the max over the ensemble is not bounded by 1e-5.  What is asserted:
+  99.9 % of all positions within 1e-5 relative, 99.999 % within 1e-3, work within 2e-5, ensemble-mean
+  work within 2e-6 and gradients within 1e-4."""
+  from noneq_opt_b200 import barrier_crossing as bc, random as nqr, space
+  _, shift = space.free()
+  B, S = 256, 2000
+  coeffs = np.array([20., 19.95996, 0.3, -0.2, 0.1, 0.05, 0., 0., 0., 0., 0., 0., 0.01], np.float32)
+  pot_o = L.V_biomolecule_shifted(KAPPA, KAPPA, XM, 0., 1.5, BETA)
+  pot_g = bc.V_biomolecule_shifted(KAPPA, KAPPA, XM, 0., 1.5, BETA)
+  x0 = np.zeros(B, np.float32)
+  o = L.estimate_gradient(pot_o, coeffs, x0, J.PRNGKey(0), 0., 40., 0, S, 1e-8, KT, 1.0, KT / 1e7, record=True)
+  seeds = nqr.split(J.PRNGKey(0), B)
+  bc.set_math_mode('fast')
+  try:
+    g = bc.gradient_terms(pot_g, coeffs, x0, seeds, 0., 40., 0, shift, S, 1e-8, KT, 1.0, KT / 1e7)
+    pos, lps, works = bc.run_brownian_opt(pot_g, coeffs, x0.reshape(B, 1, 1), 0., 40., 0, shift, seeds, S, 1e-8, KT, 1.0,
+                                          KT / 1e7)
+  finally:
+    bc.set_math_mode('strict')
+  ref = o['traj']['positions']
+  err = np.abs(pos.cpu().numpy()[..., 0, 0] - ref) / np.abs(ref).max()
+  assert np.quantile(err, 0.999) < POS_RTOL and np.quantile(err, 0.99999) < 1e-3
+  w = g['work'].cpu().numpy()
+  assert rel(w, o['total_work']) < 2e-5
+  assert abs(w.astype(np.float64).mean() / o['total_work'].astype(np.float64).mean() - 1) < 2e-6
+  assert rel(works.cpu().numpy().sum(1), o['total_work']) < 2e-5
+  assert rel(lps.cpu().numpy(), o['traj']['log_probs']) < 1e-4
+  gs = g['grad_sums'].cpu().numpy() / B
+  assert rel(gs[0], o['grad_logP']) < GRAD_RTOL and rel(gs[1], o['grad_reparam']) < GRAD_RTOL
+
+
+def test_persistent_scheduler_matches_static_launch(cuda):
+  """NQ_PERSISTENT=1 (FIFO ready-queue of trajectory groups, carry handed over through HBM every 512
+  steps) must reproduce the static launch bit for bit."""
+  import subprocess, sys, json
+  code = r"""
+import json, sys, numpy as np, torch
+sys.path.insert(0, %r)
+from noneq_opt_b200 import barrier_crossing as bc, random as nqr, space
+_, shift = space.free()
+KT = 4.183; BETA = 1 / KT; XM = 14.; KAPPA = 21.3863 / (BETA * XM ** 2)
+pot = bc.V_biomolecule_shifted(KAPPA, KAPPA, XM, 0., 1.5, BETA)
+B, S = 148 * 64 * 2 + 37, 1300
+coeffs = np.array([20., 19.9, 0.4, -0.2, 0.1], np.float32)
+seeds = nqr.split(nqr.PRNGKey(5), B)
+g = bc.gradient_terms(pot, coeffs, torch.zeros(B, device='cuda'), seeds, 0., 40., 3, shift, S, 1e-8, KT, 1.0, KT / 1e7)
+print(json.dumps(dict(work=g['work'].double().sum().item(), w3=g['work'][:3].tolist(), logp=g['logp'].double().sum().item(),
+                      grad=g['grad_sums'].cpu().numpy().tolist(), mom=g['moments'].cpu().numpy().tolist())))
+""" % ROOT
+  import os
+  outs = []
+  for flag in ('0', '1'):
+    env = dict(os.environ, NQ_PERSISTENT=flag)
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+  assert outs[0] == outs[1]
