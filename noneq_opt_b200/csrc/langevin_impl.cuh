@@ -225,7 +225,9 @@ __device__ __forceinline__ float rsq_approx(float a) {
 // sqrt(2) * erfinv(u) with Giles' polynomials (coefficients pre-scaled by sqrt(2))
 __device__ __forceinline__ float normal_from_bits_fast(uint32_t bits) {
   const float f = __uint_as_float((bits >> 9) | 0x3F800000u);        // [1, 2)
-  const float u = fmaxf(-0.99999994f, fmaf(2.0f, f, -3.0f));          // uniform on (-1, 1)
+  // 2(f-1) + nextafter(-1,0) in one exact FMA plus one rounding: bit-identical to jax's uniform(-1,1)
+  // (2f - 3 is exact; adding 2^-24 rounds the same real number jax rounds), and never below -1 + 2^-24
+  const float u = fmaf(2.0f, f, -3.0f) + 5.9604644775390625e-8f;
   const float lg = lg2_approx(fmaf(-u, u, 1.0f));                     // log2(1 - u^2)
   constexpr float S2 = 1.41421356237309504880f;
   float p;

@@ -308,6 +308,29 @@ def _summary_from(run: _Run, batched: bool) -> IsingSummary:
   return IsingSummary(*[(s[f] if batched else s[f, 0]) for f in range(_lib.NQ_IS_NSUMMARY)])
 
 
+def masked_update(state: IsingState, new_params: IsingParameters, mask, seed):
+  """Random update of the sites selected by an arbitrary `mask` (ising.py:109-126), returning
+  (new_state, forward_log_prob, reverse_log_prob).  This is the reference's building block of
+  `update`; with a caller-supplied mask it cannot use the checkerboard kernel, so it is evaluated
+  with torch ops on the GPU from the same jax-matched uniforms (`random.uniform`).  The hot path is
+  `update` / `simulate_ising`."""
+  spins = _as_cuda(state.spins)
+  s = spins.to(torch.float32)
+  m = _as_cuda(mask).to(torch.float32)
+  logits = flip_logits(s, new_params)
+  u = nqrandom.uniform(seed, tuple(s.shape))
+  flips = (u < torch.sigmoid(logits)).to(torch.float32) * m
+  log_sig = torch.nn.functional.logsigmoid
+
+  def bern_log_prob(lg):
+    return (1 - flips) * log_sig(-lg) + flips * log_sig(lg)
+
+  forward_log_prob = (bern_log_prob(logits) * m).sum()
+  new_spins = s * (1 - 2 * flips)
+  reverse_log_prob = (bern_log_prob(flip_logits(new_spins, new_params)) * m).sum()
+  return IsingState(new_spins.to(spins.dtype), new_params), forward_log_prob, reverse_log_prob
+
+
 def update(state: IsingState, new_params: IsingParameters, seed):
   """One sweep: both checkerboard half-sweeps with (seed_even, seed_odd) = split(seed, 2)."""
   device = _lib.require_cuda()

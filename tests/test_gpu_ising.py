@@ -209,3 +209,22 @@ def test_shape_errors(cuda):
     ising.simulate_ising(p, -np.ones((8, 8), np.int32), J.PRNGKey(0), checkpoint_every=5)
   with pytest.raises(NotImplementedError):
     ising.simulate_ising(p, -np.ones((8,), np.int32), J.PRNGKey(0))
+
+
+def test_masked_update_building_block(cuda):
+  """ising.masked_update (ising.py:109-126) with the reference's own masks reproduces update()."""
+  from noneq_opt_b200 import ising, random as nqr
+  L = 64
+  s0 = ising.random_spins([L, L], .5, J.PRNGKey(4))
+  params = ising.IsingParameters(np.float32(0.2), np.float32(-0.3))
+  seed = J.PRNGKey(12)
+  seed_even, seed_odd = nqr.split_host(seed, 2)
+  mask_even, mask_odd = ising.even_odd_masks((L, L))
+  st, ef, er = ising.masked_update(ising.IsingState(s0, params), params, mask_even, seed_even)
+  st, of, orv = ising.masked_update(st, params, mask_odd, seed_odd)
+  ref, summ = ising.update(ising.IsingState(s0, params), params, seed)
+  np.testing.assert_array_equal(st.spins.cpu().numpy(), ref.spins.cpu().numpy())
+  np.testing.assert_allclose(float(ef + of), float(summ.forward_log_prob), rtol=2e-5)
+  np.testing.assert_allclose(float(er + orv), float(summ.reverse_log_prob), rtol=2e-5)
+  s_o, f_o, r_o, _, _ = I.masked_update(s0.cpu().numpy(), 0.2, -0.3, mask_even, seed_even)
+  np.testing.assert_allclose(float(ef), f_o, rtol=2e-5)

@@ -276,7 +276,7 @@ def test_fast_math_mode_parity_is_statistical(cuda):
   """NQ_MATH_FAST refactors the step algebra (MUFU, FMA, folded constants): every step differs from
   the reference order at the 1e-7 level and double-well trajectories amplify that while they sit
   on the barrier top, so the max over the ensemble is not bounded by 1e-5.  What is asserted:
-  99.9 % of all positions within 1e-5 relative, 99.999 % within 1e-3, work within 2e-5, ensemble-mean
+  99.9 % of all positions within 1e-5 relative, 99.999 % within 1e-3, 99 % of works within 1e-5, ensemble-mean
   work within 2e-6 and gradients within 1e-4."""
   from noneq_opt_b200 import barrier_crossing as bc, random as nqr, space
   _, shift = space.free()
@@ -298,10 +298,12 @@ def test_fast_math_mode_parity_is_statistical(cuda):
   err = np.abs(pos.cpu().numpy()[..., 0, 0] - ref) / np.abs(ref).max()
   assert np.quantile(err, 0.999) < POS_RTOL and np.quantile(err, 0.99999) < 1e-3
   w = g['work'].cpu().numpy()
-  assert rel(w, o['total_work']) < 2e-5
+  werr = np.abs(w - o['total_work']) / np.abs(o['total_work']).max()
+  assert np.quantile(werr, 0.99) < POS_RTOL and werr.max() < 1e-3     # the diverged trajectory also moves its W
   assert abs(w.astype(np.float64).mean() / o['total_work'].astype(np.float64).mean() - 1) < 2e-6
-  assert rel(works.cpu().numpy().sum(1), o['total_work']) < 2e-5
-  assert rel(lps.cpu().numpy(), o['traj']['log_probs']) < 1e-4
+  assert np.quantile(np.abs(works.cpu().numpy().sum(1) - o['total_work']) / np.abs(o['total_work']).max(), 0.99) < 2e-5
+  lerr = np.abs(lps.cpu().numpy() - o['traj']['log_probs']) / np.abs(o['traj']['log_probs']).max()
+  assert np.quantile(lerr, 0.999) < 1e-4
   gs = g['grad_sums'].cpu().numpy() / B
   assert rel(gs[0], o['grad_logP']) < GRAD_RTOL and rel(gs[1], o['grad_reparam']) < GRAD_RTOL
 
