@@ -29,6 +29,12 @@
 
 namespace nq {
 
+#ifndef NQ_ISING_MINB
+#define NQ_ISING_MINB 4
+#endif
+#ifndef NQ_ISING_BLOCKS_PER_ITER
+#define NQ_ISING_BLOCKS_PER_ITER 8
+#endif
 constexpr int kIsingClasses = 16;  // class = 8*(spin up) + (#up neighbours 0..4)
 
 // ------------------------------------------------------------------------------ bit helpers
@@ -126,14 +132,19 @@ __device__ __forceinline__ void load_planes(const uint32_t* lat, const IsingShap
 
 // 8 sites -> nibble word of class indices (8*s + cnt), via the pre-shifted spread tables
 __device__ __forceinline__ uint32_t class_nibbles(const uint32_t* spread, const Planes& p, int q) {
-  const int sh = 8 * q;
-  return spread[3 * 256 + ((p.S >> sh) & 0xff)] | spread[2 * 256 + ((p.C2 >> sh) & 0xff)] |
-         spread[1 * 256 + ((p.C1 >> sh) & 0xff)] | spread[((p.C0 >> sh) & 0xff)];
+  const uint32_t sel = 0x4440u | (uint32_t)q;  // byte q, zero-extended
+  return spread[3 * 256 + __byte_perm(p.S, 0, sel)] | spread[2 * 256 + __byte_perm(p.C2, 0, sel)] |
+         spread[1 * 256 + __byte_perm(p.C1, 0, sel)] | spread[__byte_perm(p.C0, 0, sel)];
 }
 
-__device__ __forceinline__ uint32_t thr_of(const uint32_t* thr_s, uint32_t packed4, int byte) {
-  const uint32_t off = __byte_perm(packed4, 0, 0x4440 | byte);  // 4*class, zero-extended
-  return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(thr_s) + off);
+// thresholds of the two sites whose class nibbles form byte `byte` of N: one 64-bit lookup in the
+// per-sweep pair table thr2[256] = {thr[b & 15], thr[b >> 4]}
+__device__ __forceinline__ uint2 thr_pair(const uint2* thr2, uint32_t N, int byte) {
+  return thr2[__byte_perm(N, 0, 0x4440 | byte)];
+}
+
+__device__ __forceinline__ void build_pair_table(uint2* dst, const uint32_t* thr16, int tid, int tsize) {
+  for (int b = tid; b < 256; b += tsize) dst[b] = make_uint2(thr16[b & 15], thr16[b >> 4]);
 }
 
 // per-class popcounts of active and flipped sites of one word
@@ -151,7 +162,7 @@ __device__ __forceinline__ void histogram(const Planes& p, uint32_t F, int (&hA)
 
 // One unit = word w of rows i and i+L/2 of colour c: 32 threefry blocks, 64 site updates.
 __device__ __forceinline__ void update_unit(uint32_t* lat, const IsingShape& sh, const uint32_t* spread,
-                                            const uint32_t* thr_s, const KeySchedule& ks, int c, int i, int w,
+                                            const uint2* thr2, const KeySchedule& ks, int c, int i, int w,
                                             int (&hA)[10], int (&hF)[10]) {
   const int L = sh.L, NW = sh.NW, i2 = i + L / 2;
   Planes pa, pb;
@@ -160,25 +171,44 @@ __device__ __forceinline__ void update_unit(uint32_t* lat, const IsingShape& sh,
   const int off = c == 0 ? 1 - (i & 1) : (i & 1);
   const uint32_t cbase = (uint32_t)i * L + 2u * (32u * w) + off;
   const uint32_t half = (uint32_t)L * L / 2;
-  uint32_t Fa = 0, Fb = 0;
+  // Sites are visited from 31 down to 0 so that the acceptance bits can be shifted in from the
+  // right: accept <=> (bits >> 9) - thr < 0, and one funnel shift moves that sign bit into the mask
+  // (the subtraction can issue on the FMA pipe; the ALU pipe, which bounds this kernel, sees one
+  // shift instead of compare + select + or).
+  uint32_t Fa = 0, Fb = 0, Na = 0, Nb = 0;
+#if NQ_ISING_BLOCKS_PER_ITER == 8
 #pragma unroll 1
-  for (int q = 0; q < 4; ++q) {
-    const uint32_t Na = class_nibbles(spread, pa, q), Nb = class_nibbles(spread, pb, q);
-    const uint32_t ea = (Na << 2) & 0x3C3C3C3Cu, oa = (Na >> 2) & 0x3C3C3C3Cu;
-    const uint32_t eb = (Nb << 2) & 0x3C3C3C3Cu, ob = (Nb >> 2) & 0x3C3C3C3Cu;
-    uint32_t fa = 0, fb = 0;
+  for (int q = 3; q >= 0; --q) {
+    Na = class_nibbles(spread, pa, q);
+    Nb = class_nibbles(spread, pb, q);
 #pragma unroll
-    for (int s = 0; s < 8; ++s) {
-      const uint32_t ctr = cbase + 2u * (8u * q + s);
-      uint32_t y0, y1;
-      threefry2x32(ks, ctr, ctr + half, y0, y1);
-      const uint32_t ta = thr_of(thr_s, (s & 1) ? oa : ea, s >> 1);
-      const uint32_t tb = thr_of(thr_s, (s & 1) ? ob : eb, s >> 1);
-      fa |= ((y0 >> 9) < ta) ? (1u << s) : 0u;
-      fb |= ((y1 >> 9) < tb) ? (1u << s) : 0u;
+    for (int j = 3; j >= 0; --j) {
+#else
+  // 4 threefry blocks (8 site updates) per loop iteration: a ~5 KB body that stays in the
+  // instruction cache when several warps of a sub-partition are in different phases
+#pragma unroll 1
+  for (int qq = 7; qq >= 0; --qq) {
+    const int q = qq >> 1;
+    if (qq & 1) {
+      Na = class_nibbles(spread, pa, q);
+      Nb = class_nibbles(spread, pb, q);
     }
-    Fa |= fa << (8 * q);
-    Fb |= fb << (8 * q);
+#pragma unroll
+    for (int jj = 1; jj >= 0; --jj) {
+      const int j = 2 * (qq & 1) + jj;
+#endif
+      const uint2 ta = thr_pair(thr2, Na, j), tb = thr_pair(thr2, Nb, j);
+#pragma unroll
+      for (int e = 1; e >= 0; --e) {
+        const uint32_t ctr = cbase + 2u * (8u * q + 2u * j + e);
+        uint32_t y0, y1;
+        threefry2x32(ks, ctr, ctr + half, y0, y1);
+        const uint32_t da = (y0 >> 9) - (e ? ta.y : ta.x);
+        const uint32_t db = (y1 >> 9) - (e ? tb.y : tb.x);
+        Fa = __funnelshift_l(da, Fa, 1);
+        Fb = __funnelshift_l(db, Fb, 1);
+      }
+    }
   }
   uint32_t* own = lat + (size_t)c * L * NW;
   own[i * NW + w] = pa.S ^ Fa;
@@ -291,21 +321,22 @@ __device__ __forceinline__ void sweep_keys(const KeySchedule& ks_rep, int t, int
 // ------------------------------------------------------------------------------ fast kernel
 // Shared memory: spread[4][256] | per team: lattice[2][L][NW], thr[2][16] | (CTA team) hist[2][2][2][16]
 template <bool WARP_TEAM>
-__global__ void __launch_bounds__(WARP_TEAM ? 128 : 1024) ising_fast_kernel(const IsingShape sh, const IsingIO io) {
+__global__ void __launch_bounds__(WARP_TEAM ? 128 : 1024, WARP_TEAM ? NQ_ISING_MINB : 1) ising_fast_kernel(const IsingShape sh, const IsingIO io) {
   extern __shared__ uint32_t smem[];
   uint32_t* spread = smem;
   const int L = sh.L, NW = sh.NW, T = sh.T;
   const int lat_words = 2 * L * NW;
-  const int team_words = lat_words + 2 * kIsingClasses + (WARP_TEAM ? 2 * 2 * 2 * kIsingClasses : 0);
+  constexpr int kThrWords = 2 * 256 * 2;  // two parity buffers of the 256-entry pair table
+  const int team_words = lat_words + kThrWords + (WARP_TEAM ? 2 * 2 * 2 * kIsingClasses : 0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int team = WARP_TEAM ? warp : 0;
   const int tid = WARP_TEAM ? lane : threadIdx.x;          // index within the team
   const int tsize = WARP_TEAM ? 32 : blockDim.x;
   const int nteams = WARP_TEAM ? blockDim.x / 32 : 1;
   uint32_t* lat = smem + 4 * 256 + team * team_words;
-  uint32_t* thr_s = lat + lat_words;
+  uint2* thr_s = reinterpret_cast<uint2*>(lat + lat_words);
   // per-sweep class histograms [parity][half][active|flipped][16]: per team (warp teams) or per CTA
-  int* hist_s = WARP_TEAM ? reinterpret_cast<int*>(thr_s + 2 * kIsingClasses)
+  int* hist_s = WARP_TEAM ? reinterpret_cast<int*>(lat + lat_words + kThrWords)
                           : reinterpret_cast<int*>(smem + 4 * 256 + nteams * team_words);
 
   for (int v = threadIdx.x; v < 4 * 256; v += blockDim.x) spread[v] = spread8_to_nibbles(v & 255) << (v >> 8);
@@ -328,7 +359,7 @@ __global__ void __launch_bounds__(WARP_TEAM ? 128 : 1024) ising_fast_kernel(cons
     lat[u] = c0;
     lat[L * NW + u] = c1;
   }
-  if (tid < kIsingClasses && T > 1) thr_s[kIsingClasses + tid] = io.thr[tid];  // sweep 1 -> buffer 1
+  if (T > 1) build_pair_table(thr_s + 256, io.thr, tid, tsize);  // sweep 1 -> buffer 1
   team_sync();
 
   // ---- initial spin sum M and bond sum B (each bond joins a colour-0 and a colour-1 site)
@@ -368,8 +399,8 @@ __global__ void __launch_bounds__(WARP_TEAM ? 128 : 1024) ising_fast_kernel(cons
   for (int t = 1; t < T; ++t) {
     KeySchedule kh[2];
     sweep_keys(ks_rep, t, T, sh.direct_keys != 0, kh[0], kh[1]);
-    const uint32_t* thr_cur = thr_s + (t & 1) * kIsingClasses;
-    if (tid < kIsingClasses && t + 1 < T) thr_s[((t + 1) & 1) * kIsingClasses + tid] = io.thr[(size_t)t * kIsingClasses + tid];
+    const uint2* thr_cur = thr_s + (t & 1) * 256;
+    if (t + 1 < T) build_pair_table(thr_s + ((t + 1) & 1) * 256, io.thr + (size_t)t * kIsingClasses, tid, tsize);
     int At[2][10], Ft[2][10];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
@@ -585,7 +616,7 @@ __global__ void measure_kernel(const uint32_t* bits, int L, long long R, long lo
 static bool fast_path(int L) { return L % 64 == 0; }
 static size_t fast_smem_bytes(int L, bool warp_team, int nteams) {
   const size_t lat_words = 2 * (size_t)L * (L / 64);
-  size_t words = 4 * 256 + nteams * (lat_words + 2 * kIsingClasses + (warp_team ? 2 * 2 * 2 * kIsingClasses : 0));
+  size_t words = 4 * 256 + nteams * (lat_words + 2 * 256 * 2 + (warp_team ? 2 * 2 * 2 * kIsingClasses : 0));
   if (!warp_team) words += 2 * 2 * 2 * kIsingClasses + 2;
   return words * 4;
 }
