@@ -67,7 +67,7 @@ class ClockSampler:
   def start(self):
     try:
       self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
-                                    '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                    '--format=csv,noheader,nounits', '-lms', '20'], stdout=subprocess.PIPE,
                                    stderr=subprocess.DEVNULL, text=True)
       self.thread = threading.Thread(target=self._read, daemon=True)
       self.thread.start()
@@ -114,7 +114,7 @@ def run_reference(args):
   from oracle import c_oracle, jaxlike as J, langevin_ref as L
   pot = L.V_biomolecule_shifted(KAPPA, KAPPA, X_M, 0., K_TRAP, BETA)
   r, phi = L.make_schedule_chebyshev(C2_S, C2_COEFFS, 0., 40.)
-  n = 1024
+  n = 1024 * c_oracle.max_threads()
   seeds = J.split(J.PRNGKey(0), C2_B)[:n]
   x0 = np.zeros(n, np.float32)
   times = []
@@ -171,7 +171,7 @@ def run_native(args):
                             1000, DT, KT, GAMMA).reshape(-1).contiguous()
   r_np, phi_np = bc._schedule_and_jacobian(np.arange(C2_S + 1), C2_COEFFS, 0., 40.)
   r_dev = torch.from_numpy(r_np).to(dev)
-  phi_dev = torch.from_numpy(phi_np).to(dev)
+  phi_dev = torch.from_numpy(np.array(phi_np)).to(dev)
 
   def step_resident():
     out = bc._simulate(pot, shift, r_dev, phi_dev, x0, seeds, C2_S, 0, DT, KT, 1.0, GAMMA)
@@ -235,6 +235,10 @@ def run_native(args):
   value = units / (ms * 1e-3)
   ms_e2e, _, _, grad_e2e = timed(step_e2e, max(3, args.steps // 2), 2)
   e2e_value = units / (ms_e2e * 1e-3)
+  other = 'fast' if args.math == 'strict' else 'strict'
+  bc.set_math_mode(other)
+  ms_other, _, _, (grad_other, mom_other) = timed(step_resident, max(3, args.steps // 2), 2)
+  bc.set_math_mode(args.math)
 
   line = None
   if rank == 0:
@@ -261,7 +265,11 @@ def run_native(args):
                          d2h_bytes_per_step=d2h, api='noneq_opt_b200.distributed.langevin_gradient_sharded '
                          '(= barrier_crossing.estimate_gradient_boltzinit per rank)'),
                 roofline=roofline,
-                check=dict(mean_work=float(mom[1] / mom[0]), grad0=float(grad[0]), grad0_e2e=float(grad_e2e[0])))
+                check=dict(mean_work=float(mom[1] / mom[0]), grad0=float(grad[0]), grad0_e2e=float(grad_e2e[0])),
+                other_math_mode={'math_mode': other, 'value': units / (ms_other * 1e-3), 'ms_per_step': ms_other,
+                                 'mean_work': float(mom_other[1] / mom_other[0]), 'grad0': float(grad_other[0]),
+                                 'note': 'strict = reference operation order (parity-certified, default); fast = MUFU/FMA '
+                                         'refactored step, parity statistical (DESIGN.md 5)'})
 
   # ---- secondary: Ising spin-updates/s (rank-local replicas; no collective on the data path)
   ising_res = None if args.no_ising else bench_ising(args, dev, rank, ws)
@@ -348,7 +356,7 @@ def cpu_baseline():
   from oracle import c_oracle, jaxlike as J, langevin_ref as L
   pot = L.V_biomolecule_shifted(KAPPA, KAPPA, X_M, 0., K_TRAP, BETA)
   r, phi = L.make_schedule_chebyshev(C2_S, C2_COEFFS, 0., 40.)
-  n = 2048
+  n = min(C2_B, 4096 * c_oracle.max_threads())     # ~10 s of CPU work
   seeds = J.split(J.PRNGKey(0), C2_B)[:n]
   c_oracle.langevin(pot, r, phi, np.zeros(64, np.float32), seeds[:64], C2_S, 0, DT, KT, GAMMA, 1.0)   # warm
   t0 = time.perf_counter()
