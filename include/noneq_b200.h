@@ -177,16 +177,19 @@ int nq_langevin_apply(const NqLangevinDesc* desc /*host*/, float r0, float* x, u
 #define NQ_IS_NPARTIAL 4
 
 typedef struct NqIsingDesc {
-  int32_t L;          /* lattice side (2-D, periodic, even)          ising.py:99-106 */
+  int32_t L;          /* lattice side of the 2-D square lattice (used when ndim == 0) ising.py:99-106 */
   int32_t T;          /* time_steps; T-1 sweeps                      ising.py:153-173 */
   int64_t R;          /* replicas (rows of split(seed, batch_size),  ising.py:283)   */
   int32_t spins0_broadcast; /* 1: spins0 holds ONE lattice shared by all replicas    */
   int32_t sweep_key_mode;   /* 0: sweep t uses split(seed_r, T-1)[t-1] (simulate_ising :161);
                                1: T must be 2 and the single sweep uses seed_r itself (update :132) */
+  int32_t ndim;             /* 0: 2-D square L x L; 1..3: general periodic lattice dims[0..ndim-1], all even
+                               (sum_neighbors :75-83 and even_odd_masks :99-106 are rank-generic)        */
+  int32_t dims[3];
 } NqIsingDesc;
 
 size_t nq_ising_words_per_lattice(int32_t L); /* = L*L/32 (bit b of word w = site 32*w+b, row-major; 1 = spin +1) */
-size_t nq_ising_workspace_bytes(const NqIsingDesc* desc);
+size_t nq_ising_workspace_bytes(const NqIsingDesc* desc); /* 0 unless the lattice exceeds shared memory on the generic path */
 
 /* simulate_ising (ising.py:153-173) for R replicas: T-1 x update (:129-150), each two
  * masked_update half-sweeps (:109-126, odd-parity sites first :99-106), with
@@ -210,14 +213,15 @@ int nq_ising_run(const NqIsingDesc* desc /*host*/, const uint32_t* thr, const do
                  int32_t* counts, uint32_t* states,
                  void* workspace, size_t workspace_bytes, void* stream);
 
-/* random_spins(shape, p, seed) (ising.py:71-72) bit-packed: bit = uniform(seed)[i] < p */
-int nq_ising_random_spins(const uint32_t key[2] /*host*/, int32_t L, float p, uint32_t* out_bits,
+/* random_spins(shape, p, seed) (ising.py:71-72) bit-packed, n_sites = prod(shape): bit i = uniform(seed)[i] < p */
+int nq_ising_random_spins(const uint32_t key[2] /*host*/, int64_t n_sites, float p, uint32_t* out_bits,
                           void* stream);
 /* pack / unpack between +-1 spins (int32 or float32 elements) and the bit-packed layout */
 int nq_ising_pack(const void* spins, int32_t is_float, int64_t n_sites, uint32_t* bits, void* stream);
 int nq_ising_unpack(const uint32_t* bits, int64_t n_sites, int32_t is_float, void* spins, void* stream);
 /* sum_neighbors / energy / magnetisation of bit-packed lattices: out[r] = {M, bond sum B} as int64[2] */
-int nq_ising_measure(const uint32_t* bits, int32_t L, int64_t R, int64_t* out_MB, void* stream);
+int nq_ising_measure(const uint32_t* bits, int32_t ndim, const int32_t dims[3] /*host*/, int64_t R,
+                     int64_t* out_MB, void* stream);
 
 /* ------------------------------------------------------------------ calibration */
 /* issue-rate microbenchmark: runs `iters` dependent-chain iterations of

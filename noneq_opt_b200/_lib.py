@@ -31,7 +31,8 @@ class NqLangevinDesc(C.Structure):
 
 class NqIsingDesc(C.Structure):
   _fields_ = [('L', C.c_int32), ('T', C.c_int32), ('R', C.c_int64),
-              ('spins0_broadcast', C.c_int32), ('sweep_key_mode', C.c_int32)]
+              ('spins0_broadcast', C.c_int32), ('sweep_key_mode', C.c_int32),
+              ('ndim', C.c_int32), ('dims', C.c_int32 * 3)]
 
 
 _P = C.c_void_p
@@ -62,10 +63,10 @@ SIGNATURES = {
     'nq_ising_workspace_bytes': (C.c_size_t, [C.POINTER(NqIsingDesc)]),
     'nq_ising_run': (C.c_int, [C.POINTER(NqIsingDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                _P, C.c_size_t, _P]),
-    'nq_ising_random_spins': (C.c_int, [_KEY, C.c_int32, C.c_float, _P, _P]),
+    'nq_ising_random_spins': (C.c_int, [_KEY, C.c_int64, C.c_float, _P, _P]),
     'nq_ising_pack': (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P]),
     'nq_ising_unpack': (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P]),
-    'nq_ising_measure': (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P]),
+    'nq_ising_measure': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.c_int64, _P, _P]),
     'nq_microbench': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
 }
 

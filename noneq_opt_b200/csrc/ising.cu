@@ -91,10 +91,13 @@ __device__ __forceinline__ void count_planes(uint32_t a, uint32_t b, uint32_t c,
 }
 
 struct IsingShape {
-  int L, NW, T;     // NW = L/64 words per row per colour
+  int L, NW, T;     // NW = L/64 words per row per colour (2-D fast path)
   long long R;
   int broadcast0;
   int direct_keys;
+  int ndim, d0, d1, d2;  // general lattice d0 x d1 x d2 (unused trailing dims = 1), row-major
+  int N;                 // sites
+  signed char* scratch;  // generic path: global spin scratch [R][N] when N does not fit shared memory
 };
 
 struct IsingIO {
@@ -218,8 +221,9 @@ __device__ __forceinline__ void update_unit(uint32_t* lat, const IsingShape& sh,
 }
 
 // ------------------------------------------------------------------------------ summaries
-// class c10 in [0,10): spin = c10 >= 5 ? +1 : -1, #up-neighbours = c10 % 5; table slot = 8*(c10>=5) + c10%5
-__device__ __forceinline__ int slot_of(int c10) { return c10 >= 5 ? 8 + (c10 - 5) : c10; }
+// A site has 2*ndim neighbours, so ncls = 2*ndim+1 up-neighbour counts per spin value.  Class
+// c in [0, 2*ncls): spin = c >= ncls ? +1 : -1, #up-neighbours = c % ncls; table slot = 8*(spin up) + n_up
+__device__ __forceinline__ int slot_of(int c, int ncls) { return c >= ncls ? 8 + (c - ncls) : c; }
 
 // Integer sufficient statistics of one sweep -> the float outputs.  Executed by one full warp;
 // lane c < 10 owns class c and holds A[h], F[h] (active / flipped counts of its class in
@@ -227,14 +231,15 @@ __device__ __forceinline__ int slot_of(int c10) { return c10 >= 5 ? 8 + (c10 - 5
 __device__ __forceinline__ void emit_summary(const int (&A)[2], const int (&F)[2], const IsingIO& io,
                                              const IsingShape& sh, long long rep, int t, long long& M,
                                              long long& B, int lane) {
-  const bool on = lane < 10;
+  const int ncls = 2 * sh.ndim + 1;
+  const bool on = lane < 2 * ncls;
   const int c10 = on ? lane : 0;
-  const int slot = slot_of(c10);
+  const int slot = slot_of(c10, ncls);
   const double* lut = io.lut + (size_t)(t - 1) * 4 * kIsingClasses;
   const double ell = lut[slot], lsn = lut[kIsingClasses + slot], lsp = lut[2 * kIsingClasses + slot],
                sig = lut[3 * kIsingClasses + slot];
-  const int s = c10 >= 5 ? 1 : -1;
-  const int nsum = 2 * (c10 % 5) - 4;
+  const int s = c10 >= ncls ? 1 : -1;
+  const int nsum = 2 * (c10 % ncls) - 2 * sh.ndim;
   double fwd[2], rev[2], lF = 0.0, sAs = 0.0, lAs = 0.0;
   int dM = 0, dB = 0;
 #pragma unroll
@@ -274,7 +279,7 @@ __device__ __forceinline__ void emit_summary(const int (&A)[2], const int (&F)[2
     case NQ_IS_FWD: v = fwd32; break;
     case NQ_IS_REV: v = rev32; break;
     case NQ_IS_EP: v = __fsub_rn(fwd32, rev32); break;
-    case NQ_IS_MAG: v = (float)((double)M2 / ((double)sh.L * sh.L)); break;
+    case NQ_IS_MAG: v = (float)((double)M2 / (double)sh.N); break;
     case NQ_IS_ENERGY: v = e_fin; break;
     default: break;
   }
@@ -476,33 +481,42 @@ __global__ void __launch_bounds__(WARP_TEAM ? 128 : 1024, WARP_TEAM ? NQ_ISING_M
 }
 
 // ------------------------------------------------------------------------------ generic kernel
-// Any even L: one CTA per replica, one spin per byte in shared memory, one threefry block per
-// updated site (the (p, p+L*L/2) partner may have the other colour when L/2 is odd).
+// Any even-sided 1-D / 2-D / 3-D periodic lattice (the reference's tests use 10000, 256x256 and
+// 64^3): one CTA per replica, one spin per byte in shared memory (or in a global scratch when the
+// lattice does not fit), one threefry block per updated site -- the (p, p+N/2) counter partner may
+// have the other colour here.  Correctness path; the tuned path is ising_fast_kernel.
 __global__ void __launch_bounds__(256) ising_generic_kernel(const IsingShape sh, const IsingIO io) {
   extern __shared__ uint32_t smem[];
   int* hist_s = reinterpret_cast<int*>(smem);               // [2][2][16]
   int* scratch = hist_s + 2 * 2 * kIsingClasses;            // [2]
   uint32_t* thr_s = reinterpret_cast<uint32_t*>(scratch + 2);  // [16]
-  signed char* sp = reinterpret_cast<signed char*>(thr_s + kIsingClasses);
-  const int L = sh.L, T = sh.T, N = L * L;
+  const int T = sh.T, N = sh.N, d0 = sh.d0, d1 = sh.d1, d2 = sh.d2, ndim = sh.ndim;
   const long long rep = blockIdx.x;
+  signed char* sp = sh.scratch ? sh.scratch + (size_t)rep * N : reinterpret_cast<signed char*>(thr_s + kIsingClasses);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ncls = 2 * ndim + 1;
   const size_t ext_words = ((size_t)N + 31) / 32;
   const uint32_t* ext0 = io.spins0 + (sh.broadcast0 ? 0 : rep * ext_words);
   for (int p = threadIdx.x; p < N; p += blockDim.x) sp[p] = ((ext0[p >> 5] >> (p & 31)) & 1u) ? 1 : -1;
   if (threadIdx.x < 2) scratch[threadIdx.x] = 0;
   __syncthreads();
-  auto nsum_at = [&](int i, int j) {
-    const int iu = i == 0 ? L - 1 : i - 1, id = i == L - 1 ? 0 : i + 1;
-    const int jl = j == 0 ? L - 1 : j - 1, jr = j == L - 1 ? 0 : j + 1;
-    return (int)sp[iu * L + j] + sp[id * L + j] + sp[i * L + jl] + sp[i * L + jr];
+  // (parity of the index sum, sum of the 2*ndim neighbours) of site p
+  auto site = [&](int p, int& parity) {
+    const int k = p % d2, ij = p / d2, j = ij % d1, i = ij / d1;
+    parity = (i + j + k) & 1;
+    int n = 0;
+    if (ndim >= 1) n += sp[((i == 0 ? d0 - 1 : i - 1) * d1 + j) * d2 + k] + sp[((i == d0 - 1 ? 0 : i + 1) * d1 + j) * d2 + k];
+    if (ndim >= 2) n += sp[(i * d1 + (j == 0 ? d1 - 1 : j - 1)) * d2 + k] + sp[(i * d1 + (j == d1 - 1 ? 0 : j + 1)) * d2 + k];
+    if (ndim >= 3) n += sp[(i * d1 + j) * d2 + (k == 0 ? d2 - 1 : k - 1)] + sp[(i * d1 + j) * d2 + (k == d2 - 1 ? 0 : k + 1)];
+    return n;
   };
   {
     int m = 0, b = 0;
     for (int p = threadIdx.x; p < N; p += blockDim.x) {
-      const int i = p / L, j = p - i * L;
+      int par;
+      const int n = site(p, par);
       m += sp[p];
-      if ((i + j) & 1) b += sp[p] * nsum_at(i, j);
+      if (par) b += sp[p] * n;   // every bond joins an odd-parity and an even-parity site
     }
     m = __reduce_add_sync(0xffffffffu, m);
     b = __reduce_add_sync(0xffffffffu, b);
@@ -518,12 +532,13 @@ __global__ void __launch_bounds__(256) ising_generic_kernel(const IsingShape sh,
     for (int v = threadIdx.x; v < 2 * 2 * kIsingClasses; v += blockDim.x) hist_s[v] = 0;
     __syncthreads();
     for (int c = 0; c < 2; ++c) {
-      const int want = c == 0 ? 1 : 0;  // parity of i+j updated in this half-sweep
+      const int want = c == 0 ? 1 : 0;  // parity of the index sum updated in this half-sweep
       for (int p = threadIdx.x; p < N; p += blockDim.x) {
-        const int i = p / L, j = p - i * L;
-        if (((i + j) & 1) != want) continue;
+        int par;
+        const int n = site(p, par);
+        if (par != want) continue;
         const int s = sp[p];
-        const int slot = (s > 0 ? 8 : 0) + (nsum_at(i, j) + 4) / 2;
+        const int slot = (s > 0 ? 8 : 0) + (n + 2 * ndim) / 2;
         const uint32_t bits = random_bits_at(kh[c], (uint64_t)p, (uint64_t)N);
         const bool flip = (bits >> 9) < thr_s[slot];
         atomicAdd(&hist_s[(c * 2 + 0) * kIsingClasses + slot], 1);
@@ -532,6 +547,7 @@ __global__ void __launch_bounds__(256) ising_generic_kernel(const IsingShape sh,
           sp[p] = (signed char)(-s);
         }
       }
+      __threadfence_block();
       __syncthreads();
     }
     if (io.states) {
@@ -545,9 +561,9 @@ __global__ void __launch_bounds__(256) ising_generic_kernel(const IsingShape sh,
     if (warp == 0) {
       int a2[2], f2[2];
       for (int c = 0; c < 2; ++c) {
-        const int slot = slot_of(lane < 10 ? lane : 0);
-        a2[c] = lane < 10 ? hist_s[(c * 2 + 0) * kIsingClasses + slot] : 0;
-        f2[c] = lane < 10 ? hist_s[(c * 2 + 1) * kIsingClasses + slot] : 0;
+        const int slot = slot_of(lane < 2 * ncls ? lane : 0, ncls);
+        a2[c] = lane < 2 * ncls ? hist_s[(c * 2 + 0) * kIsingClasses + slot] : 0;
+        f2[c] = lane < 2 * ncls ? hist_s[(c * 2 + 1) * kIsingClasses + slot] : 0;
       }
       emit_summary(a2, f2, io, sh, rep, t, M, B, lane);
     }
@@ -591,18 +607,23 @@ __global__ void random_spins_kernel(uint32_t k0, uint32_t k1, long long n_sites,
   bits[w] = word;
 }
 
-// out[r] = {sum of spins, sum over bonds of s_i s_j}
-__global__ void measure_kernel(const uint32_t* bits, int L, long long R, long long* out) {
+// out[r] = {sum of spins, sum over bonds of s_i s_j} of a d0 x d1 x d2 periodic lattice
+__global__ void measure_kernel(const uint32_t* bits, int ndim, int d0, int d1, int d2, long long* out) {
   const long long rep = blockIdx.x;
-  const size_t ext_words = ((size_t)L * L + 31) / 32;
+  const int N = d0 * d1 * d2;
+  const size_t ext_words = ((size_t)N + 31) / 32;
   const uint32_t* x = bits + rep * ext_words;
-  auto spin = [&](int i, int j) { const int p = i * L + j; return ((x[p >> 5] >> (p & 31)) & 1u) ? 1 : -1; };
+  auto spin = [&](int p) { return ((x[p >> 5] >> (p & 31)) & 1u) ? 1 : -1; };
   long long m = 0, b = 0;
-  for (int p = threadIdx.x; p < L * L; p += blockDim.x) {
-    const int i = p / L, j = p - i * L;
-    const int s = spin(i, j);
+  for (int p = threadIdx.x; p < N; p += blockDim.x) {
+    const int k = p % d2, ij = p / d2, j = ij % d1, i = ij / d1;
+    const int s = spin(p);
     m += s;
-    b += s * (spin(i, j == L - 1 ? 0 : j + 1) + spin(i == L - 1 ? 0 : i + 1, j));
+    int fwd = 0;   // one neighbour per axis counts every bond once
+    if (ndim >= 1) fwd += spin(((i == d0 - 1 ? 0 : i + 1) * d1 + j) * d2 + k);
+    if (ndim >= 2) fwd += spin((i * d1 + (j == d1 - 1 ? 0 : j + 1)) * d2 + k);
+    if (ndim >= 3) fwd += spin((i * d1 + j) * d2 + (k == d2 - 1 ? 0 : k + 1));
+    b += s * fwd;
   }
   __shared__ long long acc[2];
   if (threadIdx.x < 2) acc[threadIdx.x] = 0;
@@ -620,8 +641,23 @@ static size_t fast_smem_bytes(int L, bool warp_team, int nteams) {
   if (!warp_team) words += 2 * 2 * 2 * kIsingClasses + 2;
   return words * 4;
 }
-static size_t generic_smem_bytes(int L) {
-  return (2 * 2 * kIsingClasses + 2 + kIsingClasses) * 4 + (((size_t)L * L + 3) / 4) * 4;
+static size_t generic_smem_bytes(long long N) {
+  return (2 * 2 * kIsingClasses + 2 + kIsingClasses) * 4 + (((size_t)N + 3) / 4) * 4;
+}
+static const size_t kGenericSmemHeader = (2 * 2 * kIsingClasses + 2 + kIsingClasses) * 4;
+
+// lattice geometry of a descriptor: ndim == 0 means the 2-D square L x L
+static int lattice_dims(const NqIsingDesc* d, int dims[3]) {
+  int ndim = d->ndim;
+  if (ndim == 0) {
+    dims[0] = dims[1] = d->L;
+    dims[2] = 1;
+    return 2;
+  }
+  dims[0] = d->dims[0];
+  dims[1] = ndim >= 2 ? d->dims[1] : 1;
+  dims[2] = ndim >= 3 ? d->dims[2] : 1;
+  return ndim;
 }
 
 }  // namespace nq
@@ -629,37 +665,53 @@ static size_t generic_smem_bytes(int L) {
 using namespace nq;
 
 extern "C" size_t nq_ising_words_per_lattice(int32_t L) { return ((size_t)L * L + 31) / 32; }
-extern "C" size_t nq_ising_workspace_bytes(const NqIsingDesc*) { return 0; }
+
+// the generic path keeps one byte per spin in a global scratch when the lattice exceeds shared memory
+extern "C" size_t nq_ising_workspace_bytes(const NqIsingDesc* desc) {
+  if (!desc) return 0;
+  int dims[3];
+  const int ndim = lattice_dims(desc, dims);
+  const long long N = (long long)dims[0] * dims[1] * dims[2];
+  const bool fast = ndim == 2 && dims[0] == dims[1] && fast_path(dims[0]) &&
+                    fast_smem_bytes(dims[0], dims[0] <= 128, dims[0] <= 128 ? 4 : 1) <= 227 * 1024;
+  if (fast || generic_smem_bytes(N) <= 200 * 1024) return 0;
+  return (size_t)desc->R * N;
+}
 
 extern "C" int nq_ising_run(const NqIsingDesc* desc, const uint32_t* thr, const double* lut, const float* field,
                             const float* log_temp, const uint32_t* spins0, const uint32_t* seeds,
                             uint32_t* spins_out, float* summary, float* partials, int32_t* counts, uint32_t* states,
                             void* workspace, size_t workspace_bytes, void* stream) {
-  (void)workspace;
-  (void)workspace_bytes;
   NQ_CHECK_ARG(desc != nullptr, "desc is null");
-  const int L = desc->L, T = desc->T;
-  if (L <= 0 || (L & 1)) {
-    set_error("All entries in `shape` must be even; got (%d, %d).", L, L);  // ising.py:101-103
-    return NQ_ERR_INVALID_ARGUMENT;
+  int dims[3];
+  const int ndim = lattice_dims(desc, dims);
+  const int T = desc->T;
+  NQ_CHECK_ARG(ndim >= 1 && ndim <= 3, "lattices must be 1-, 2- or 3-dimensional (got ndim=%d)", ndim);
+  for (int a = 0; a < ndim; ++a) {
+    if (dims[a] <= 0 || (dims[a] & 1)) {  // ising.py:101-103
+      if (ndim == 1) set_error("All entries in `shape` must be even; got (%d,).", dims[0]);
+      else if (ndim == 2) set_error("All entries in `shape` must be even; got (%d, %d).", dims[0], dims[1]);
+      else set_error("All entries in `shape` must be even; got (%d, %d, %d).", dims[0], dims[1], dims[2]);
+      return NQ_ERR_INVALID_ARGUMENT;
+    }
   }
+  const long long N = (long long)dims[0] * dims[1] * dims[2];
   NQ_CHECK_ARG(T >= 1 && desc->R >= 1, "need T >= 1 and R >= 1 (got T=%d R=%lld)", T, (long long)desc->R);
   NQ_CHECK_ARG(thr && lut && field && log_temp && spins0 && seeds && summary, "null required pointer");
-  NQ_CHECK_ARG((long long)L * L <= 0x7fffffffll, "lattice too large");
+  NQ_CHECK_ARG(N <= 0x3fffffffll, "lattice too large");
   NQ_CHECK_ARG(desc->sweep_key_mode == 0 || (desc->sweep_key_mode == 1 && T == 2), "sweep_key_mode 1 needs T == 2");
-  IsingShape sh{L, L / 64, T, desc->R, desc->spins0_broadcast, desc->sweep_key_mode};
+  const int L = dims[0];
+  IsingShape sh{L, L / 64, T, desc->R, desc->spins0_broadcast, desc->sweep_key_mode, ndim, dims[0], dims[1], dims[2],
+                (int)N, nullptr};
   IsingIO io{thr, lut, field, log_temp, spins0, seeds, spins_out, summary, partials, counts, states};
   cudaStream_t st = (cudaStream_t)stream;
-  if (fast_path(L)) {
-    const bool warp_team = L <= 128;
-    const int nteams = warp_team ? 4 : 1;
+  const bool square2d = ndim == 2 && dims[0] == dims[1];
+  const bool warp_team = L <= 128;
+  const int nteams = warp_team ? 4 : 1;
+  if (square2d && fast_path(L) && fast_smem_bytes(L, warp_team, nteams) <= 227 * 1024) {
     const int units = (L / 2) * (L / 64);
     const int threads = warp_team ? 32 * nteams : (units >= 1024 ? 1024 : ((units + 31) / 32) * 32);
     const size_t smem = fast_smem_bytes(L, warp_team, nteams);
-    if (smem > 227 * 1024) {
-      set_error("L=%d needs %zu bytes of shared memory per replica (> 227 KB); the streamed large-lattice path is not built", L, smem);
-      return NQ_ERR_UNSUPPORTED;
-    }
     const unsigned blocks = (unsigned)((desc->R + nteams - 1) / nteams);
     if (warp_team) {
       NQ_CUDA(cudaFuncSetAttribute(ising_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -669,10 +721,15 @@ extern "C" int nq_ising_run(const NqIsingDesc* desc, const uint32_t* thr, const 
       ising_fast_kernel<false><<<blocks, threads, smem, st>>>(sh, io);
     }
   } else {
-    const size_t smem = generic_smem_bytes(L);
-    if (smem > 227 * 1024) {
-      set_error("generic path: L=%d does not fit shared memory; use a multiple of 64", L);
-      return NQ_ERR_UNSUPPORTED;
+    size_t smem = generic_smem_bytes(N);
+    if (smem > 200 * 1024) {   // spins live in the caller's workspace (L2-resident), tables stay in shared memory
+      const size_t need = (size_t)desc->R * N;
+      if (workspace == nullptr || workspace_bytes < need) {
+        set_error("lattice of %lld sites needs a %zu-byte workspace (nq_ising_workspace_bytes)", N, need);
+        return NQ_ERR_WORKSPACE;
+      }
+      sh.scratch = (signed char*)workspace;
+      smem = kGenericSmemHeader;
     }
     NQ_CUDA(cudaFuncSetAttribute(ising_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ising_generic_kernel<<<(unsigned)desc->R, 256, smem, st>>>(sh, io);
@@ -681,9 +738,10 @@ extern "C" int nq_ising_run(const NqIsingDesc* desc, const uint32_t* thr, const 
   return NQ_OK;
 }
 
-extern "C" int nq_ising_random_spins(const uint32_t key[2], int32_t L, float p, uint32_t* out_bits, void* stream) {
-  NQ_CHECK_ARG(key && out_bits && L > 0, "bad arguments");
-  const long long n = (long long)L * L;
+extern "C" int nq_ising_random_spins(const uint32_t key[2], int64_t n_sites, float p, uint32_t* out_bits,
+                                     void* stream) {
+  NQ_CHECK_ARG(key && out_bits && n_sites > 0 && n_sites <= 0x7fffffffll, "bad arguments");
+  const long long n = n_sites;
   // u < p  with u = m * 2^-23  <=>  m < ceil(p * 2^23)
   double scaled = ceil((double)p * 8388608.0);
   if (scaled < 0) scaled = 0;
@@ -714,9 +772,12 @@ extern "C" int nq_ising_unpack(const uint32_t* bits, int64_t n_sites, int32_t is
   return NQ_OK;
 }
 
-extern "C" int nq_ising_measure(const uint32_t* bits, int32_t L, int64_t R, int64_t* out_MB, void* stream) {
-  NQ_CHECK_ARG(bits && out_MB && L > 0 && R > 0, "bad arguments");
-  measure_kernel<<<(unsigned)R, 256, 0, (cudaStream_t)stream>>>(bits, L, R, (long long*)out_MB);
+extern "C" int nq_ising_measure(const uint32_t* bits, int32_t ndim, const int32_t dims[3], int64_t R,
+                                int64_t* out_MB, void* stream) {
+  NQ_CHECK_ARG(bits && out_MB && dims && ndim >= 1 && ndim <= 3 && R > 0, "bad arguments");
+  const int d0 = dims[0], d1 = ndim >= 2 ? dims[1] : 1, d2 = ndim >= 3 ? dims[2] : 1;
+  NQ_CHECK_ARG(d0 > 0 && d1 > 0 && d2 > 0, "bad lattice shape");
+  measure_kernel<<<(unsigned)R, 256, 0, (cudaStream_t)stream>>>(bits, ndim, d0, d1, d2, (long long*)out_MB);
   NQ_LAUNCHED();
   return NQ_OK;
 }

@@ -108,10 +108,10 @@ def _as_cuda(x, dtype=None):
   return t if dtype is None else t.to(dtype)
 
 
-def _pack(spins) -> torch.Tensor:
-  """+-1 spins `[..., L, L]` (int or float) -> bit-packed int32 words `[..., ceil(L*L/32)]`."""
+def _pack(spins, lattice_ndim: int = 2) -> torch.Tensor:
+  """+-1 spins `[..., *lattice]` (int or float) -> bit-packed int32 words `[..., ceil(sites/32)]`."""
   t = _as_cuda(spins)
-  lead, n = t.shape[:-2], t.shape[-2] * t.shape[-1]
+  lead, n = t.shape[:t.dim() - lattice_ndim], int(np.prod(t.shape[t.dim() - lattice_ndim:]))
   words = (n + 31) // 32
   is_float = t.is_floating_point()
   flat = t.to(torch.float32 if is_float else torch.int32).reshape(-1, n).contiguous()
@@ -125,11 +125,17 @@ def _pack(spins) -> torch.Tensor:
   return out.reshape(tuple(lead) + (words,))
 
 
-def _unpack(bits: torch.Tensor, L: int, like) -> torch.Tensor:
-  """bit-packed `[..., words]` -> +-1 spins `[..., L, L]` with the dtype family of `like`."""
+def _shape_of(L):
+  return (int(L), int(L)) if np.isscalar(L) else tuple(int(v) for v in L)
+
+
+def _unpack(bits: torch.Tensor, L, like) -> torch.Tensor:
+  """bit-packed `[..., words]` -> +-1 spins `[..., *lattice]` with the dtype family of `like`
+  (`L`: side of a square 2-D lattice, or the lattice shape)."""
+  shape = _shape_of(L)
   is_float = bool(like.is_floating_point()) if isinstance(like, torch.Tensor) else \
       np.issubdtype(np.asarray(like).dtype, np.floating)
-  n = L * L
+  n = int(np.prod(shape))
   flat = bits.reshape(-1, bits.shape[-1]).contiguous()
   out = torch.empty((flat.shape[0], n), dtype=torch.float32 if is_float else torch.int32, device=bits.device)
   lib = _lib.lib()
@@ -138,20 +144,20 @@ def _unpack(bits: torch.Tensor, L: int, like) -> torch.Tensor:
   else:
     for r in range(flat.shape[0]):
       _lib.check(lib.nq_ising_unpack(_lib.ptr(flat[r]), n, int(is_float), _lib.ptr(out[r]), _lib.stream_arg()))
-  return out.reshape(tuple(bits.shape[:-1]) + (L, L))
+  return out.reshape(tuple(bits.shape[:-1]) + shape)
 
 
 def random_spins(shape, p, seed):
-  """2 * Bernoulli(p).sample(shape) - 1 with jax's uniform stream; int32 CUDA tensor."""
-  shape = tuple(shape)
-  if len(shape) != 2 or shape[0] != shape[1]:
-    raise NotImplementedError('this build supports square 2-D lattices')
+  """2 * Bernoulli(p).sample(shape) - 1 with jax's uniform stream; int32 CUDA tensor (1-3 dims)."""
+  shape = (int(shape),) if np.isscalar(shape) else tuple(int(v) for v in shape)
+  if not 1 <= len(shape) <= 3:
+    raise NotImplementedError('lattices must have 1, 2 or 3 dimensions')
   device = _lib.require_cuda()
-  L = shape[0]
-  bits = torch.empty((L * L + 31) // 32, dtype=torch.int32, device=device)
-  _lib.check(_lib.lib().nq_ising_random_spins(_lib.key_arg(nqrandom._host_key(seed)), L, float(p),
+  n = int(np.prod(shape))
+  bits = torch.empty((n + 31) // 32, dtype=torch.int32, device=device)
+  _lib.check(_lib.lib().nq_ising_random_spins(_lib.key_arg(nqrandom._host_key(seed)), n, float(p),
                                               _lib.ptr(bits), _lib.stream_arg()))
-  return _unpack(bits, L, torch.zeros((), dtype=torch.int32))
+  return _unpack(bits, shape, torch.zeros((), dtype=torch.int32))
 
 
 def sum_neighbors(spins):
@@ -209,8 +215,8 @@ def _log_sigmoid32(x):
   return (-(np.maximum(a, F32(0)) + _log1p32(_exp32(-np.abs(a))))).astype(F32)
 
 
-def class_tables(log_temp, field):
-  """Per-sweep tables for the 2x5 (spin, #up-neighbours) site classes.
+def class_tables(log_temp, field, ndim: int = 2):
+  """Per-sweep tables for the 2 x (2*ndim+1) (spin, #up-neighbours) site classes (2x5 in 2-D).
 
   Class slot = 8*(spin up) + n_up.  For sweep t = 1..T-1 (parameters[t]):
     logits  : ((-2 s) (nsum + h_t)) exp(-log_temp_t) in float32, the reference's operation order
@@ -227,9 +233,9 @@ def class_tables(log_temp, field):
   einv = _exp32(-lt)
   for up in (0, 1):
     s = F32(1 if up else -1)
-    for n_up in range(5):
+    for n_up in range(2 * ndim + 1):
       slot = 8 * up + n_up
-      nsum = F32(2 * n_up - 4)
+      nsum = F32(2 * n_up - 2 * ndim)
       logit = (((F32(-2) * s) * (nsum + h).astype(F32)).astype(F32) * einv).astype(F32)
       prob = (F32(1) / (F32(1) + _exp32(-logit))).astype(F32)
       thr[:, slot] = np.ceil(prob.astype(np.float64) * 8388608.0).astype(np.uint32)
@@ -255,15 +261,20 @@ def _run_kernel(log_temp, field, spins0_bits, broadcast, seeds, L, want_partials
   device = seeds.device
   lib = _lib.lib()
   R, T = int(seeds.shape[0]), int(np.asarray(field).shape[0])
-  if L % 2:
-    raise ValueError(f'All entries in `shape` must be even; got {(L, L)}.')
-  thr, lut = class_tables(log_temp, field)
+  shape = _shape_of(L)
+  ndim = len(shape)
+  if any(v % 2 for v in shape):
+    raise ValueError(f'All entries in `shape` must be even; got {shape}.')
+  thr, lut = class_tables(log_temp, field, ndim)
   thr_d = torch.from_numpy(thr.view(np.int32)).to(device)
   lut_d = torch.from_numpy(lut).to(device)
   field_d = torch.from_numpy(np.ascontiguousarray(np.asarray(field, F32))).to(device)
   lt_d = torch.from_numpy(np.ascontiguousarray(np.asarray(log_temp, F32))).to(device)
-  words = (L * L + 31) // 32
-  desc = _lib.NqIsingDesc(L=L, T=T, R=R, spins0_broadcast=int(broadcast), sweep_key_mode=int(direct_keys))
+  words = (int(np.prod(shape)) + 31) // 32
+  dims = (C.c_int32 * 3)(*(list(shape) + [1] * (3 - ndim)))
+  square = ndim == 2 and shape[0] == shape[1]
+  desc = _lib.NqIsingDesc(L=shape[0], T=T, R=R, spins0_broadcast=int(broadcast), sweep_key_mode=int(direct_keys),
+                          ndim=0 if square else ndim, dims=dims)
   final_bits = torch.empty((R, words), dtype=torch.int32, device=device)
   summary = torch.zeros((_lib.NQ_IS_NSUMMARY, R, max(T - 1, 0)), dtype=torch.float32, device=device)
   partials = torch.zeros((_lib.NQ_IS_NPARTIAL, R, T - 1), dtype=torch.float32, device=device) if want_partials else None
@@ -271,11 +282,13 @@ def _run_kernel(log_temp, field, spins0_bits, broadcast, seeds, L, want_partials
   states = torch.empty((R, T - 1, words), dtype=torch.int32, device=device) if want_states else None
   n0 = 1 if broadcast else R
   MB0 = torch.empty((n0, 2), dtype=torch.int64, device=device)
-  _lib.check(lib.nq_ising_measure(_lib.ptr(spins0_bits), L, n0, _lib.ptr(MB0), _lib.stream_arg()))
+  _lib.check(lib.nq_ising_measure(_lib.ptr(spins0_bits), ndim, dims, n0, _lib.ptr(MB0), _lib.stream_arg()))
+  ws_bytes = lib.nq_ising_workspace_bytes(C.byref(desc))
+  ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device) if ws_bytes else None
   if T > 1:
     _lib.check(lib.nq_ising_run(C.byref(desc), _lib.ptr(thr_d), _lib.ptr(lut_d), _lib.ptr(field_d), _lib.ptr(lt_d),
                                 _lib.ptr(spins0_bits), _lib.ptr(seeds), _lib.ptr(final_bits), _lib.ptr(summary),
-                                _lib.ptr(partials), _lib.ptr(counts), _lib.ptr(states), None, 0,
+                                _lib.ptr(partials), _lib.ptr(counts), _lib.ptr(states), _lib.ptr(ws), ws_bytes,
                                 _lib.stream_arg()))
   else:
     final_bits.copy_(spins0_bits.expand(R, words))
@@ -289,17 +302,17 @@ def _prepare(parameters: IsingParameters, initial_spins, seed):
   if log_temp.shape != field.shape:
     raise ValueError('log_temp and field schedules must have the same length')
   spins = _as_cuda(initial_spins)
-  if spins.dim() not in (2, 3) or spins.shape[-1] != spins.shape[-2]:
-    raise NotImplementedError('this build supports square 2-D lattices ([L, L] or [R, L, L])')
-  L = int(spins.shape[-1])
-  if L % 2:
-    raise ValueError(f'All entries in `shape` must be even; got {tuple(spins.shape[-2:])}.')
   batched = np.ndim(seed) == 2 if not isinstance(seed, torch.Tensor) else seed.dim() == 2
   seeds = nqrandom.as_key_tensor(seed, device).reshape(-1, 2)
-  broadcast = spins.dim() == 2
-  if not broadcast and spins.shape[0] != seeds.shape[0]:
-    raise ValueError('initial_spins and seeds disagree on the number of replicas')
-  bits = _pack(spins).reshape(-1, (L * L + 31) // 32)
+  if not 1 <= spins.dim() <= 3:
+    raise NotImplementedError('initial_spins must be ONE periodic lattice of 1, 2 or 3 dimensions (as in the '
+                              'reference, replicas differ by their seeds only)')
+  shape = tuple(int(v) for v in spins.shape)
+  if any(v % 2 for v in shape):
+    raise ValueError(f'All entries in `shape` must be even; got {shape}.')
+  L = shape[0] if len(shape) == 2 and shape[0] == shape[1] else shape
+  broadcast = True
+  bits = _pack(spins, len(shape)).reshape(1, -1)
   return log_temp, field, spins, L, batched, seeds, broadcast, bits
 
 
@@ -403,6 +416,7 @@ def _loss_kind(loss_function):
 
 
 def _loss_and_sensitivities(kind, run: _Run, log_temp, field, L):
+  n_sites = float(np.prod(_shape_of(L)))
   """Per replica: loss [R] (float32) and d loss / d field_t, d loss / d log_temp_t as [R, T] float64."""
   S = run.summary.to(torch.float64)                 # [7, R, T-1]
   R, Tm1 = S.shape[1], S.shape[2]
@@ -412,7 +426,6 @@ def _loss_and_sensitivities(kind, run: _Run, log_temp, field, L):
   h = torch.from_numpy(np.asarray(field, np.float64)).to(dev)
   dL_dh = torch.zeros((R, T), dtype=torch.float64, device=dev)
   dL_dl = torch.zeros((R, T), dtype=torch.float64, device=dev)
-  n_sites = float(L * L)
   M0 = run.MB0[:, 0].to(torch.float64).expand(R)
   B0 = run.MB0[:, 1].to(torch.float64).expand(R)
   M_after = torch.round(S[_lib.NQ_IS_MAG] * n_sites)              # spin sum after each sweep (exact integers)

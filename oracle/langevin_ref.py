@@ -184,14 +184,18 @@ def brownian_apply(pot, sc, x, rng, r0, shift='free', dtype=F32):
 
 
 def make_schedule_chebyshev(S, coeffs, r0_init, r0_final, dtype=F32):
-  """MakeSchedule_chebyshev(arange(S+1), ...) :145-151 -> r[S+1]; also the [S-1, D] Jacobian."""
+  """MakeSchedule_chebyshev(arange(S+1), ...) :145-151 -> r[S+1]; also the [S-1, D] Jacobian.
+
+  `coeffs` may also be any parameterisation object of oracle.parameterization_ref (callable with
+  `.jacobian`), e.g. PiecewiseLinear -- the "piecewise" protocols of the north star: the reference
+  builds the table as `p10n.<Class>(...)(scaled_timevec)` in exactly the same way."""
   d = dtype
   tv = np.arange(S + 1)[1:-1]
   scaled = ((tv - 1).astype(d) / d(tv[-1] - 1)).astype(d)
-  cheb = Chebyshev(coeffs, d)
-  vals = cheb(scaled)
+  proto = coeffs if hasattr(coeffs, 'jacobian') else Chebyshev(coeffs, d)
+  vals = proto(scaled)
   r = np.concatenate([[d(r0_init)], vals, [d(r0_final)]]).astype(d)
-  return r, cheb.jacobian(scaled)
+  return r, proto.jacobian(scaled)
 
 
 def fit_linear_to_cheby(end_time, dt, r0_init, r0_final, degree):

@@ -29,9 +29,9 @@ def test_binding_covers_header(built_lib):
 
 
 def test_struct_layouts_match_header(built_lib):
-  # 4 int32 + 11 double + 2 int64 ; 2 int32 + int64 + 2 int32
+  # 4 int32 + 11 double + 2 int64 ; 2 int32 + int64 + 2 int32 + (1 + 3) int32
   assert ctypes.sizeof(_lib.NqLangevinDesc) == 16 + 11 * 8 + 16
-  assert ctypes.sizeof(_lib.NqIsingDesc) == 24
+  assert ctypes.sizeof(_lib.NqIsingDesc) == 40
 
 
 def test_argument_errors_do_not_need_a_gpu(built_lib):

@@ -208,7 +208,9 @@ def test_shape_errors(cuda):
   with pytest.raises(ValueError):
     ising.simulate_ising(p, -np.ones((8, 8), np.int32), J.PRNGKey(0), checkpoint_every=5)
   with pytest.raises(NotImplementedError):
-    ising.simulate_ising(p, -np.ones((8,), np.int32), J.PRNGKey(0))
+    ising.simulate_ising(p, -np.ones((2, 2, 2, 2), np.int32), J.PRNGKey(0))
+  with pytest.raises(ValueError):
+    ising.simulate_ising(p, -np.ones((4, 6, 5), np.int32), J.PRNGKey(0))
 
 
 def test_masked_update_building_block(cuda):
@@ -228,3 +230,51 @@ def test_masked_update_building_block(cuda):
   np.testing.assert_allclose(float(er + orv), float(summ.reverse_log_prob), rtol=2e-5)
   s_o, f_o, r_o, _, _ = I.masked_update(s0.cpu().numpy(), 0.2, -0.3, mask_even, seed_even)
   np.testing.assert_allclose(float(ef), f_o, rtol=2e-5)
+
+
+@pytest.mark.parametrize('shape', [(1000,), (6, 10), (8, 6, 4), (16, 16, 16)])
+def test_other_lattice_ranks_bit_exact(cuda, shape):
+  """sum_neighbors / even_odd_masks are rank-generic in the reference (ising.py:75-106; its tests use
+  1-D chains and 64^3 cubes): the generic kernel handles 1-3 dimensions and non-square lattices."""
+  from noneq_opt_b200 import ising
+  T, R = 5, 3
+  rs = np.random.RandomState(1)
+  lt = rs.uniform(-0.5, 1.0, T).astype(np.float32)
+  h = rs.uniform(-1, 1, T).astype(np.float32)
+  s0 = I.random_spins(shape, .5, J.PRNGKey(7))
+  np.testing.assert_array_equal(ising.random_spins(shape, .5, J.PRNGKey(7)).cpu().numpy(), s0)
+  seeds = J.split(J.PRNGKey(2), R)
+  final, (summary, states) = ising.simulate_ising(ising.IsingParameters(lt, h), s0, seeds, return_states=True)
+  assert final.spins.shape == (R,) + shape and states.spins.shape == (R, T - 1) + shape
+  for r in range(R):
+    fin_o, summ_o, st_o = I.simulate_ising(lt, h, s0, seeds[r], return_states=True)
+    np.testing.assert_array_equal(final.spins[r].cpu().numpy(), fin_o)
+    np.testing.assert_array_equal(states.spins[r].cpu().numpy(), st_o)
+    got = np.stack([getattr(summary, f)[r].cpu().numpy() for f in FIELDS])
+    check_summary(got, np.stack([getattr(summ_o, f) for f in FIELDS]), int(np.prod(shape)))
+  # gradients through the same closed forms
+  from noneq_opt_b200 import parameterization as p10n
+  sched = ising.IsingSchedule(p10n.Chebyshev(np.array([0.2, -0.1, 0.05], np.float32)),
+                              p10n.Chebyshev(np.array([-0.5, 0.7, 0.1], np.float32)))
+  times = np.linspace(0, 1, T, dtype=np.float32)
+  g, _ = ising.estimate_gradient_rev(ising.total_entropy_production)(sched, times, s0, seeds[0])
+  so = P.Chebyshev(np.array([0.2, -0.1, 0.05], np.float32)), P.Chebyshev(np.array([-0.5, 0.7, 0.1], np.float32))
+  cf = I.closed_form_gradient('total_entropy_production', so[0](times), so[1](times), so[0].jacobian(times),
+                              so[1].jacobian(times), s0, seeds[0])
+  assert rel(g.log_temp.weights.cpu().numpy(), cf['grad'][0]) < 1e-4
+  assert rel(g.field.weights.cpu().numpy(), cf['grad'][1]) < 1e-4
+
+
+@pytest.mark.parametrize('shape, field, temperature, expected', [((10000,), 0., 1., .5), ((64, 64, 64), -4., .5, 0.)])
+def test_statistics_reference_shapes(cuda, shape, field, temperature, expected):
+  """tests/ising_test.py:111-127 at the reference's own 1-D and 3-D sizes (64^3 spins live in the
+  workspace, not in shared memory); 200 sweeps are enough to reach the asserted proportions."""
+  from noneq_opt_b200 import ising
+  init_seed, sim_seed = J.split(J.PRNGKey(0), 2)
+  s0 = ising.random_spins(shape, .5, init_seed)
+  params = ising.IsingParameters(np.full(200, np.log(temperature), np.float32), np.full(200, field, np.float32))
+  state, summ = ising.simulate_ising(params, s0, sim_seed)
+  np.testing.assert_allclose(float(((state.spins + 1) / 2).float().mean()), expected, atol=.05)
+  # heat == T * entropy production on every sweep (tests/ising_test.py:91-109)
+  np.testing.assert_allclose(summ.dissipated_heat.cpu().numpy(), summ.entropy_production.cpu().numpy() * temperature,
+                             rtol=1e-4, atol=2e-2)

@@ -364,3 +364,22 @@ def test_config2_full_length_slice_vs_c_oracle(cuda):
   assert rel(gs[0], o['grad_sums'][0]) < GRAD_RTOL and rel(gs[1], o['grad_sums'][1]) < GRAD_RTOL
   print('full-length slice: max/q99.5 position err %.2e / %.2e, work err %.2e / %.2e' %
         (xerr.max(), np.quantile(xerr, 0.995), werr.max(), np.quantile(werr, 0.995)))
+
+
+def test_piecewise_linear_protocol_gradient(cuda):
+  """A PiecewiseLinear trap protocol (north star: "Chebyshev/piecewise"): the estimators take any
+  Parameterization in place of the Chebyshev coefficient vector; gradient wrt the knot values."""
+  from noneq_opt_b200 import barrier_crossing as bc, parameterization as p10n, space
+  from oracle import parameterization_ref as P
+  _, shift = space.free()
+  B, S = 128, 400
+  knots = np.linspace(5, 10, 10)[1:-1].astype(np.float32) + np.float32(0.2) * np.sin(np.arange(8)).astype(np.float32)
+  proto_g = p10n.PiecewiseLinear(knots, 0., 1., 5., 10.)
+  proto_o = P.PiecewiseLinear(knots, 0., 1., 5., 10.)
+  x0 = np.full(B, 5.0, np.float32)
+  o = L.estimate_gradient(L.V_spring(1.0), proto_o, x0, J.PRNGKey(1), 5., 10., 10, S, 2.5e-3, 1.0, 1.0, 1.0)
+  est = bc.estimate_gradient_boltzinit(B, bc.V_spring(1.0), 5., 10., 10, shift, S, 2.5e-3, 1.0, 1.0, 1.0)
+  grad, (_, (_, lp, w)) = est(proto_g, x0.reshape(B, 1, 1), J.PRNGKey(1))
+  assert grad.shape == (8,)
+  assert rel(w.cpu().numpy(), o['total_work']) < POS_RTOL
+  assert rel(grad.cpu().numpy(), o['grad']) < GRAD_RTOL
