@@ -507,11 +507,11 @@ __device__ __forceinline__ void langevin_chunk(const LangevinConsts& c, const La
     if (lane == 0) red_s[warp][q] = s;
   }
   __syncthreads();
-  if (threadIdx.x < NV) {
+  for (int q = threadIdx.x; q < NV; q += kThreads) {  // NV = 8 + 2*DPS reaches 72 > kThreads for D > 28
     double s = 0.0;
 #pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) s += red_s[w][threadIdx.x];
-    io.partials[block * NV + threadIdx.x] = s;
+    for (int w = 0; w < kThreads / 32; ++w) s += red_s[w][q];
+    io.partials[block * NV + q] = s;
   }
 }
 

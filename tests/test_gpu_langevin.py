@@ -383,3 +383,35 @@ def test_piecewise_linear_protocol_gradient(cuda):
   assert grad.shape == (8,)
   assert rel(w.cpu().numpy(), o['total_work']) < POS_RTOL
   assert rel(grad.cpu().numpy(), o['grad']) < GRAD_RTOL
+
+
+@pytest.mark.parametrize('D', [1, 2, 5, 12, 16, 17, 21, 24, 29, 32])
+@pytest.mark.parametrize('mode', ['strict', 'fast'])
+def test_every_coefficient_count_instantiation(cuda, D, mode):
+  """The fused kernel is instantiated for padded coefficient counts (4..32 and 13): every one of
+  them against the oracle, ragged trajectory counts (not a multiple of the 64-thread CTA) and step
+  counts (not a multiple of the 128-step tile) included."""
+  from noneq_opt_b200 import barrier_crossing as bc, space
+  _, shift = space.free()
+  B, S = 131, 150
+  rs = np.random.RandomState(D)
+  coeffs = np.concatenate([[7.5, 2.5], 0.05 * rs.normal(size=30)])[:D].astype(np.float32)
+  x0 = np.full(B, 5.0, np.float32)
+  o = L.estimate_gradient(L.V_spring(1.0), coeffs, x0, J.PRNGKey(D), 5., 10., 3, S, 1e-2, 1.0, 1.0, 1.0)
+  bc.set_math_mode(mode)
+  try:
+    est = bc.estimate_gradient_boltzinit(B, bc.V_spring(1.0), 5., 10., 3, shift, S, 1e-2, 1.0, 1.0, 1.0)
+    grad, (_, (_, lp, w)) = est(coeffs, x0.reshape(B, 1, 1), J.PRNGKey(D))
+  finally:
+    bc.set_math_mode('strict')
+  assert grad.shape == (D,)
+  assert rel(w.cpu().numpy(), o['total_work']) < (POS_RTOL if mode == 'strict' else 1e-4)
+  assert rel(grad.cpu().numpy(), o['grad']) < GRAD_RTOL
+
+
+def test_coefficient_count_limit(cuda):
+  from noneq_opt_b200 import barrier_crossing as bc, space
+  _, shift = space.free()
+  est = bc.estimate_gradient_boltzinit(8, bc.V_spring(1.0), 5., 10., 0, shift, 50, 1e-2, 1.0, 1.0, 1.0)
+  with pytest.raises(RuntimeError, match='D must be in'):
+    est(np.zeros(33, np.float32), np.zeros((8, 1, 1), np.float32), J.PRNGKey(0))
