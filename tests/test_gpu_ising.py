@@ -278,3 +278,42 @@ def test_statistics_reference_shapes(cuda, shape, field, temperature, expected):
   # heat == T * entropy production on every sweep (tests/ising_test.py:91-109)
   np.testing.assert_allclose(summ.dissipated_heat.cpu().numpy(), summ.entropy_production.cpu().numpy() * temperature,
                              rtol=1e-4, atol=2e-2)
+
+
+def test_cta_team_path_states_counts_and_gradients(cuda):
+  """L = 256 runs one 1024-thread CTA per replica (histograms through shared-memory atomics, summary
+  emitted by warp 0 while the other warps start the next sweep): states, counts and gradients."""
+  from noneq_opt_b200 import ising, parameterization as p10n
+  L, T, R = 256, 4, 3
+  wl, wh = np.array([0.3, -0.2, 0.1], np.float32), np.array([-0.4, 0.6, 0.2], np.float32)
+  sched = ising.IsingSchedule(p10n.Chebyshev(wl), p10n.Chebyshev(wh))
+  times = np.linspace(0, 1, T, dtype=np.float32)
+  params = sched(times)
+  s0 = I.random_spins((L, L), .5, J.PRNGKey(11))
+  seeds = J.split(J.PRNGKey(3), R)
+  final, (summary, states) = ising.simulate_ising(params, s0, seeds, return_states=True)
+  for r in (0, 2):
+    fin_o, summ_o, st_o = I.simulate_ising(params.log_temp, params.field, s0, seeds[r], return_states=True)
+    np.testing.assert_array_equal(states.spins[r].cpu().numpy(), st_o)
+    np.testing.assert_array_equal(final.spins[r].cpu().numpy(), fin_o)
+    check_summary(np.stack([getattr(summary, f)[r].cpu().numpy() for f in FIELDS]),
+                  np.stack([getattr(summ_o, f) for f in FIELDS]), L * L)
+  for loss_fn, name in ((ising.total_work, 'total_work'), (ising.total_entropy_production, 'total_entropy_production')):
+    g, _ = ising.estimate_gradient_rev(loss_fn)(sched, times, s0, seeds)
+    so = P.Chebyshev(wl), P.Chebyshev(wh)
+    cf = I.closed_form_gradient(name, so[0](times), so[1](times), so[0].jacobian(times), so[1].jacobian(times), s0, seeds[1])
+    assert rel(g.log_temp.weights[1].cpu().numpy(), cf['grad'][0]) < 1e-4
+    assert rel(g.field.weights[1].cpu().numpy(), cf['grad'][1]) < 1e-4
+
+
+def test_update_with_a_batch_of_seeds(cuda):
+  from noneq_opt_b200 import ising
+  L = 64
+  s0 = I.random_spins((L, L), .5, J.PRNGKey(5))
+  params = ising.IsingParameters(np.float32(0.4), np.float32(0.25))
+  seeds = J.split(J.PRNGKey(8), 5)
+  state, summ = ising.update(ising.IsingState(s0, params), params, seeds)
+  assert state.spins.shape == (5, L, L) and summ.work.shape == (5,)
+  for r in range(5):
+    s_o, summ_o = I.update(s0, (0.4, 0.25), (0.4, 0.25), seeds[r])
+    np.testing.assert_array_equal(state.spins[r].cpu().numpy(), s_o)

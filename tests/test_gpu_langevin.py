@@ -415,3 +415,23 @@ def test_coefficient_count_limit(cuda):
   est = bc.estimate_gradient_boltzinit(8, bc.V_spring(1.0), 5., 10., 0, shift, 50, 1e-2, 1.0, 1.0, 1.0)
   with pytest.raises(RuntimeError, match='D must be in'):
     est(np.zeros(33, np.float32), np.zeros((8, 1, 1), np.float32), J.PRNGKey(0))
+
+
+def test_checkpoint_replay_in_fast_math_and_with_periodic_shift(cuda):
+  from noneq_opt_b200 import barrier_crossing as bc, space
+  B, S, K = 96, 512, 128
+  coeffs = np.array([1.0, 1.0, 0.2], np.float32)
+  x0 = np.full((B, 1, 1), 0.5, np.float32)
+  for mode, shift in (('fast', space.free()[1]), ('strict', space.periodic(6.0)[1])):
+    bc.set_math_mode(mode)
+    try:
+      args = (bc.V_biomolecule(0.4, 0.5, 1.5, 0.3, 1.2, 1.0), 0.5, 2.5, 2, shift, S, 2e-3, 1.0, 1.0, 1.0)
+      g_fused, (_, (_, lp, w)) = bc.estimate_gradient_boltzinit(B, *args)(coeffs, x0, J.PRNGKey(21))
+      g_ckpt, (_, (_, lp2, w2)), _ = bc.estimate_gradient_boltzinit_checkpointed(B, *args, checkpoint_every=K)(
+          coeffs, x0, J.PRNGKey(21))
+    finally:
+      bc.set_math_mode('strict')
+    assert torch.equal(w, w2)
+    # FAST accumulates sum(z^2) in the fused kernel and per-step log-probs in the recording one
+    np.testing.assert_allclose(lp.cpu().numpy(), lp2.cpu().numpy(), rtol=2e-6)
+    assert rel(g_ckpt.cpu().numpy(), g_fused.cpu().numpy()) < 2e-5
