@@ -1,4 +1,4 @@
-"""Running and optimising 2-D Ising simulations under a time-varying field and temperature --
+"""Running and optimising Ising simulations under a time-varying field and temperature --
 B200 drop-in for `noneq_opt/ising.py`.
 
 Same names, argument order and return nesting as the reference:
@@ -15,8 +15,9 @@ tables from the schedule, launches the kernel and assembles losses and gradients
 kernel's per-sweep sufficient statistics (closed forms of SURVEY Appendix B.2 -- flips are
 integer samples, so spins carry no derivative and no tape is needed).
 
-Differences from the reference: lattices are 2-D; a batch of seeds `[R, 2]` may be
-passed wherever the reference uses `jax.vmap`; loss functions must be `total_work` or
+Differences from the reference: lattices have rank 1-3 (square 2-D lattices with
+`L % 64 == 0` take the tuned kernel); a batch of seeds `[R, 2]` may be passed wherever the reference
+uses `jax.vmap`; loss functions must be `total_work` or
 `total_entropy_production` (the two the reference ships); arrays are CUDA torch tensors.
 """
 from __future__ import annotations
