@@ -98,6 +98,7 @@ struct IsingShape {
   int ndim, d0, d1, d2;  // general lattice d0 x d1 x d2 (unused trailing dims = 1), row-major
   int N;                 // sites
   signed char* scratch;  // generic path: global spin scratch [R][N] when N does not fit shared memory
+  uint32_t* lat_global;  // fast path, lattices beyond shared memory: colour planes [R][2][L][NW] in HBM/L2
 };
 
 struct IsingIO {
@@ -325,23 +326,28 @@ __device__ __forceinline__ void sweep_keys(const KeySchedule& ks_rep, int t, int
 
 // ------------------------------------------------------------------------------ fast kernel
 // Shared memory: spread[4][256] | per team: lattice[2][L][NW], thr[2][16] | (CTA team) hist[2][2][2][16]
-template <bool WARP_TEAM>
+// GLOBAL_LAT: the colour planes of a replica live in global memory (L2-resident) instead of shared
+// memory -- same code, for lattices whose 2 x L x L/64 words exceed 227 KB (L >= 2048).
+template <bool WARP_TEAM, bool GLOBAL_LAT = false>
 __global__ void __launch_bounds__(WARP_TEAM ? 128 : 1024, WARP_TEAM ? NQ_ISING_MINB : 1) ising_fast_kernel(const IsingShape sh, const IsingIO io) {
   extern __shared__ uint32_t smem[];
   uint32_t* spread = smem;
   const int L = sh.L, NW = sh.NW, T = sh.T;
   const int lat_words = 2 * L * NW;
   constexpr int kThrWords = 2 * 256 * 2;  // two parity buffers of the 256-entry pair table
-  const int team_words = lat_words + kThrWords + (WARP_TEAM ? 2 * 2 * 2 * kIsingClasses : 0);
+  const int smem_lat_words = GLOBAL_LAT ? 0 : lat_words;
+  const int team_words = smem_lat_words + kThrWords + (WARP_TEAM ? 2 * 2 * 2 * kIsingClasses : 0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int team = WARP_TEAM ? warp : 0;
   const int tid = WARP_TEAM ? lane : threadIdx.x;          // index within the team
   const int tsize = WARP_TEAM ? 32 : blockDim.x;
   const int nteams = WARP_TEAM ? blockDim.x / 32 : 1;
-  uint32_t* lat = smem + 4 * 256 + team * team_words;
-  uint2* thr_s = reinterpret_cast<uint2*>(lat + lat_words);
+  uint32_t* team_base = smem + 4 * 256 + team * team_words;
+  const long long rep_early = (long long)blockIdx.x * nteams + team;
+  uint32_t* lat = GLOBAL_LAT ? sh.lat_global + (size_t)(rep_early < sh.R ? rep_early : 0) * lat_words : team_base;
+  uint2* thr_s = reinterpret_cast<uint2*>(team_base + smem_lat_words);
   // per-sweep class histograms [parity][half][active|flipped][16]: per team (warp teams) or per CTA
-  int* hist_s = WARP_TEAM ? reinterpret_cast<int*>(lat + lat_words + kThrWords)
+  int* hist_s = WARP_TEAM ? reinterpret_cast<int*>(team_base + smem_lat_words + kThrWords)
                           : reinterpret_cast<int*>(smem + 4 * 256 + nteams * team_words);
 
   for (int v = threadIdx.x; v < 4 * 256; v += blockDim.x) spread[v] = spread8_to_nibbles(v & 255) << (v >> 8);
@@ -635,8 +641,8 @@ __global__ void measure_kernel(const uint32_t* bits, int ndim, int d0, int d1, i
 }
 
 static bool fast_path(int L) { return L % 64 == 0; }
-static size_t fast_smem_bytes(int L, bool warp_team, int nteams) {
-  const size_t lat_words = 2 * (size_t)L * (L / 64);
+static size_t fast_smem_bytes(int L, bool warp_team, int nteams, bool global_lat = false) {
+  const size_t lat_words = global_lat ? 0 : 2 * (size_t)L * (L / 64);
   size_t words = 4 * 256 + nteams * (lat_words + 2 * 256 * 2 + (warp_team ? 2 * 2 * 2 * kIsingClasses : 0));
   if (!warp_team) words += 2 * 2 * 2 * kIsingClasses + 2;
   return words * 4;
@@ -672,9 +678,11 @@ extern "C" size_t nq_ising_workspace_bytes(const NqIsingDesc* desc) {
   int dims[3];
   const int ndim = lattice_dims(desc, dims);
   const long long N = (long long)dims[0] * dims[1] * dims[2];
-  const bool fast = ndim == 2 && dims[0] == dims[1] && fast_path(dims[0]) &&
-                    fast_smem_bytes(dims[0], dims[0] <= 128, dims[0] <= 128 ? 4 : 1) <= 227 * 1024;
-  if (fast || generic_smem_bytes(N) <= 200 * 1024) return 0;
+  if (ndim == 2 && dims[0] == dims[1] && fast_path(dims[0])) {
+    if (fast_smem_bytes(dims[0], dims[0] <= 128, dims[0] <= 128 ? 4 : 1) <= 227 * 1024) return 0;
+    return (size_t)desc->R * 2 * dims[0] * (dims[0] / 64) * 4;   // colour planes in global memory
+  }
+  if (generic_smem_bytes(N) <= 200 * 1024) return 0;
   return (size_t)desc->R * N;
 }
 
@@ -702,18 +710,28 @@ extern "C" int nq_ising_run(const NqIsingDesc* desc, const uint32_t* thr, const 
   NQ_CHECK_ARG(desc->sweep_key_mode == 0 || (desc->sweep_key_mode == 1 && T == 2), "sweep_key_mode 1 needs T == 2");
   const int L = dims[0];
   IsingShape sh{L, L / 64, T, desc->R, desc->spins0_broadcast, desc->sweep_key_mode, ndim, dims[0], dims[1], dims[2],
-                (int)N, nullptr};
+                (int)N, nullptr, nullptr};
   IsingIO io{thr, lut, field, log_temp, spins0, seeds, spins_out, summary, partials, counts, states};
   cudaStream_t st = (cudaStream_t)stream;
   const bool square2d = ndim == 2 && dims[0] == dims[1];
   const bool warp_team = L <= 128;
   const int nteams = warp_team ? 4 : 1;
-  if (square2d && fast_path(L) && fast_smem_bytes(L, warp_team, nteams) <= 227 * 1024) {
+  if (square2d && fast_path(L)) {
     const int units = (L / 2) * (L / 64);
     const int threads = warp_team ? 32 * nteams : (units >= 1024 ? 1024 : ((units + 31) / 32) * 32);
-    const size_t smem = fast_smem_bytes(L, warp_team, nteams);
+    const bool global_lat = fast_smem_bytes(L, warp_team, nteams) > 227 * 1024;
+    const size_t smem = fast_smem_bytes(L, warp_team, nteams, global_lat);
     const unsigned blocks = (unsigned)((desc->R + nteams - 1) / nteams);
-    if (warp_team) {
+    if (global_lat) {
+      const size_t need = (size_t)desc->R * 2 * L * (L / 64) * 4;
+      if (workspace == nullptr || workspace_bytes < need) {
+        set_error("L=%d keeps its lattice in global memory and needs a %zu-byte workspace (nq_ising_workspace_bytes)", L, need);
+        return NQ_ERR_WORKSPACE;
+      }
+      sh.lat_global = (uint32_t*)workspace;
+      NQ_CUDA(cudaFuncSetAttribute(ising_fast_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ising_fast_kernel<false, true><<<blocks, threads, smem, st>>>(sh, io);
+    } else if (warp_team) {
       NQ_CUDA(cudaFuncSetAttribute(ising_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       ising_fast_kernel<true><<<blocks, threads, smem, st>>>(sh, io);
     } else {

@@ -317,3 +317,19 @@ def test_update_with_a_batch_of_seeds(cuda):
   for r in range(5):
     s_o, summ_o = I.update(s0, (0.4, 0.25), (0.4, 0.25), seeds[r])
     np.testing.assert_array_equal(state.spins[r].cpu().numpy(), s_o)
+
+
+def test_lattice_larger_than_shared_memory(cuda):
+  """L = 2048 (1 MB of bits per replica) does not fit one SM's shared memory: the same kernel runs
+  with its colour planes in global memory (L2).  Bit-exact against the oracle."""
+  from noneq_opt_b200 import ising
+  L, T, R = 2048, 3, 2
+  s0 = I.random_spins((L, L), .5, J.PRNGKey(1))
+  lt = np.log(np.array([2.5, 2.3, 2.1], np.float32))
+  h = np.array([-0.2, 0.0, 0.2], np.float32)
+  seeds = J.split(J.PRNGKey(0), R)
+  final, summary = ising.simulate_ising(ising.IsingParameters(lt, h), s0, seeds)
+  fin_o, summ_o = I.simulate_ising(lt, h, s0, seeds[1])
+  np.testing.assert_array_equal(final.spins[1].cpu().numpy(), fin_o)
+  check_summary(np.stack([getattr(summary, f)[1].cpu().numpy() for f in FIELDS]),
+                np.stack([getattr(summ_o, f) for f in FIELDS]), L * L)
