@@ -404,6 +404,7 @@ __device__ __forceinline__ void langevin_chunk(const LangevinConsts& c, const La
         }
       }
       float dW, dR;
+      const float x_before = x;
       if (FAST) {
         const float4 tab = lds_f32x4(tab_addr);
         dW = fmaf(tab.y, x, tab.z);
@@ -424,7 +425,9 @@ __device__ __forceinline__ void langevin_chunk(const LangevinConsts& c, const La
       if (GRAD) {
         // d logp_k / d r_k = z * ca and d W / d r_k = k_s * dR: the constant factors are applied
         // once, after the trajectory
-        const float a = z, b = dR;
+        // d W / d r_k = -k_s (x_{k-1} - r_k) + k_s (x_k - r_k) = k_s (x_k - x_{k-1}); that is k_s dR unless a
+        // periodic shift wrapped the position
+        const float a = z, b = c.shift_kind == NQ_SHIFT_PERIODIC ? x - x_before : dR;
 #pragma unroll
         for (int q = 0; q < DPS / 4; ++q) {
           const float4 p = lds_f32x4(phi_addr + 16 * q);

@@ -152,6 +152,9 @@ class PiecewiseLinear(Parameterization):
     return jac
 
 
+_BASIS_CACHE = {}
+
+
 def chebyshev_coefficients(degree):
   """Rows j = 0..degree of monic Chebyshev-T_j in the power basis, highest power first."""
   rows = []
@@ -190,14 +193,24 @@ class Chebyshev(Parameterization):
     return np.stack(rows, 0)
 
   def basis(self, x):
-    """[len(x), degree+1] monic Chebyshev basis at 2x-1 (float32, power-basis evaluation)."""
+    """[len(x), degree+1] monic Chebyshev basis at 2x-1 (float32, power-basis evaluation).  The
+    basis depends on (degree, x) only, not on the weights: it is cached, so that an optimisation
+    loop which re-evaluates the schedule and its Jacobian on the same time grid pays once."""
     xs = np.atleast_1d(_f32(x))
+    key = (self.degree, xs.shape, xs.tobytes())
+    hit = _BASIS_CACHE.get(key)
+    if hit is not None:
+      return hit
     t = (F32(2) * xs - F32(1)).astype(F32)
     pw = self._powers(t)
     coef = self.coefficients.astype(F32)
     out = np.zeros((xs.shape[0], self.degree + 1), F32)
     for p in range(self.degree + 1):
       out = (out + (coef[:, p][None, :] * pw[p][:, None]).astype(F32)).astype(F32)
+    out.setflags(write=False)
+    if len(_BASIS_CACHE) >= 64:
+      _BASIS_CACHE.pop(next(iter(_BASIS_CACHE)))
+    _BASIS_CACHE[key] = out
     return out
 
   def __call__(self, x):

@@ -281,7 +281,15 @@ def estimate_gradient(pot, coeffs, x0, seed, r0_init, r0_final, Neq, S, dt, kT, 
   # d logp_k / d r_k = z_k/sigma * nu*dt*k_s  with z_k = (dR_k - mean_k)/sigma   (k = 1..S-1)
   z = ((out['dR'] / sc.sigma).astype(d) - (out['mean'] / sc.sigma).astype(d)).astype(d)
   a = (((z / sc.sigma).astype(d) * sc.nu).astype(d) * sc.dt * ks).astype(d)[:, :S - 1]
-  b = (ks * out['dR']).astype(d)[:, :S - 1]               # d W / d r_k = k_s dR_k
+  # d W / d r_k = -k_s (x_{k-1} - r_k) + k_s (x_k - r_k) = k_s (x_k - x_{k-1}) = k_s dR_k, except where a
+  # periodic shift wrapped the position (the trap energy itself is not periodic in the reference)
+  if shift in (None, 'free'):
+    step_dx = out['dR']
+  else:
+    if not record:
+      raise ValueError('periodic gradients need record=True (positions)')
+    step_dx = (out['positions'][:, 1:] - out['positions'][:, :-1]).astype(d)
+  b = (ks * step_dx).astype(d)[:, :S - 1]
   A = (a.astype(np.float64) @ phi.astype(np.float64))     # [B, D]
   Bm = (b.astype(np.float64) @ phi.astype(np.float64))
   g_logp = (total_work.astype(np.float64)[:, None] * A)
