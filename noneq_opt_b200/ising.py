@@ -171,22 +171,27 @@ def sum_neighbors(spins):
   return out
 
 
+def _param(x):
+  """A schedule value as a float32 CUDA scalar; torch tensors pass through (keeps autograd / vmap)."""
+  device = _lib.require_cuda()
+  if isinstance(x, torch.Tensor):
+    return x.to(device=device, dtype=torch.float32)
+  return torch.tensor(float(np.asarray(x)), dtype=torch.float32, device=device)
+
+
 def energy(state: IsingState):
   s = _as_cuda(state.spins).to(torch.float32)
-  field = float(np.asarray(_to_host(state.params.field)))
-  return (-s * (sum_neighbors(s) / 2 + field)).sum()
+  return (-s * (sum_neighbors(s) / 2 + _param(state.params.field))).sum()
 
 
 def log_prob(state: IsingState):
-  return -energy(state) / float(np.exp(np.asarray(_to_host(state.params.log_temp), np.float64)))
+  return -energy(state) / torch.exp(_param(state.params.log_temp))
 
 
 def flip_logits(spins, params: IsingParameters):
   """Log odds of a flip at each site under Glauber dynamics."""
   s = _as_cuda(spins).to(torch.float32)
-  field = float(np.asarray(_to_host(params.field)))
-  log_temp = float(np.asarray(_to_host(params.log_temp)))
-  return -2 * s * (sum_neighbors(s) + field) * float(np.exp(F32(-log_temp)))
+  return -2 * s * (sum_neighbors(s) + _param(params.field)) * torch.exp(-_param(params.log_temp))
 
 
 def even_odd_masks(shape):
@@ -408,12 +413,59 @@ _LOSS_KINDS = {total_work: 'work', total_entropy_production: 'entropy'}
 
 
 def _loss_kind(loss_function):
+  """'work' / 'entropy' for the two losses the reference ships (closed-form fast path), 'generic' for any
+  other callable `loss(initial_state, final_state, summary)` written with torch ops."""
+  if not callable(loss_function):
+    raise TypeError('loss_function must be callable')
   try:
-    return _LOSS_KINDS[loss_function]
-  except (KeyError, TypeError):
-    raise NotImplementedError(
-        'loss_function must be ising.total_work or ising.total_entropy_production: gradients are '
-        'assembled from closed-form per-sweep sensitivities, not traced autodiff') from None
+    return _LOSS_KINDS.get(loss_function, 'generic')
+  except TypeError:
+    return 'generic'
+
+
+def _generic_loss_sensitivities(loss_function, run: _Run, log_temp, field, L, initial_spins, final_spins):
+  """Arbitrary LossFn (ising.py:177): the loss is evaluated per replica with torch (vmap) on the
+  summary and the two end-point states; torch autograd gives d loss / d summary and
+  d loss / d end-point parameters, and the chain rule to the schedule tables uses the same closed-form
+  per-sweep sensitivities as the built-in losses:
+     work_t = -(h_t - h_{t-1}) M_{t-1}          heat_t = dB_t + h_t dM_t          energy_t = -(B_t + h_t M_t)
+     d fwd_lp_t, d rev_lp_t / d(h_t, lt_t) from the kernel's partials; entropy_production = fwd - rev."""
+  n_sites = float(np.prod(_shape_of(L)))
+  S32 = run.summary                                              # [7, R, T-1]
+  R, Tm1 = S32.shape[1], S32.shape[2]
+  T = Tm1 + 1
+  dev = S32.device
+  lt = torch.from_numpy(np.asarray(log_temp, F32)).to(dev)
+  h = torch.from_numpy(np.asarray(field, F32)).to(dev)
+  spins0 = _as_cuda(initial_spins).to(torch.float32)
+
+  def per_replica(summ, fin, lt0, h0, ltf, hf):
+    initial_state = IsingState(spins0, IsingParameters(lt0, h0))
+    final_state = IsingState(fin, IsingParameters(ltf, hf))
+    out = loss_function(initial_state, final_state, IsingSummary(*summ.unbind(0)))
+    return out, out
+
+  grad_fn = torch.func.vmap(torch.func.grad(per_replica, argnums=(0, 2, 3, 4, 5), has_aux=True),
+                            in_dims=(1, 0, None, None, None, None))
+  (g_summ, g_lt0, g_h0, g_ltf, g_hf), loss = grad_fn(S32, final_spins.to(torch.float32), lt[0], h[0], lt[-1], h[-1])
+  g = g_summ.to(torch.float64)                                   # [R, 7, T-1]
+  P = run.partials.to(torch.float64)
+  M0 = run.MB0[:, 0].to(torch.float64).expand(R)
+  M_after = torch.round(S32[_lib.NQ_IS_MAG].to(torch.float64) * n_sites)
+  M_before = torch.cat([M0[:, None], M_after[:, :-1]], 1)
+  dL_dh = torch.zeros((R, T), dtype=torch.float64, device=dev)
+  dL_dl = torch.zeros((R, T), dtype=torch.float64, device=dev)
+  gW, gQ, gF, gR, gE, gEn = (g[:, i] for i in (_lib.NQ_IS_WORK, _lib.NQ_IS_HEAT, _lib.NQ_IS_FWD, _lib.NQ_IS_REV,
+                                              _lib.NQ_IS_EP, _lib.NQ_IS_ENERGY))
+  dL_dh[:, 1:] += -gW * M_before + gQ * (M_after - M_before) - gEn * M_after
+  dL_dh[:, :-1] += gW * M_before
+  dL_dh[:, 1:] += (gF + gE) * P[_lib.NQ_IS_DFWD_DH] + (gR - gE) * P[_lib.NQ_IS_DREV_DH]
+  dL_dl[:, 1:] += (gF + gE) * P[_lib.NQ_IS_DFWD_DL] + (gR - gE) * P[_lib.NQ_IS_DREV_DL]
+  dL_dh[:, 0] += g_h0.to(torch.float64)
+  dL_dl[:, 0] += g_lt0.to(torch.float64)
+  dL_dh[:, -1] += g_hf.to(torch.float64)
+  dL_dl[:, -1] += g_ltf.to(torch.float64)
+  return loss.to(torch.float32), dL_dh, dL_dl
 
 
 def _loss_and_sensitivities(kind, run: _Run, log_temp, field, L):
@@ -488,7 +540,11 @@ def _gradient_terms(loss_function, schedule, times, initial_spins, seed, checkpo
   if checkpoint_every is not None:
     control_flow.check_divides(len(times) - 1, checkpoint_every)
   run = _run_kernel(log_temp, field, bits, broadcast, seeds, L, want_partials=True)
-  loss, dL_dh, dL_dl = _loss_and_sensitivities(kind, run, log_temp, field, L)
+  if kind == 'generic':
+    final_spins = _unpack(run.final_bits, L, torch.zeros((), dtype=torch.float32))
+    loss, dL_dh, dL_dl = _generic_loss_sensitivities(loss_function, run, log_temp, field, L, spins, final_spins)
+  else:
+    loss, dL_dh, dL_dl = _loss_and_sensitivities(kind, run, log_temp, field, L)
   P = run.partials.to(torch.float64)
   dev = P.device
   R = P.shape[1]

@@ -333,3 +333,54 @@ def test_lattice_larger_than_shared_memory(cuda):
   np.testing.assert_array_equal(final.spins[1].cpu().numpy(), fin_o)
   check_summary(np.stack([getattr(summary, f)[1].cpu().numpy() for f in FIELDS]),
                 np.stack([getattr(summ_o, f) for f in FIELDS]), L * L)
+
+
+def test_arbitrary_loss_function_through_torch_autograd(cuda):
+  """LossFn is an arbitrary callable in the reference (ising.py:177).  A loss written with torch ops is
+  differentiated wrt the summary / end-point states by torch autograd and chained analytically to the
+  schedule; checked against the closed-form fast path and against brute-force finite differences."""
+  from noneq_opt_b200 import ising, parameterization as p10n
+  T, R = 6, 4
+  w = (0.1 * np.random.RandomState(0).normal(size=(2, 8))).astype(np.float32)
+  sched = _schedule(w)
+  times = np.linspace(0, 1, T, dtype=np.float32)
+  s0 = -np.ones((10, 10), np.float32)
+  seeds = J.split(J.PRNGKey(5), R)
+
+  def flat(g):
+    return np.concatenate([g.log_temp.wrapped.wrapped.weights.cpu().numpy(), g.field.wrapped.wrapped.weights.cpu().numpy()], -1)
+
+  def my_work(initial_state, final_state, summary):
+    return summary.work.sum()
+
+  def my_entropy(initial_state, final_state, summary):
+    return summary.entropy_production.sum() + ising.log_prob(initial_state) - ising.log_prob(final_state)
+
+  for custom, builtin in ((my_work, ising.total_work), (my_entropy, ising.total_entropy_production)):
+    g_c, _ = ising.estimate_gradient_rev(custom)(sched, times, s0, seeds)
+    g_b, _ = ising.estimate_gradient_rev(builtin)(sched, times, s0, seeds)
+    np.testing.assert_allclose(flat(g_c), flat(g_b), rtol=2e-4, atol=2e-4 * np.abs(flat(g_b)).max())
+
+  def exotic(initial_state, final_state, summary):
+    return (1e-3 * (summary.dissipated_heat ** 2).sum() + 0.1 * summary.energy[-1] + 0.01 * summary.forward_log_prob.sum()
+            - summary.reverse_log_prob.mean() + 0.05 * ising.energy(final_state))
+
+  def exotic_oracle(initial_spins, final_spins, log_temp, field, summary, dtype=np.float32):
+    return (1e-3 * (np.asarray(summary.dissipated_heat, np.float64) ** 2).sum() + 0.1 * summary.energy[-1]
+            + 0.01 * np.sum(summary.forward_log_prob) - np.mean(summary.reverse_log_prob)
+            + 0.05 * I.energy(final_spins, field[-1], np.float64))
+
+  I.LOSSES['exotic'] = exotic_oracle
+  try:
+    def sched_fn(wl, wh, ts):
+      d = wl.dtype.type
+      lt = P.AddBaseline(P.ConstrainEndpoints(P.Chebyshev(wl, d), 0., 0.), P.log_temp_baseline(dtype=d))
+      hh = P.AddBaseline(P.ConstrainEndpoints(P.Chebyshev(wh, d), 0., 0.), P.field_baseline(dtype=d))
+      return lt(ts.astype(d)), hh(ts.astype(d))
+    g, _ = ising.estimate_gradient_rev(exotic)(sched, times, s0, seeds[2])
+    fd = I.fd_gradient('exotic', sched_fn, w[0].astype(np.float64), w[1].astype(np.float64), times.astype(np.float64),
+                       s0.astype(np.int32), seeds[2])
+    ref = np.concatenate(fd['reinforce'])
+    assert rel(flat(g), ref) < 5e-4
+  finally:
+    del I.LOSSES['exotic']
