@@ -189,7 +189,12 @@ typedef struct NqIsingDesc {
 } NqIsingDesc;
 
 size_t nq_ising_words_per_lattice(int32_t L); /* = L*L/32 (bit b of word w = site 32*w+b, row-major; 1 = spin +1) */
-size_t nq_ising_workspace_bytes(const NqIsingDesc* desc); /* 0 unless the lattice exceeds shared memory on the generic path */
+/* Scratch nq_ising_run wants for this shape on the current device.  Required (NQ_ERR_WORKSPACE
+ * otherwise) when the lattice exceeds shared memory (L >= 2048, or a large general lattice).
+ * Optional for 512 <= L <= 1024 with R above and not a multiple of the SM count: there it holds the
+ * replicas between time segments so that the last, partly filled round of CTAs is 1/n as long;
+ * without it the run is one CTA per replica and gives bit-identical results. */
+size_t nq_ising_workspace_bytes(const NqIsingDesc* desc);
 
 /* simulate_ising (ising.py:153-173) for R replicas: T-1 x update (:129-150), each two
  * masked_update half-sweeps (:109-126, odd-parity sites first :99-106), with

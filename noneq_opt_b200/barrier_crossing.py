@@ -70,7 +70,7 @@ def _desc(energy_fn, shift, steps, Neq, dt, kT, mass, gamma):
 def _dev_f32(a, device):
   if isinstance(a, torch.Tensor):
     return a.to(device=device, dtype=torch.float32).contiguous()
-  return torch.from_numpy(np.ascontiguousarray(np.asarray(a, np.float32))).to(device)
+  return torch.from_numpy(np.array(a, dtype=np.float32, order="C")).to(device)
 
 
 def _is_batched_key(key):

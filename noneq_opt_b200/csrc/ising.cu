@@ -100,6 +100,13 @@ struct IsingShape {
   signed char* scratch;  // generic path: global spin scratch [R][N] when N does not fit shared memory
   uint32_t* lat_global;  // fast path, lattices beyond shared memory: colour planes [R][2][L][NW] in HBM/L2
   uint32_t one;          // = 1 at run time (see threefry2x32_allmad)
+  // segment scheduling (CTA-team kernel, R not a multiple of the resident CTAs): the T-1 sweeps of a
+  // replica are cut into n_seg segments handed out through a ticket counter, so the last wave is
+  // 1/n_seg as long.  Between segments a replica lives in seg_lat / seg_mb.
+  int n_seg;
+  unsigned* seg_ctl;     // [0] ticket counter, [1 + r] segments of replica r completed (zeroed per launch)
+  long long* seg_mb;     // [R][2] spin sum, bond sum carried between segments
+  uint32_t* seg_lat;     // [R][2][L][NW] colour planes carried between segments
 };
 
 struct IsingIO {
@@ -334,8 +341,9 @@ __device__ __forceinline__ void sweep_keys(const KeySchedule& ks_rep, int t, int
 // Shared memory: spread[4][256] | per team: lattice[2][L][NW], thr[2][16] | (CTA team) hist[2][2][2][16]
 // GLOBAL_LAT: the colour planes of a replica live in global memory (L2-resident) instead of shared
 // memory -- same code, for lattices whose 2 x L x L/64 words exceed 227 KB (L >= 2048).
-template <bool WARP_TEAM, bool GLOBAL_LAT = false>
+template <bool WARP_TEAM, bool GLOBAL_LAT = false, bool SEG = false>
 __global__ void __launch_bounds__(WARP_TEAM ? 128 : 1024, WARP_TEAM ? NQ_ISING_MINB : 1) ising_fast_kernel(const IsingShape sh, const IsingIO io) {
+  static_assert(!SEG || (!WARP_TEAM && !GLOBAL_LAT), "segments are scheduled per CTA with the lattice in shared memory");
   extern __shared__ uint32_t smem[];
   uint32_t* spread = smem;
   const int L = sh.L, NW = sh.NW, T = sh.T;
@@ -360,28 +368,67 @@ __global__ void __launch_bounds__(WARP_TEAM ? 128 : 1024, WARP_TEAM ? NQ_ISING_M
   if (!WARP_TEAM)
     for (int v = threadIdx.x; v < 2 * 2 * 2 * kIsingClasses; v += blockDim.x) hist_s[v] = 0;
   __syncthreads();
-  const long long rep = (long long)blockIdx.x * nteams + team;
-  if (rep >= sh.R) return;  // whole team leaves together (warp-uniform / CTA-uniform)
   auto team_sync = [&]() {
     if (WARP_TEAM) __syncwarp(); else __syncthreads();
   };
+  const size_t ext_words = (size_t)L * L / 32;
+  __shared__ unsigned ticket_s;
+  for (;;) {  // one pass per (replica, segment); a single pass when !SEG
+  long long rep = (long long)blockIdx.x * nteams + team;
+  int seg = 0, t_first = 1, t_end = T;
+  if (SEG) {
+    const unsigned total = (unsigned)sh.R * (unsigned)sh.n_seg;
+    if (threadIdx.x == 0) {
+      const unsigned it = atomicAdd(&sh.seg_ctl[0], 1u);
+      if (it < total && it >= (unsigned)sh.R) {
+        // the previous segment of this replica was handed out R tickets ago: it is running or done
+        const volatile unsigned* done = sh.seg_ctl + 1 + it % (unsigned)sh.R;
+        const unsigned want = it / (unsigned)sh.R;
+        unsigned polls = 0;
+        while (*done < want) {
+          __nanosleep(256);
+          if (++polls > (1u << 24)) __trap();  // bounded wait: a lost segment must not hang the device
+        }
+        __threadfence();
+      }
+      ticket_s = it;
+    }
+    __syncthreads();
+    const unsigned it = ticket_s;
+    __syncthreads();
+    if (it >= total) return;
+    rep = it % (unsigned)sh.R;
+    seg = it / (unsigned)sh.R;
+    t_first = 1 + (int)((long long)seg * (T - 1) / sh.n_seg);
+    t_end = 1 + (int)((long long)(seg + 1) * (T - 1) / sh.n_seg);
+  } else if (rep >= sh.R) {
+    return;  // whole team leaves together (warp-uniform / CTA-uniform)
+  }
 
   // ---- load the lattice (row-major bits -> colour planes)
-  const size_t ext_words = (size_t)L * L / 32;
-  const uint32_t* ext0 = io.spins0 + (sh.broadcast0 ? 0 : rep * ext_words);
-  for (int u = tid; u < L * NW; u += tsize) {
-    const int r = u / NW, w = u - r * NW;
-    uint32_t c0, c1;
-    split_colours(r, ext0[r * (L / 32) + 2 * w], ext0[r * (L / 32) + 2 * w + 1], c0, c1);
-    lat[u] = c0;
-    lat[L * NW + u] = c1;
+  if (SEG && seg > 0) {
+    const uint32_t* src = sh.seg_lat + (size_t)rep * lat_words;
+    for (int u = tid; u < lat_words; u += tsize) lat[u] = __ldcg(src + u);  // written by another SM: skip L1
+  } else {
+    const uint32_t* ext0 = io.spins0 + (sh.broadcast0 ? 0 : rep * ext_words);
+    for (int u = tid; u < L * NW; u += tsize) {
+      const int r = u / NW, w = u - r * NW;
+      uint32_t c0, c1;
+      split_colours(r, ext0[r * (L / 32) + 2 * w], ext0[r * (L / 32) + 2 * w + 1], c0, c1);
+      lat[u] = c0;
+      lat[L * NW + u] = c1;
+    }
   }
-  if (T > 1) build_pair_table(thr_s + 256, io.thr, tid, tsize);  // sweep 1 -> buffer 1
+  if (t_first < t_end)  // first sweep of the pass -> the buffer of its parity
+    build_pair_table(thr_s + (t_first & 1) * 256, io.thr + (size_t)(t_first - 1) * kIsingClasses, tid, tsize);
   team_sync();
 
   // ---- initial spin sum M and bond sum B (each bond joins a colour-0 and a colour-1 site)
   long long M, B;
-  {
+  if (SEG && seg > 0) {
+    M = __ldcg(sh.seg_mb + 2 * rep);
+    B = __ldcg(sh.seg_mb + 2 * rep + 1);
+  } else {
     int hA[10], hF[10];
 #pragma unroll
     for (int k = 0; k < 10; ++k) hA[k] = hF[k] = 0;
@@ -413,11 +460,11 @@ __global__ void __launch_bounds__(WARP_TEAM ? 128 : 1024, WARP_TEAM ? NQ_ISING_M
 
   const KeySchedule ks_rep = key_schedule(io.seeds[2 * rep], io.seeds[2 * rep + 1]);
   const int units = (L / 2) * NW;
-  for (int t = 1; t < T; ++t) {
+  for (int t = t_first; t < t_end; ++t) {
     KeySchedule kh[2];
     sweep_keys(ks_rep, t, T, sh.direct_keys != 0, kh[0], kh[1]);
     const uint2* thr_cur = thr_s + (t & 1) * 256;
-    if (t + 1 < T) build_pair_table(thr_s + ((t + 1) & 1) * 256, io.thr + (size_t)t * kIsingClasses, tid, tsize);
+    if (t + 1 < t_end) build_pair_table(thr_s + ((t + 1) & 1) * 256, io.thr + (size_t)t * kIsingClasses, tid, tsize);
     int At[2][10], Ft[2][10];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
@@ -480,7 +527,14 @@ __global__ void __launch_bounds__(WARP_TEAM ? 128 : 1024, WARP_TEAM ? NQ_ISING_M
     }
   }
   team_sync();
-  if (io.spins_out) {
+  if (SEG && seg + 1 < sh.n_seg) {
+    uint32_t* dst = sh.seg_lat + (size_t)rep * lat_words;
+    for (int u = tid; u < lat_words; u += tsize) dst[u] = lat[u];
+    if (threadIdx.x == 0) {  // warp 0 carries M, B (emit_summary)
+      sh.seg_mb[2 * rep] = M;
+      sh.seg_mb[2 * rep + 1] = B;
+    }
+  } else if (io.spins_out) {
     uint32_t* dst = io.spins_out + (size_t)rep * ext_words;
     for (int u = tid; u < L * NW; u += tsize) {
       const int r = u / NW, w = u - r * NW;
@@ -489,6 +543,13 @@ __global__ void __launch_bounds__(WARP_TEAM ? 128 : 1024, WARP_TEAM ? NQ_ISING_M
       dst[r * (L / 32) + 2 * w] = lo;
       dst[r * (L / 32) + 2 * w + 1] = hi;
     }
+  }
+  if (!SEG) break;
+  __syncthreads();  // every thread's stores are ordered before thread 0's fence + publish
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicExch(&sh.seg_ctl[1 + rep], (unsigned)(seg + 1));
+  }
   }
 }
 
@@ -653,6 +714,53 @@ static size_t fast_smem_bytes(int L, bool warp_team, int nteams, bool global_lat
   if (!warp_team) words += 2 * 2 * 2 * kIsingClasses + 2;
   return words * 4;
 }
+
+// Segment scheduling plan for the CTA-team kernel (see IsingShape::n_seg).  R replicas on `slots`
+// resident CTAs take ceil(R / slots) rounds; cutting every replica into n segments makes that
+// ceil(R n / slots) / n.  n = 1 (off) unless some n <= 16 saves at least 3 %.
+struct SegPlan {
+  int n_seg = 1;
+  int grid = 0;
+  size_t ctl_bytes = 0, mb_bytes = 0, lat_bytes = 0;
+  size_t bytes() const { return ctl_bytes + mb_bytes + lat_bytes; }
+};
+template <bool W, bool G, bool S>
+__global__ void ising_fast_kernel(const IsingShape, const IsingIO);
+static SegPlan plan_segments(int L, long long R, int T) {
+  SegPlan p;
+  if (L <= 128 || R * 16 >= 0xffffffffll || T - 1 < 2) return p;
+  const size_t smem = fast_smem_bytes(L, false, 1);
+  if (smem > 227 * 1024) return p;
+  const int units = (L / 2) * (L / 64);
+  const int threads = units >= 1024 ? 1024 : ((units + 31) / 32) * 32;
+  int dev = 0, sms = 0, occ = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      cudaFuncSetAttribute(ising_fast_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ising_fast_kernel<false, false, true>, threads, smem) != cudaSuccess) {
+    cudaGetLastError();  // no device (host-only symbol checks): no plan
+    return p;
+  }
+  // with two or more CTAs per SM a lone CTA in the last round already runs faster: measured no gain
+  if (occ != 1) return p;
+  const long long slots = sms;
+  if (slots <= 0 || R <= slots || R % slots == 0) return p;
+  double best = (double)((R + slots - 1) / slots);
+  const int n_max = T - 1 < 16 ? T - 1 : 16;
+  for (int n = 2; n <= n_max; ++n) {
+    const double rounds = (double)((R * n + slots - 1) / slots) / n;
+    if (rounds < 0.97 * best) {
+      best = rounds;
+      p.n_seg = n;
+    }
+  }
+  if (p.n_seg == 1) return p;
+  p.grid = (int)slots;
+  p.ctl_bytes = (((size_t)R + 1) * 4 + 15) / 16 * 16;
+  p.mb_bytes = (size_t)R * 2 * 8;
+  p.lat_bytes = (size_t)R * 2 * L * (L / 64) * 4;
+  return p;
+}
 static size_t generic_smem_bytes(long long N) {
   return (2 * 2 * kIsingClasses + 2 + kIsingClasses) * 4 + (((size_t)N + 3) / 4) * 4;
 }
@@ -685,7 +793,8 @@ extern "C" size_t nq_ising_workspace_bytes(const NqIsingDesc* desc) {
   const int ndim = lattice_dims(desc, dims);
   const long long N = (long long)dims[0] * dims[1] * dims[2];
   if (ndim == 2 && dims[0] == dims[1] && fast_path(dims[0])) {
-    if (fast_smem_bytes(dims[0], dims[0] <= 128, dims[0] <= 128 ? 4 : 1) <= 227 * 1024) return 0;
+    if (fast_smem_bytes(dims[0], dims[0] <= 128, dims[0] <= 128 ? 4 : 1) <= 227 * 1024)
+      return plan_segments(dims[0], desc->R, desc->T).bytes();  // optional: without it the run is unsegmented
     return (size_t)desc->R * 2 * dims[0] * (dims[0] / 64) * 4;   // colour planes in global memory
   }
   if (generic_smem_bytes(N) <= 200 * 1024) return 0;
@@ -716,7 +825,7 @@ extern "C" int nq_ising_run(const NqIsingDesc* desc, const uint32_t* thr, const 
   NQ_CHECK_ARG(desc->sweep_key_mode == 0 || (desc->sweep_key_mode == 1 && T == 2), "sweep_key_mode 1 needs T == 2");
   const int L = dims[0];
   IsingShape sh{L, L / 64, T, desc->R, desc->spins0_broadcast, desc->sweep_key_mode, ndim, dims[0], dims[1], dims[2],
-                (int)N, nullptr, nullptr, 1u};
+                (int)N, nullptr, nullptr, 1u, 1, nullptr, nullptr, nullptr};
   IsingIO io{thr, lut, field, log_temp, spins0, seeds, spins_out, summary, partials, counts, states};
   cudaStream_t st = (cudaStream_t)stream;
   const bool square2d = ndim == 2 && dims[0] == dims[1];
@@ -741,8 +850,19 @@ extern "C" int nq_ising_run(const NqIsingDesc* desc, const uint32_t* thr, const 
       NQ_CUDA(cudaFuncSetAttribute(ising_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       ising_fast_kernel<true><<<blocks, threads, smem, st>>>(sh, io);
     } else {
-      NQ_CUDA(cudaFuncSetAttribute(ising_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      ising_fast_kernel<false><<<blocks, threads, smem, st>>>(sh, io);
+      const SegPlan plan = plan_segments(L, desc->R, T);
+      if (plan.n_seg > 1 && workspace != nullptr && workspace_bytes >= plan.bytes() && getenv("NQ_ISING_NO_SEGMENTS") == nullptr) {
+        char* ws = (char*)workspace;
+        sh.n_seg = plan.n_seg;
+        sh.seg_ctl = (unsigned*)ws;
+        sh.seg_mb = (long long*)(ws + plan.ctl_bytes);
+        sh.seg_lat = (uint32_t*)(ws + plan.ctl_bytes + plan.mb_bytes);
+        NQ_CUDA(cudaMemsetAsync(sh.seg_ctl, 0, plan.ctl_bytes, st));
+        ising_fast_kernel<false, false, true><<<plan.grid, threads, smem, st>>>(sh, io);
+      } else {
+        NQ_CUDA(cudaFuncSetAttribute(ising_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ising_fast_kernel<false><<<blocks, threads, smem, st>>>(sh, io);
+      }
     }
   } else {
     size_t smem = generic_smem_bytes(N);

@@ -384,3 +384,41 @@ def test_arbitrary_loss_function_through_torch_autograd(cuda):
     assert rel(flat(g), ref) < 5e-4
   finally:
     del I.LOSSES['exotic']
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('L,R,T', [(512, 149, 9), (1024, 150, 6)])
+def test_segment_scheduled_run_is_bit_identical(cuda, L, R, T, monkeypatch):
+  """When R is not a multiple of the resident CTAs, nq_ising_run cuts every replica's sweeps into
+  segments handed out through a ticket counter (lattice, M and B carried through the workspace).
+  Outputs must be bit-identical to the one-CTA-per-replica launch, and one replica to the oracle."""
+  import torch
+  from noneq_opt_b200 import ising
+  lt = np.log(np.linspace(2.6, 2.0, T).astype(np.float32))
+  h = np.linspace(-0.3, 0.3, T).astype(np.float32)
+  params = ising.IsingParameters(lt, h)
+  s0 = I.random_spins((L, L), .5, J.PRNGKey(21))
+  seeds = J.split(J.PRNGKey(4), R)
+
+  def run():
+    final, summary = ising.simulate_ising(params, s0, seeds, return_states=(L == 512))
+    states = None
+    if L == 512:
+      summary, states = summary
+    out = [final.spins] + [getattr(summary, f) for f in FIELDS]
+    if states is not None:
+      out.append(states.spins[-3:])
+    torch.cuda.synchronize()
+    return [o.clone() for o in out]
+
+  seg = run()
+  monkeypatch.setenv('NQ_ISING_NO_SEGMENTS', '1')
+  flat = run()
+  monkeypatch.delenv('NQ_ISING_NO_SEGMENTS')
+  for a, b in zip(seg, flat):
+    assert torch.equal(a, b)
+  r = R - 2
+  fin_o, summ_o = I.simulate_ising(lt, h, s0, seeds[r])
+  np.testing.assert_array_equal(seg[0][r].cpu().numpy(), fin_o)
+  check_summary(np.stack([seg[1 + i][r].cpu().numpy() for i in range(len(FIELDS))]),
+                np.stack([getattr(summ_o, f) for f in FIELDS]), L * L)
