@@ -228,6 +228,50 @@ int nq_ising_unpack(const uint32_t* bits, int64_t n_sites, int32_t is_float, voi
 int nq_ising_measure(const uint32_t* bits, int32_t ndim, const int32_t dims[3] /*host*/, int64_t R,
                      int64_t* out_MB, void* stream);
 
+/* ------------------------------------------------------------------ device-resident training step */
+/* The pieces that let one optimisation step of the reference's drivers
+ * (run_barrier_crossing_opt.py:113-137; ising.py:263-290) run as a fixed launch sequence with
+ * every operand in device memory, so that the host captures it once in a CUDA graph.          */
+
+/* jax.random.split(key, num)[first : first+count] with the key READ FROM DEVICE MEMORY
+ * (`key, a, b = split(key, 3)` of run_barrier_crossing_opt.py:125 without a host round trip). */
+int nq_random_split_dev(const uint32_t* key_dev /*device [2]*/, int64_t num, int64_t first, int64_t count,
+                        uint32_t* out, void* stream);
+
+/* Protocol table from its variables: table[0] = first, table[K+1] = last,
+ *   table[1+i] = offset[i] + sum_j variables[j] * basis[i][j]      (offset nullable)
+ * i.e. MakeSchedule_chebyshev (barrier_crossing.py:145-151) for basis = the monic Chebyshev basis
+ * on the step grid, and any other Parameterization of parameterization.py:67-344 (all are affine in
+ * their variables) for basis = its Jacobian, offset = its value at variables = 0.  basis is the
+ * same [K][D] array nq_langevin_grad takes as phi.                                              */
+int nq_schedule_affine(const float* basis, const float* variables, const float* offset, float first, float last,
+                       int64_t K, int32_t D, float* table /*[K+2]*/, void* stream);
+
+typedef struct NqAdamDesc {
+  double step_size, decay_steps, decay_rate; /* lr(i) = step_size * decay_rate^(i/decay_steps);
+                                                decay_steps <= 0: constant  (optimizers.exponential_decay) */
+  double b1, b2, eps;                        /* optimizers.adam defaults 0.9, 0.999, 1e-8 */
+  double max_norm;                           /* optimizers.clip_grads (ising.py:287); <= 0: no clipping */
+  double w0, w1, denom;                      /* g = (w0*grad_sums0 + w1*grad_sums1) / denom  (barrier_crossing.py:222) */
+} NqAdamDesc;
+
+/* clip_grads + jax.example_libraries.optimizers.adam update of x[P] (binary32, one rounding per
+ * operation, as the reference computes it), with the gradient taken either from the float64 sums
+ * nq_langevin_grad leaves on the device (grad_sums1 nullable) or from grad_f32[P]; increments the
+ * device step counter; grad_out (nullable) receives the clipped gradient.                       */
+int nq_adam_step(const NqAdamDesc* desc /*host*/, int32_t P, const double* grad_sums0, const double* grad_sums1,
+                 const float* grad_f32, float* x, float* m, float* v, int64_t* step_dev, float* grad_out,
+                 void* stream);
+
+/* ------------------------------------------------------------------ multi-GPU combine */
+/* The one collective of the path: in-place sum of `n` f64 values (gradient sums and
+ * moments) over the ranks of `nccl_comm`, an ncclComm_t the CALLER created.  The reference has no
+ * multi-device code; each rank runs its contiguous slice of split(seed, B) and calls this once.
+ * ncclAllReduce is resolved at run time from the libnccl the process already holds (else the
+ * system one), so the library itself carries no NCCL link dependency.  nq_langevin_grad /
+ * nq_ising_run leave their sums on the device; enqueue this on the same stream.               */
+int nq_allreduce_f64(void* nccl_comm, double* buf /*device [n]*/, int64_t n, void* stream);
+
 /* ------------------------------------------------------------------ calibration */
 /* issue-rate microbenchmark: runs `iters` dependent-chain iterations of
  * instruction mix `which` on `blocks` x `threads`; elapsed SM cycles (max over blocks) -> host out.

@@ -35,6 +35,11 @@ class NqIsingDesc(C.Structure):
               ('ndim', C.c_int32), ('dims', C.c_int32 * 3)]
 
 
+class NqAdamDesc(C.Structure):
+  _fields_ = [(n, C.c_double) for n in ('step_size', 'decay_steps', 'decay_rate', 'b1', 'b2', 'eps', 'max_norm',
+                                        'w0', 'w1', 'denom')]
+
+
 _P = C.c_void_p
 _KEY = C.POINTER(C.c_uint32)
 
@@ -67,6 +72,10 @@ SIGNATURES = {
     'nq_ising_pack': (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P]),
     'nq_ising_unpack': (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P]),
     'nq_ising_measure': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.c_int64, _P, _P]),
+    'nq_random_split_dev': (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, _P, _P]),
+    'nq_schedule_affine': (C.c_int, [_P, _P, _P, C.c_float, C.c_float, C.c_int64, C.c_int32, _P, _P]),
+    'nq_adam_step': (C.c_int, [C.POINTER(NqAdamDesc), C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'nq_allreduce_f64': (C.c_int, [_P, _P, C.c_int64, _P]),
     'nq_microbench': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
 }
 

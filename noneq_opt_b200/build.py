@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libnoneq_b200.so')
 STAMP = os.path.join(HERE, 'csrc', '.build_stamp')
 SOURCES = ['core.cu', 'langevin.cu', 'langevin_pot_spring.cu', 'langevin_pot_biomolecule.cu', 'langevin_pot_shifted.cu',
-           'ising.cu', 'microbench.cu']
+           'ising.cu', 'train.cu', 'microbench.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr'] + os.environ.get('NQ_EXTRA_NVCC_FLAGS', '').split()
 

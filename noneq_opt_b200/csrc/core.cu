@@ -2,6 +2,8 @@
 // key / bits / uniform / normal generators.
 #include <string.h>
 
+#include <dlfcn.h>
+
 #include "nq_common.cuh"
 
 namespace nq {
@@ -66,6 +68,35 @@ using namespace nq;
 extern "C" int nq_version(void) { return NQ_VERSION; }
 extern "C" const char* nq_last_error(void) { return g_err; }
 extern "C" uint64_t nq_launch_count(void) { return g_launches.load(); }
+
+// ncclAllReduce(sendbuf, recvbuf, count, ncclFloat64 = 8, ncclSum = 0, comm, stream), looked up once
+typedef int (*NcclAllReduceFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+static NcclAllReduceFn find_nccl_allreduce() {
+  static std::atomic<NcclAllReduceFn> cached{nullptr};
+  NcclAllReduceFn fn = cached.load();
+  if (fn) return fn;
+  void* h = dlopen("libnccl.so.2", RTLD_LAZY | RTLD_NOLOAD);  // the copy torch (or the caller) already loaded
+  if (!h) h = dlopen("libnccl.so.2", RTLD_LAZY);
+  if (!h) h = dlopen("libnccl.so", RTLD_LAZY);
+  if (h) fn = (NcclAllReduceFn)dlsym(h, "ncclAllReduce");
+  if (fn) cached.store(fn);
+  return fn;
+}
+
+extern "C" int nq_allreduce_f64(void* nccl_comm, double* buf, int64_t n, void* stream) {
+  NQ_CHECK_ARG(nccl_comm != nullptr && buf != nullptr && n >= 1, "need a communicator, a buffer and n >= 1");
+  NcclAllReduceFn fn = find_nccl_allreduce();
+  if (!fn) {
+    set_error("libnccl.so.2 is not loadable in this process: %s", dlerror());
+    return NQ_ERR_CUDA;
+  }
+  const int rc = fn(buf, buf, (size_t)n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, nccl_comm, (cudaStream_t)stream);
+  if (rc != 0) {
+    set_error("ncclAllReduce failed with ncclResult_t %d", rc);
+    return NQ_ERR_CUDA;
+  }
+  return NQ_OK;
+}
 
 extern "C" int nq_random_split(const uint32_t key[2], int64_t num, int64_t first, int64_t count, uint32_t* out,
                                void* stream) {

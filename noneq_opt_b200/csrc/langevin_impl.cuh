@@ -22,6 +22,18 @@
 #ifndef NQ_TF_FORCE_IMAD
 #define NQ_TF_FORCE_IMAD 0
 #endif
+#ifndef NQ_FAST_EXP   // precision-study toggles of the FAST path (scripts/precision_study.py)
+#define NQ_FAST_EXP 0
+#endif
+#ifndef NQ_FAST_RCP
+#define NQ_FAST_RCP 0
+#endif
+#ifndef NQ_FAST_NORMAL
+#define NQ_FAST_NORMAL 0
+#endif
+#ifndef NQ_FAST_WORK
+#define NQ_FAST_WORK 0
+#endif
 #ifndef NQ_TF_WIDE_MASK
 #define NQ_TF_WIDE_MASK 0
 #endif
@@ -264,17 +276,30 @@ __device__ __forceinline__ float fast_mean(const LangevinConsts& c, float x, flo
   if (POT == NQ_POT_SPRING) return -c.f_cu * u;
   const float ul = POT == NQ_POT_BIOMOLECULE ? x + c.xm : x;
   const float ur = POT == NQ_POT_BIOMOLECULE ? x - c.xm : x - c.two_xm;
+#if NQ_FAST_EXP == 1
+  const float A = expf(c.cl * (ul * ul));
+  const float B = expf(-fmaf(c.cr, ur * ur, c.bde));
+#else
   const float A = ex2_approx(c.f_cl2 * (ul * ul));                    // exp(cl ul^2)
   const float B = ex2_approx(fmaf(c.f_ncr2, ur * ur, c.f_nbde2));     // exp(-(cr ur^2 + beta dE))
+#endif
   // -dEm/dx * nu dt = (nu dt / beta) (2 cl A ul - 2 cr B ur) / (A + B)
   const float num = fmaf(c.f_clm, A * ul, -c.f_crm * (B * ur));
+#if NQ_FAST_RCP == 1
+  return fmaf(-c.f_cu, u, __fdiv_rn(num, A + B));
+#else
   return fmaf(-c.f_cu, u, num * rcp_approx(A + B));
+#endif
 }
 
 template <int POT>
 __device__ __forceinline__ float fast_step(const LangevinConsts& c, float& x, uint32_t bits, float r, float& z) {
   const float mean = fast_mean<POT>(c, x, r);
+#if NQ_FAST_NORMAL == 1
+  z = normal_from_bits<false>(bits);
+#else
   z = normal_from_bits_fast(bits);
+#endif
   const float dR = fmaf(z, c.sigma, mean);
   x += dR;
   if (c.shift_kind == NQ_SHIFT_PERIODIC) x = py_mod(x, c.box);
@@ -408,6 +433,13 @@ __device__ __forceinline__ void langevin_chunk(const LangevinConsts& c, const La
       if (FAST) {
         const float4 tab = lds_f32x4(tab_addr);
         dW = fmaf(tab.y, x, tab.z);
+#if NQ_FAST_WORK == 1
+        {
+          Landscape<POT, false> ls;
+          ls.eval(c, x);
+          dW = work_increment<POT, false>(c, ls, x, lds_f32(r_addr), tab.x);
+        }
+#endif
         dR = fast_step<POT>(c, x, rng.next(c.one, c.pow2), tab.x, z);
         if (RECORD) lp = fmaf(-0.5f * z, z, -c.log_norm);
       } else {

@@ -20,6 +20,12 @@ def test_barrier_crossing_drivers(cuda, tmp_path, monkeypatch):
   prefix = 'end_time_%.10f_dt_%.10f_chebdeg_%i_kappa_%.4f_batch_%i_trainsteps_%i_' % (2e-6, 1e-8, 12, 21.3863, 512, 4)
   assert len(pickle.load(open(out + prefix + 'all_works.pkl', 'rb'))) == 4
   assert pickle.load(open(out + prefix + 'coeffs.pkl', 'rb'))[-1][0] == 4
+  # the same loop as CUDA-graph replays with device-resident state: same key, same trajectory of coefficients
+  coeffs_d, works_d = run_barrier_crossing_opt.main(['2e-6', '1e-8', '12', '21.3863', '512', '4'], savedir=out,
+                                                    quiet=True, device_loop=True)
+  assert [c[0] for c in coeffs_d] == [c[0] for c in coeffs]
+  np.testing.assert_allclose(coeffs_d[-1][1], coeffs[-1][1], rtol=0, atol=2e-6 * np.abs(coeffs[-1][1]).max())
+  np.testing.assert_allclose(works_d[-1], works[-1], rtol=1e-5, atol=1e-5)
   res = run_barrier_crossing_fwd.main(['2e-6', '1e-8', '12', '21.3863', '64', 'test_'], savedir=out)
   assert res['all_pos'].shape == (64, 201, 1, 1) and res['all_works'].shape == (64, 201)
   assert sorted(f for f in os.listdir(out) if 'test_' in f)[0].endswith('all_log_probs.pkl')
