@@ -31,9 +31,6 @@
 #ifndef NQ_FAST_NORMAL
 #define NQ_FAST_NORMAL 0
 #endif
-#ifndef NQ_FAST_WORK
-#define NQ_FAST_WORK 0
-#endif
 #ifndef NQ_TF_WIDE_MASK
 #define NQ_TF_WIDE_MASK 0
 #endif
@@ -433,13 +430,6 @@ __device__ __forceinline__ void langevin_chunk(const LangevinConsts& c, const La
       if (FAST) {
         const float4 tab = lds_f32x4(tab_addr);
         dW = fmaf(tab.y, x, tab.z);
-#if NQ_FAST_WORK == 1
-        {
-          Landscape<POT, false> ls;
-          ls.eval(c, x);
-          dW = work_increment<POT, false>(c, ls, x, lds_f32(r_addr), tab.x);
-        }
-#endif
         dR = fast_step<POT>(c, x, rng.next(c.one, c.pow2), tab.x, z);
         if (RECORD) lp = fmaf(-0.5f * z, z, -c.log_norm);
       } else {

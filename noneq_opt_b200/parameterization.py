@@ -5,7 +5,8 @@ arguments, `variables` / `constants` / `domain` / `tree_flatten` / `tree_unflatt
 (parameterization.py:34-64), for
   Constant :67-79, PiecewiseLinear :82-133, Chebyshev :144-179 (monic, power basis :137-141),
   ChangeDomain :268-292, ConstrainEndpoints :295-322, AddBaseline :325-344.
-`Spline` (:182-265) is out of scope for this build (it needs jax_cosmo's spline).
+`Spline` (:182-265) is built from the definition of the interpolating spline (jax_cosmo is not
+available offline; see the class docstring for what that pins and what it does not).
 
 What is different, by design: there is no tracing autodiff here, so every class also provides
 `jacobian(x) -> [len(x), n_variables]`, the derivative of the value wrt its flattened variables
@@ -296,11 +297,147 @@ class AddBaseline(Parameterization):
     return self.wrapped.jacobian(x)
 
 
+def _spline_matrix(xk, k, endpoints, xs):
+  """M [len(xs), len(xk)] with spline(xs) = M @ y for the interpolating spline of degree k through
+  (xk, y): piecewise polynomials on the data intervals, C^{k-1} at the interior points, closed by
+  the `endpoints` condition -- 'not-a-knot' (the k-th derivative is continuous at the first and,
+  for k = 3, also the last interior point) or 'natural' (second derivative zero at the ends).
+  Evaluation outside [xk[0], xk[-1]] continues the end pieces.  float64 dense solve: a protocol has
+  a few dozen knots and the matrix is cached by the caller."""
+  xk = np.asarray(xk, np.float64)
+  xs = np.atleast_1d(np.asarray(xs, np.float64))
+  n = xk.shape[0]
+  if k not in (1, 2, 3):
+    raise ValueError(f'spline degree must be 1, 2 or 3 (got {k})')
+  if endpoints not in ('not-a-knot', 'natural'):
+    raise ValueError(f"endpoints must be 'not-a-knot' or 'natural' (got {endpoints!r})")
+  if n < k + 1:
+    raise ValueError(f'a degree-{k} spline needs at least {k + 1} points (got {n})')
+  if np.any(np.diff(xk) <= 0):
+    raise ValueError('spline knots must be strictly increasing')
+  nint, nc = n - 1, k + 1
+  h = np.diff(xk)
+  rows, rhs = [], []      # rows act on the coefficient vector c[i * nc + d]; rhs rows act on y
+
+  def deriv_row(i, t, order):
+    """coefficients of d^order/dt^order p_i at offset t from x_i"""
+    r = np.zeros(nint * nc)
+    for d in range(order, nc):
+      f = 1.0
+      for q in range(order):
+        f *= d - q
+      r[i * nc + d] = f * t ** (d - order)
+    return r
+
+  def unit(j):
+    e = np.zeros(n)
+    if j is not None:
+      e[j] = 1.0
+    return e
+  for i in range(nint):
+    rows.append(deriv_row(i, 0.0, 0)); rhs.append(unit(i))
+    rows.append(deriv_row(i, h[i], 0)); rhs.append(unit(i + 1))
+  for i in range(nint - 1):
+    for order in range(1, k):
+      rows.append(deriv_row(i, h[i], order) - deriv_row(i + 1, 0.0, order)); rhs.append(unit(None))
+  if k >= 2:
+    if endpoints == 'not-a-knot' and nint >= 2:
+      rows.append(deriv_row(0, h[0], k) - deriv_row(1, 0.0, k)); rhs.append(unit(None))
+      if k == 3:
+        if nint >= 3:
+          rows.append(deriv_row(nint - 2, h[nint - 2], k) - deriv_row(nint - 1, 0.0, k))
+        else:   # three points: the single cubic through them with zero third derivative
+          rows.append(deriv_row(0, 0.0, 3))
+        rhs.append(unit(None))
+    else:
+      rows.append(deriv_row(0, 0.0, 2)); rhs.append(unit(None))
+      if k == 3:
+        rows.append(deriv_row(nint - 1, h[-1], 2)); rhs.append(unit(None))
+  A, Bm = np.stack(rows), np.stack(rhs)
+  coef = np.linalg.solve(A, Bm)                     # [nint*nc, n]: coefficients as linear maps of y
+  idx = np.clip(np.searchsorted(xk, xs, side='right') - 1, 0, nint - 1)
+  t = xs - xk[idx]
+  M = np.zeros((xs.shape[0], n))
+  for d in range(nc):
+    M += (t ** d)[:, None] * coef[idx * nc + d]
+  return M
+
+
+_SPLINE_CACHE = {}
+
+
 class Spline(Parameterization):
-  """parameterization.py:182-265 -- not available in this build (needs jax_cosmo's spline)."""
+  """Interpolating spline through (x0, y0), (knots, values), (x1, y1) (parameterization.py:182-265).
+
+  The reference delegates to `jax_cosmo.scipy.interpolate.InterpolatedUnivariateSpline(x, y,
+  k=spline_degree, endpoints=spline_endpoints)`, which is not available offline; this class builds
+  the spline from its definition (`_spline_matrix`).  Cubic not-a-knot / natural splines are unique
+  and agree with scipy's CubicSpline (tests/test_host_logic.py); for degree 2 the closing condition
+  is an assumption about jax_cosmo's convention -- parity unpinned.  `variable_knots=True` (knots as
+  trainable variables) is not supported: the value is not affine in the knots."""
   knots: np.ndarray
   values: np.ndarray
+  x0: np.ndarray = 0.
+  x1: np.ndarray = 1.
+  y0: np.ndarray = 0.
+  y1: np.ndarray = 1.
+  spline_degree: int = 2
+  spline_endpoints: str = 'not-a-knot'
+  variable_knots: bool = False
   _VARIABLES = ('values',)
 
   def __post_init__(self):
-    raise NotImplementedError('Spline is out of scope for the B200 hot-path build (SURVEY N4)')
+    if self.variable_knots:
+      raise NotImplementedError('Spline(variable_knots=True) is not supported: the kernels need a protocol '
+                                'that is affine in its variables')
+
+  @property
+  def domain(self):
+    return (self.x0, self.x1)
+
+  @property
+  def degree(self):
+    return np.shape(self.knots)[-1]
+
+  @property
+  def length(self):
+    return self.degree + 2
+
+  @property
+  def x(self):
+    return np.concatenate([[F32(self.x0)], _f32(self.knots), [F32(self.x1)]]).astype(F32)
+
+  @property
+  def y(self):
+    return np.concatenate([[F32(self.y0)], _f32(self.values), [F32(self.y1)]]).astype(F32)
+
+  @classmethod
+  def equidistant(cls, d, x0=0., x1=1., y0=0., y1=1., **kwargs):
+    knots = np.linspace(F32(x0), F32(x1), d + 2, dtype=F32)[1:-1]
+    values = np.linspace(F32(y0), F32(y1), d + 2, dtype=F32)[1:-1]
+    return cls(knots, values, x0, x1, y0, y1, **kwargs)
+
+  @classmethod
+  def from_baseline(cls, baseline, d, x0=0., x1=1., **kwargs):
+    y0, y1 = baseline(_f32(x0)), baseline(_f32(x1))
+    knots = np.linspace(F32(x0), F32(x1), d + 2, dtype=F32)[1:-1]
+    return cls(knots, _f32(baseline(knots)), x0, x1, y0, y1, **kwargs)
+
+  def _matrix(self, x):
+    xs = np.atleast_1d(_f32(x))
+    xk = self.x
+    key = (xk.tobytes(), int(self.spline_degree), self.spline_endpoints, xs.shape, xs.tobytes())
+    hit = _SPLINE_CACHE.get(key)
+    if hit is None:
+      hit = _spline_matrix(xk, int(self.spline_degree), self.spline_endpoints, xs)
+      if len(_SPLINE_CACHE) >= 32:
+        _SPLINE_CACHE.pop(next(iter(_SPLINE_CACHE)))
+      _SPLINE_CACHE[key] = hit
+    return hit
+
+  def __call__(self, x):
+    y = (self._matrix(x) @ self.y.astype(np.float64)).astype(F32)
+    return y if np.ndim(x) else y[0]
+
+  def jacobian(self, x):
+    return self._matrix(x)[:, 1:-1].astype(F32)

@@ -12,7 +12,8 @@ order of the reference, plus `jacobian(x) -> [len(x), n_variables]`, the derivat
 of the value wrt the flattened variables (what `jax.grad` / `value_and_jacfwd`
 produce for these pytrees), obtained here by differentiating the same formulas by
 hand.  `dtype=np.float64` gives the "truth" variant used for error accounting.
-Spline (:182-265) is out of scope (needs jax_cosmo; not named by the north star).
+Spline (:182-265) has no restatement here: jax_cosmo is absent offline and not named by the north
+star; the product's Spline is checked against scipy's CubicSpline in tests/test_host_logic.py.
 """
 from __future__ import annotations
 

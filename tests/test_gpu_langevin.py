@@ -366,6 +366,24 @@ def test_config2_full_length_slice_vs_c_oracle(cuda):
         (xerr.max(), np.quantile(xerr, 0.995), werr.max(), np.quantile(werr, 0.995)))
 
 
+def test_spline_protocol_gradient(cuda):
+  """A cubic Spline trap protocol (parameterization.py:182-265): gradient wrt the knot values.
+  The oracle integrates the same protocol table and contracts with the same Jacobian."""
+  from noneq_opt_b200 import barrier_crossing as bc, parameterization as p10n, space
+  _, shift = space.free()
+  B, S = 128, 400
+  proto = p10n.Spline.equidistant(6, 0., 1., 5., 10., spline_degree=3)
+  proto = p10n.Spline(proto.knots, proto.values + np.float32(0.3) * np.cos(np.arange(6)).astype(np.float32),
+                      0., 1., 5., 10., spline_degree=3)
+  x0 = np.full(B, 5.0, np.float32)
+  o = L.estimate_gradient(L.V_spring(1.0), proto, x0, J.PRNGKey(2), 5., 10., 10, S, 2.5e-3, 1.0, 1.0, 1.0)
+  est = bc.estimate_gradient_boltzinit(B, bc.V_spring(1.0), 5., 10., 10, shift, S, 2.5e-3, 1.0, 1.0, 1.0)
+  grad, (_, (_, lp, w)) = est(proto, x0.reshape(B, 1, 1), J.PRNGKey(2))
+  assert grad.shape == (6,)
+  assert rel(w.cpu().numpy(), o['total_work']) < POS_RTOL
+  assert rel(grad.cpu().numpy(), o['grad']) < GRAD_RTOL
+
+
 def test_piecewise_linear_protocol_gradient(cuda):
   """A PiecewiseLinear trap protocol (north star: "Chebyshev/piecewise"): the estimators take any
   Parameterization in place of the Chebyshev coefficient vector; gradient wrt the knot values."""

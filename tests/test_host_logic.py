@@ -68,9 +68,44 @@ def test_add_baseline(p, baseline):           # tests/parameterization_test.py:7
   np.testing.assert_allclose(p(xs) + baseline(xs), p10n.AddBaseline(wrapped=p, baseline=baseline)(xs), rtol=1e-6)
 
 
-def test_spline_is_explicitly_out_of_scope():
+def test_spline_parameterization():
+  """parameterization.py:182-265.  The reference delegates to jax_cosmo (absent offline); the cubic
+  interpolating spline is unique, so scipy's CubicSpline is the checker for degree 3; degrees 1 and
+  2 are checked through their defining properties."""
+  from scipy.interpolate import CubicSpline
+  rng = np.random.RandomState(0)
+  kn = np.sort(rng.uniform(0.05, 0.95, 6)).astype(np.float32)
+  v = rng.normal(size=6).astype(np.float32)
+  xs = np.linspace(0, 1, 101, dtype=np.float32)
+  for ep in ('not-a-knot', 'natural'):
+    sp = p10n.Spline(kn, v, 0., 1., 0.5, -0.5, spline_degree=3, spline_endpoints=ep)
+    ref = CubicSpline(sp.x.astype(np.float64), sp.y.astype(np.float64), bc_type=ep)(xs.astype(np.float64))
+    np.testing.assert_allclose(sp(xs), ref, atol=2e-6)
+  sp2 = p10n.Spline(kn, v, 0., 1., 0.5, -0.5)           # defaults: degree 2, not-a-knot
+  np.testing.assert_allclose(sp2(sp2.x), sp2.y, atol=1e-6)   # interpolates its points
+  xk64, h = sp2.x.astype(np.float64), 1e-7                 # C^1 at an interior knot (float64 operator)
+  d = np.diff(p10n._spline_matrix(xk64, 2, 'not-a-knot', [xk64[3] - h, xk64[3], xk64[3] + h]) @ sp2.y.astype(np.float64))
+  assert abs(d[0] - d[1]) < 1e-3 * abs(d[0])
+  quad = lambda t: 1 + 2 * t - 3 * t * t
+  spq = p10n.Spline(kn, quad(kn), 0., 1., quad(0.), quad(1.))
+  np.testing.assert_allclose(spq(xs), quad(xs), atol=1e-4)   # a quadratic is its own spline
+  sp1 = p10n.Spline(kn, v, 0., 1., 0.5, -0.5, spline_degree=1)
+  np.testing.assert_allclose(sp1(xs), np.interp(xs, sp1.x, sp1.y), atol=1e-6)
+  # pytree surface and the Jacobian (the value is affine in `values`)
+  assert set(sp2.variables) == {'values'} and 'knots' in sp2.constants and sp2.degree == 6 and sp2.length == 8
+  rebuilt = p10n.Spline.tree_unflatten(*reversed(sp2.tree_flatten()))
+  assert rebuilt == sp2
+  J = sp2.jacobian(xs)
+  bumped = p10n.Spline(kn, v + np.float32(0.5) * np.eye(6, dtype=np.float32)[3], 0., 1., 0.5, -0.5)
+  np.testing.assert_allclose((bumped(xs) - sp2(xs)) / 0.5, J[:, 3], atol=1e-5)
+  eq = p10n.Spline.equidistant(4, 0., 2., 1., 3., spline_degree=3)
+  np.testing.assert_allclose(eq(np.linspace(0, 2, 9, dtype=np.float32)), np.linspace(1, 3, 9), atol=1e-6)
+  fb = p10n.Spline.from_baseline(lambda t: np.float32(2) * t, 3, 0., 1.)
+  np.testing.assert_allclose(fb(xs), 2 * xs, atol=1e-6)
   with pytest.raises(NotImplementedError):
-    p10n.Spline(np.zeros(3), np.zeros(3))
+    p10n.Spline(kn, v, variable_knots=True)
+  with pytest.raises(ValueError):
+    p10n.Spline(kn[::-1].copy(), v)(xs)
 
 
 def test_product_parameterizations_equal_oracle_bits():
