@@ -48,6 +48,23 @@ ISSUE_PEAK = 148 * 128 * 1.965e9  # thread-instructions/s at max SM clock (BASEL
 L2_FLUSH_BYTES = 256 << 20
 
 
+def profiled_dram_traffic(math_mode):
+  """dram__bytes_read.sum + dram__bytes_write.sum per launch of the Langevin kernel, from the newest
+  committed `ncu --set full` summary under profiles/ (None if there is none)."""
+  import csv
+  import glob
+  files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles',
+                                        f'r*_langevin_{math_mode}_full.csv')))
+  if not files:
+    return None, None
+  scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+  total = 0.0
+  for row in csv.reader(open(files[-1])):
+    if len(row) >= 3 and row[0] in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+      total += float(row[2]) * scale.get(row[1], 1.0)
+  return total, os.path.relpath(files[-1], os.path.dirname(os.path.abspath(__file__)))
+
+
 def measured_peaks():
   try:
     return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -246,13 +263,14 @@ def run_native(args):
     peaks = measured_peaks()
     hbm_peak = peaks['hbm_gbs'] if peaks else 6650.0
     alg_bytes = 24.0 * C2_B + 4.0 * (C2_S + 1) + 4.0 * 13 * (C2_S - 1)
+    traffic, traffic_src = profiled_dram_traffic(args.math)
     roofline = dict(
         bound='issue', kernel='langevin_kernel<BIOMOLECULE_SHIFTED, DP=16>',
         achieved=per_gpu * INSTR_PER_TRAJ_STEP / 1e12, peak=ISSUE_PEAK / 1e12, unit='Tinstr/s (thread-instructions)',
         frac=per_gpu * INSTR_PER_TRAJ_STEP / ISSUE_PEAK,
         note='instruction-issue bound (3 threefry2x32-20 blocks per step): 326 thread-instr/traj-step (SURVEY 8d) x '
              'measured traj-steps/s per GPU / (148 SM x 128 lanes x 1.965 GHz); not HBM- or tensor-bound',
-        traffic=None,
+        traffic=traffic, traffic_source=traffic_src,
         hbm=dict(bound='hbm', achieved=alg_bytes / (ms * 1e-3) / 1e9, peak=hbm_peak, unit='GB/s',
                  frac=alg_bytes / (ms * 1e-3) / 1e9 / hbm_peak,
                  peak_source='MEASURED_PEAKS.json (of measured)' if peaks else 'fallback',

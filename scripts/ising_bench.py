@@ -5,7 +5,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from noneq_opt_b200 import ising, random as nqr
 from oracle import ising_ref as I, jaxlike as J
 dev = torch.device('cuda')
-for (L, R, T) in ((64, 4096, 1001), (1024, 256, 101), (128, 2048, 201), (256, 1024, 101), (2048, 148, 21), (4096, 148, 6)):
+CONFIGS = ((64, 4096, 1001), (1024, 256, 101), (128, 2048, 201), (256, 1024, 101), (2048, 148, 21), (4096, 148, 6))
+if len(sys.argv) > 1:   # e.g. ising_bench.py 64,4736,1001 64,2368,1001
+  CONFIGS = tuple(tuple(int(v) for v in a.split(',')) for a in sys.argv[1:])
+for (L, R, T) in CONFIGS:
   times = np.linspace(0, 1, T, dtype=np.float32)
   lt = ising.log_temp_baseline(0.69, 10, 1)(times); h = ising.field_baseline(-1, 1)(times)
   s0 = -np.ones((L, L), np.float32) if L == 64 else ising.random_spins([L, L], .5, nqr.PRNGKey(1))

@@ -422,3 +422,29 @@ def test_segment_scheduled_run_is_bit_identical(cuda, L, R, T, monkeypatch):
   np.testing.assert_array_equal(seg[0][r].cpu().numpy(), fin_o)
   check_summary(np.stack([seg[1 + i][r].cpu().numpy() for i in range(len(FIELDS))]),
                 np.stack([getattr(summ_o, f) for f in FIELDS]), L * L)
+
+
+def test_config4_ensemble_carries_energy_and_magnetization_through_segments(cuda):
+  """configs[3] shape (256 replicas of 1024^2, segment-scheduled over 148 SMs), 40 sweeps: the running
+  magnetisation and energy each replica reports after its LAST sweep must equal a from-scratch
+  measurement of its final lattice (the integer spin and bond sums are handed from segment to
+  segment), and the work/heat bookkeeping must telescope: E_final - E_initial = sum(work) - sum(heat)."""
+  from noneq_opt_b200 import ising
+  L, R, T = 1024, 256, 41
+  times = np.linspace(0, 1, T, dtype=np.float32)
+  lt, h = ising.log_temp_baseline(0.69, 10, 1)(times), ising.field_baseline(-1, 1)(times)
+  s0 = ising.random_spins([L, L], .5, J.PRNGKey(1))
+  seeds = J.split(J.PRNGKey(0), R)
+  final, summary = ising.simulate_ising(ising.IsingParameters(lt, h), s0, seeds)
+  spins = final.spins.to(torch.float64)                                  # [R, L, L]
+  nbr = sum(torch.roll(spins, sh, ax) for ax in (1, 2) for sh in (-1, 1))
+  e_meas = -(spins * (nbr / 2 + float(h[-1]))).sum((1, 2))
+  m_meas = spins.mean((1, 2))
+  np.testing.assert_allclose(summary.energy[:, -1].double().cpu().numpy(), e_meas.cpu().numpy(), rtol=2e-7)
+  np.testing.assert_allclose(summary.magnetization[:, -1].double().cpu().numpy(), m_meas.cpu().numpy(), atol=1e-7)
+  s0f = torch.as_tensor(np.asarray(s0.cpu() if hasattr(s0, 'cpu') else s0), dtype=torch.float64)
+  nbr0 = sum(torch.roll(s0f, sh, ax) for ax in (0, 1) for sh in (-1, 1))
+  e0 = float(-(s0f * (nbr0 / 2 + float(h[0]))).sum())
+  tele = summary.work.double().sum(1) - summary.dissipated_heat.double().sum(1)
+  np.testing.assert_allclose((e_meas - e0).cpu().numpy(), tele.cpu().numpy(), rtol=0, atol=2e-5 * L * L)
+  assert len(set(np.round(m_meas.cpu().numpy(), 9))) > R // 2          # replicas are distinct trajectories
