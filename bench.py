@@ -73,21 +73,60 @@ def measured_peaks():
 
 
 class ClockSampler:
-  """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+  """SM clock / throttle reasons sampled DURING the timed region: NVML polled from a thread (starts
+  instantly, ~5 ms period); `nvidia-smi -lms` as the fallback when NVML cannot be loaded."""
   Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
        'clocks_event_reasons.sw_power_cap')
+  NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
   def __init__(self, index):
-    self.index, self.rows, self.proc = index, [], None
+    self.index, self.rows, self.proc, self.thread = index, [], None, None
+    self.stop_flag = threading.Event()
+    self.source = None
+
+  def _nvml_handle(self):
+    import pynvml
+    import torch
+    pynvml.nvmlInit()
+    try:
+      uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+      return pynvml, pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + uuid if not uuid.startswith('GPU-') else uuid).encode())
+    except Exception:
+      visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+      phys = int(visible.split(',')[self.index]) if visible and visible.split(',')[self.index].isdigit() else self.index
+      return pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+
+  def _poll_nvml(self, nv, h):
+    masks = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
+             nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap]
+    mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+    while not self.stop_flag.is_set():
+      try:
+        bits = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        self.rows.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx),
+                          str(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)] +
+                         ['Active' if bits & m else 'Not Active' for m in masks])
+      except Exception:
+        pass
+      time.sleep(0.005)
 
   def start(self):
+    try:
+      nv, h = self._nvml_handle()
+      self.thread = threading.Thread(target=self._poll_nvml, args=(nv, h), daemon=True)
+      self.thread.start()
+      self.source = 'nvml'
+      return
+    except Exception:
+      self.thread = None
     try:
       self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
                                     '--format=csv,noheader,nounits', '-lms', '20'], stdout=subprocess.PIPE,
                                    stderr=subprocess.DEVNULL, text=True)
       self.thread = threading.Thread(target=self._read, daemon=True)
       self.thread.start()
+      self.source = 'nvidia-smi'
     except Exception:
       self.proc = None
 
@@ -96,29 +135,32 @@ class ClockSampler:
       self.rows.append([c.strip() for c in line.split(',')])
 
   def stop(self):
-    if self.proc is None:
-      return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
-    time.sleep(0.12)
-    self.proc.terminate()
-    try:
-      self.proc.wait(timeout=5)
-    except Exception:
-      self.proc.kill()
+    if self.source is None:
+      return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvml and nvidia-smi unavailable'])
+    if self.source == 'nvml':
+      self.stop_flag.set()
+      self.thread.join(timeout=2)
+    else:
+      time.sleep(0.12)
+      self.proc.terminate()
+      try:
+        self.proc.wait(timeout=5)
+      except Exception:
+        self.proc.kill()
     sm, mx, reasons, power = [], [], set(), []
-    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-    for r in self.rows:
+    for r in list(self.rows):
       try:
         sm.append(float(r[0])); mx.append(float(r[1])); power.append(float(r[2]))
-        for nm, v in zip(names, r[3:7]):
+        for nm, v in zip(self.NAMES, r[3:7]):
           if v.lower().startswith('active'):
             reasons.add(nm)
       except Exception:
         pass
     if not sm:
-      return dict(sm_mhz=None, sm_max_mhz=None, reasons=['no samples'])
+      return dict(sm_mhz=None, sm_max_mhz=None, reasons=['no samples'], source=self.source)
     busy = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] or sm
     return dict(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
-                samples=len(sm), power_w_max=float(max(power)))
+                samples=len(sm), power_w_max=float(max(power)), source=self.source)
 
 
 # =============================================================================== reference arm

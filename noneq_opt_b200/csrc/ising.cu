@@ -717,7 +717,7 @@ static size_t fast_smem_bytes(int L, bool warp_team, int nteams, bool global_lat
 
 // Segment scheduling plan for the CTA-team kernel (see IsingShape::n_seg).  R replicas on `slots`
 // resident CTAs take ceil(R / slots) rounds; cutting every replica into n segments makes that
-// ceil(R n / slots) / n.  n = 1 (off) unless some n <= 16 saves at least 3 %.
+// ceil(R n / slots) / n.  n = 1 (off) unless some n <= 64 saves at least 3 %.
 struct SegPlan {
   int n_seg = 1;
   int grid = 0;
@@ -728,7 +728,7 @@ template <bool W, bool G, bool S>
 __global__ void ising_fast_kernel(const IsingShape, const IsingIO);
 static SegPlan plan_segments(int L, long long R, int T) {
   SegPlan p;
-  if (L <= 128 || R * 16 >= 0xffffffffll || T - 1 < 2) return p;
+  if (L <= 128 || R * 64 >= 0x7fffffffll || T - 1 < 2) return p;
   const size_t smem = fast_smem_bytes(L, false, 1);
   if (smem > 227 * 1024) return p;
   const int units = (L / 2) * (L / 64);
@@ -746,7 +746,7 @@ static SegPlan plan_segments(int L, long long R, int T) {
   const long long slots = sms;
   if (slots <= 0 || R <= slots || R % slots == 0) return p;
   double best = (double)((R + slots - 1) / slots);
-  const int n_max = T - 1 < 16 ? T - 1 : 16;
+  const int n_max = T - 1 < 64 ? T - 1 : 64;
   for (int n = 2; n <= n_max; ++n) {
     const double rounds = (double)((R * n + slots - 1) / slots) / n;
     if (rounds < 0.97 * best) {
@@ -755,6 +755,10 @@ static SegPlan plan_segments(int L, long long R, int T) {
     }
   }
   if (p.n_seg == 1) return p;
+  // keep a segment under ~512 sweeps: a CTA that has to wait for the previous segment of its replica
+  // waits at most one segment, which must stay far below the kernel's bounded-wait limit.  Doubling
+  // n never lengthens the schedule (ceil(2Rn/s)/(2n) <= ceil(Rn/s)/n).
+  while ((T - 1) / p.n_seg > 512 && 2 * p.n_seg <= T - 1 && R * 2 * p.n_seg < 0x7fffffffll) p.n_seg *= 2;
   p.grid = (int)slots;
   p.ctl_bytes = (((size_t)R + 1) * 4 + 15) / 16 * 16;
   p.mb_bytes = (size_t)R * 2 * 8;

@@ -387,7 +387,7 @@ def test_arbitrary_loss_function_through_torch_autograd(cuda):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('L,R,T', [(512, 149, 9), (1024, 150, 6)])
+@pytest.mark.parametrize('L,R,T', [(512, 149, 9), (1024, 150, 6), (512, 149, 1100)])
 def test_segment_scheduled_run_is_bit_identical(cuda, L, R, T, monkeypatch):
   """When R is not a multiple of the resident CTAs, nq_ising_run cuts every replica's sweeps into
   segments handed out through a ticket counter (lattice, M and B carried through the workspace).
@@ -401,9 +401,9 @@ def test_segment_scheduled_run_is_bit_identical(cuda, L, R, T, monkeypatch):
   seeds = J.split(J.PRNGKey(4), R)
 
   def run():
-    final, summary = ising.simulate_ising(params, s0, seeds, return_states=(L == 512))
+    final, summary = ising.simulate_ising(params, s0, seeds, return_states=(T == 9))
     states = None
-    if L == 512:
+    if T == 9:
       summary, states = summary
     out = [final.spins] + [getattr(summary, f) for f in FIELDS]
     if states is not None:
@@ -417,6 +417,8 @@ def test_segment_scheduled_run_is_bit_identical(cuda, L, R, T, monkeypatch):
   monkeypatch.delenv('NQ_ISING_NO_SEGMENTS')
   for a, b in zip(seg, flat):
     assert torch.equal(a, b)
+  if T > 100:     # long run: segments are capped at ~512 sweeps; the oracle check is done by the short cases
+    return
   r = R - 2
   fin_o, summ_o = I.simulate_ising(lt, h, s0, seeds[r])
   np.testing.assert_array_equal(seg[0][r].cpu().numpy(), fin_o)
