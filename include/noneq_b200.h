@@ -47,6 +47,11 @@ uint64_t nq_launch_count(void);
  * Replaces jax.random.split at barrier_crossing.py:221,253; ising.py:283. */
 int nq_random_split(const uint32_t key[2] /*host*/, int64_t num, int64_t first, int64_t count,
                     uint32_t* out, void* stream);
+/* The per-trajectory keys of a rank's shard: rows [n0, n0+n) of jax.random.split(seed, B_total)
+ * (barrier_crossing.py:221; SURVEY 8b/8e: the counter pairing depends on the GLOBAL batch, so results
+ * do not depend on the number of ranks).  Same as nq_random_split(seed, B_total, n0, n, ...).    */
+int nq_langevin_keys(const uint32_t seed[2] /*host*/, int64_t B_total, int64_t n0, int64_t n,
+                     uint32_t* keys /*[n][2]*/, void* stream);
 /* jax.random.bits(key, (size,), uint32)[first : first+count] */
 int nq_random_bits(const uint32_t key[2] /*host*/, int64_t size, int64_t first, int64_t count,
                    uint32_t* out, void* stream);

@@ -49,6 +49,7 @@ SIGNATURES = {
     'nq_last_error': (C.c_char_p, []),
     'nq_launch_count': (C.c_uint64, []),
     'nq_random_split': (C.c_int, [_KEY, C.c_int64, C.c_int64, C.c_int64, _P, _P]),
+    'nq_langevin_keys': (C.c_int, [_KEY, C.c_int64, C.c_int64, C.c_int64, _P, _P]),
     'nq_random_bits': (C.c_int, [_KEY, C.c_int64, C.c_int64, C.c_int64, _P, _P]),
     'nq_random_uniform': (C.c_int, [_KEY, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_float, _P, _P]),
     'nq_random_normal': (C.c_int, [_KEY, C.c_int64, C.c_int64, C.c_int64, _P, _P]),

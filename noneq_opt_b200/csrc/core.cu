@@ -104,6 +104,11 @@ extern "C" int nq_random_split(const uint32_t key[2], int64_t num, int64_t first
   return launch_bits<kRawBits>(key, 2 * num, 2 * first, 2 * count, 0.f, 1.f, out, stream);
 }
 
+extern "C" int nq_langevin_keys(const uint32_t seed[2], int64_t B_total, int64_t n0, int64_t n, uint32_t* keys,
+                                void* stream) {
+  return nq_random_split(seed, B_total, n0, n, keys, stream);
+}
+
 extern "C" int nq_random_bits(const uint32_t key[2], int64_t size, int64_t first, int64_t count, uint32_t* out,
                               void* stream) {
   return launch_bits<kRawBits>(key, size, first, count, 0.f, 1.f, out, stream);

@@ -51,3 +51,24 @@ def test_golden_rng_fixture(cuda):
   np.testing.assert_array_equal(nqr.bits(key, (9,)).cpu().numpy().view(np.uint32), np.array(g['bits9'], np.uint32))
   np.testing.assert_array_equal(nqr.uniform(key, (9,)).cpu().numpy().view(np.uint32),
                                 np.array(g['uniform9_bits'], np.uint32))
+
+
+def test_shard_keys_and_device_resident_key_entry_points(cuda):
+  """nq_langevin_keys (a rank's rows of the global split) and nq_random_split_dev (key read from device
+  memory: the training loop's `key, a, b = split(key, 3)` without a host round trip)."""
+  import ctypes as C
+  import torch
+  from noneq_opt_b200 import _lib, random as nqr
+  lib = _lib.lib()
+  key = J.PRNGKey(77)
+  full = J.split(key, 5000)
+  out = torch.empty((300, 2), dtype=torch.int32, device='cuda')
+  _lib.check(lib.nq_langevin_keys(_lib.key_arg(key), 5000, 1200, 300, _lib.ptr(out), _lib.stream_arg()))
+  np.testing.assert_array_equal(out.cpu().numpy().view(np.uint32), full[1200:1500])
+  key_dev = nqr.as_key_tensor(key, torch.device('cuda')).reshape(2).clone()
+  out3 = torch.empty((3, 2), dtype=torch.int32, device='cuda')
+  _lib.check(lib.nq_random_split_dev(_lib.ptr(key_dev), 3, 0, 3, _lib.ptr(out3), _lib.stream_arg()))
+  np.testing.assert_array_equal(out3.cpu().numpy().view(np.uint32), J.split(key, 3))
+  _lib.check(lib.nq_random_split_dev(_lib.ptr(out3[2]), 5000, 4990, 10, _lib.ptr(out[:10]), _lib.stream_arg()))
+  np.testing.assert_array_equal(out[:10].cpu().numpy().view(np.uint32), J.split(J.split(key, 3)[2], 5000)[4990:])
+  assert lib.nq_random_split_dev(_lib.ptr(key_dev), 3, 0, 1, _lib.ptr(key_dev), _lib.stream_arg()) == -1   # aliasing
