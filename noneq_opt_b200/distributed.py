@@ -70,3 +70,50 @@ def langevin_gradient_sharded(batch_size, energy_fn, r0_init, r0_final, Neq, shi
     grad = ((grad_sums[0] + grad_sums[1]) / batch_size).to(torch.float32)
     return grad, dict(moments=moments, grad_sums=grad_sums, local=out)
   return _estimate
+
+
+def ising_gradient_sharded(loss_function, batch_size, term: str = 'reinforce'):
+  """The batch-mean gradient of `ising.estimate_gradient_rev(loss_function)` (ising.py:179-198, batched
+  as in get_train_step :283-286) over all ranks: each rank runs its contiguous slice of the replicas
+  keyed by rows of the GLOBAL `split(seed, batch_size)`, then one all-reduce combines
+  [grad sums of both schedule components | n, sum(loss), sum(loss^2)].  Returns
+  (mean grad pytree like the schedule (float32 numpy leaves), dict(loss_mean, loss_var, local_summary))."""
+  from . import ising
+  from . import random as nqrandom
+  if term not in ('reinforce', 'logP', 'reparam'):
+    raise ValueError(f'unknown gradient term {term!r}')
+
+  def _estimate(schedule, times, initial_spins, seed):
+    rank, ws = world()
+    first, count = shard_range(batch_size, rank, ws)
+    seeds = nqrandom.split(seed, batch_size, first=first, count=count)
+    t = ising._gradient_terms(loss_function, schedule, times, initial_spins, seeds)
+    pick = {'reinforce': tuple(a + b for a, b in zip(t['logP'], t['reparam'])), 'logP': t['logP'],
+            'reparam': t['reparam']}[term]
+    loss = t['loss'].to(torch.float64)
+    mom = torch.stack([torch.tensor(float(count), dtype=torch.float64, device=loss.device), loss.sum(), (loss * loss).sum()])
+    g_lt, g_h, mom = allreduce_sums([pick[0].to(torch.float64).sum(0), pick[1].to(torch.float64).sum(0), mom])
+    grad = ising._pack_grad_like(schedule, (g_lt / batch_size)[None], (g_h / batch_size)[None], True)
+    from . import tree
+    grad = tree.tree_map(lambda x: x[0].to(torch.float32).cpu().numpy(), grad)
+    mean = float(mom[1] / mom[0])
+    return grad, dict(loss_mean=mean, loss_var=float(mom[2] / mom[0]) - mean * mean, local_summary=t['summary'])
+  return _estimate
+
+
+def ising_train_step_sharded(optimizer, initial_spins, batch_size: int, time_steps: int, loss_function=None,
+                             max_grad=1e4):
+  """`ising.get_train_step` (ising.py:263-290) with the batch sharded over the ranks: every rank applies
+  the same clipped Adam update to its copy of the optimiser state (the all-reduced gradient is
+  identical on all ranks), so the schedules stay in lock step without a broadcast."""
+  import numpy as np
+  from . import ising, optimizers
+  loss_function = loss_function or ising.total_entropy_production
+  estimator = ising_gradient_sharded(loss_function, batch_size)
+  times = np.linspace(0, 1, time_steps, dtype=np.float32)
+  update_fn, params_fn = optimizer[1], optimizer[2]
+
+  def _train_step(opt_state, step, seed):
+    grad, aux = estimator(params_fn(opt_state), times, initial_spins, seed)
+    return update_fn(step, optimizers.clip_grads(grad, max_grad), opt_state), aux
+  return _train_step
