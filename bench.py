@@ -281,6 +281,8 @@ def run_native(args):
       e1.record()
       torch.cuda.synchronize()
       total_ms += e0.elapsed_time(e1)
+      if os.environ.get('NQ_BENCH_DEBUG'):
+        print(f'[bench rank {rank}] {fn.__name__}: {e0.elapsed_time(e1):.3f} ms', file=sys.stderr)
     launches = lib.nq_launch_count() - launches0
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)

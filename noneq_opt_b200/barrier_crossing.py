@@ -168,6 +168,40 @@ def _schedule_and_jacobian(timevec, coeffs, r0_init, r0_final):
   return vals, jac
 
 
+_DEVICE_BASIS = {}
+
+
+def _device_schedule_and_jacobian(S, coeffs, r0_init, r0_final, device):
+  """Trap table and protocol Jacobian for a Chebyshev coefficient vector, built ON the device: the
+  basis (= Jacobian) is uploaded once per (S, D, device) and the table is one `nq_schedule_affine`
+  launch in the float32 summation order of `_schedule_and_jacobian`, so a gradient call does no host
+  arithmetic and no table upload.  Returns None when `coeffs` is not a plain coefficient vector."""
+  if isinstance(coeffs, p10n.Parameterization):
+    return None
+  if isinstance(coeffs, torch.Tensor):
+    if coeffs.dim() != 1:
+      return None
+    w = coeffs.detach().to(device=device, dtype=torch.float32).contiguous()
+  else:
+    w_np = np.asarray(coeffs, np.float32)
+    if w_np.ndim != 1:
+      return None
+    w = torch.from_numpy(np.array(w_np, dtype=np.float32, order='C')).to(device)
+  D = int(w.shape[0])
+  key = (int(S), D, str(device))
+  basis = _DEVICE_BASIS.get(key)
+  if basis is None:
+    _, host = _chebyshev_grid_basis(S + 1, D)
+    basis = torch.from_numpy(np.array(host, dtype=np.float32, order='C')).to(device)
+    if len(_DEVICE_BASIS) >= 8:
+      _DEVICE_BASIS.pop(next(iter(_DEVICE_BASIS)))
+    _DEVICE_BASIS[key] = basis
+  table = torch.empty(S + 1, dtype=torch.float32, device=device)
+  _lib.check(_lib.lib().nq_schedule_affine(_lib.ptr(basis), _lib.ptr(w), None, float(np.float32(r0_init)),
+                                           float(np.float32(r0_final)), S - 1, D, _lib.ptr(table), _lib.stream_arg()))
+  return table, basis
+
+
 def make_trap_fxn(timevec, coeffs, r0_init, r0_final):
   positions = MakeSchedule_chebyshev(timevec, coeffs, r0_init, r0_final)
 
@@ -326,7 +360,8 @@ def gradient_terms(energy_fn, coeffs, init_pos, seeds, r0_init, r0_final, Neq, s
   x0 = _dev_f32(init_pos, device).reshape(-1)
   if x0.numel() == 1:
     x0 = x0.expand(seeds.shape[0]).contiguous()
-  r, phi = _schedule_and_jacobian(np.arange(S + 1), coeffs, r0_init, r0_final)
+  on_device = _device_schedule_and_jacobian(S, coeffs, r0_init, r0_final, device) if S >= 3 else None
+  r, phi = on_device if on_device is not None else _schedule_and_jacobian(np.arange(S + 1), coeffs, r0_init, r0_final)
   return _simulate(energy_fn, shift, r, phi, x0, seeds, S, Neq, dt, temperature, mass, gamma)
 
 
