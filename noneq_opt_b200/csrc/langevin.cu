@@ -81,6 +81,7 @@ __global__ void langevin_finalize_kernel(const double* partials, int nblocks, in
 
 struct PotLaunchers {
   MainLauncher main;
+  PairLauncher pair;
   PersistentLauncher persistent;
   ReplayLauncher replay;
   StationaryLauncher stationary;
@@ -89,10 +90,10 @@ struct PotLaunchers {
 
 static PotLaunchers launchers(int potential) {
   switch (potential) {
-    case NQ_POT_SPRING: return {pot_spring_main, pot_spring_persistent, pot_spring_replay, pot_spring_stationary, pot_spring_apply};
+    case NQ_POT_SPRING: return {pot_spring_main, pot_spring_pair, pot_spring_persistent, pot_spring_replay, pot_spring_stationary, pot_spring_apply};
     case NQ_POT_BIOMOLECULE:
-      return {pot_biomolecule_main, pot_biomolecule_persistent, pot_biomolecule_replay, pot_biomolecule_stationary, pot_biomolecule_apply};
-    default: return {pot_shifted_main, pot_shifted_persistent, pot_shifted_replay, pot_shifted_stationary, pot_shifted_apply};
+      return {pot_biomolecule_main, pot_biomolecule_pair, pot_biomolecule_persistent, pot_biomolecule_replay, pot_biomolecule_stationary, pot_biomolecule_apply};
+    default: return {pot_shifted_main, pot_shifted_pair, pot_shifted_persistent, pot_shifted_replay, pot_shifted_stationary, pot_shifted_apply};
   }
 }
 
@@ -112,6 +113,18 @@ static bool use_persistent(long long n, long long S, bool record) {
   return enabled && !record && n >= 148ll * kThreads * 2 && S >= 2 * kChunkSteps;
 }
 static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+// Small ensembles run a producer + consumer warp per 32 trajectories (langevin_pair_kernel): up to
+// this many trajectories the GPU is latency-bound and overlapping the random stream with the
+// integration wins; beyond it the one-warp-per-32-trajectories kernel has the higher throughput.
+// NQ_PAIR_MAX overrides the threshold (0 = never).
+constexpr long long kPairLimit = 65536;   // nq_langevin_workspace_bytes sizes the partial rows for 32-trajectory CTAs up to here
+static long long pair_max() {
+  const char* env = getenv("NQ_PAIR_MAX");
+  const long long v = env ? atoll(env) : 12288;   // measured crossover with the one-warp kernel: ~16k trajectories
+  return v > kPairLimit ? kPairLimit : v;
+}
+static bool use_pair(long long n, bool record) { return !record && n <= pair_max(); }
 static size_t persistent_bytes(long long n, int D) {
   const long long groups = (n + kThreads - 1) / kThreads;
   const long long n_chunks_max = 1 << 16;  // callers size the workspace without knowing S: bound the ring by n
@@ -130,10 +143,11 @@ static int run(const NqLangevinDesc* desc, const LangevinIO& io_in, double* mome
   NQ_CHECK_ARG(io.D >= 0 && io.D <= 32, "D must be in [0, 32] (got %d)", io.D);
   NQ_CHECK_ARG(io.D == 0 || io.phi, "phi is null");
   const bool fast = desc->math_mode == NQ_MATH_FAST;
-  const int blocks = (int)((io.n + kThreads - 1) / kThreads);
   const int NV = partial_row(io.D);
   const bool record = io.positions || io.step_works || io.step_logps || io.ckpt_x;
-  const bool persistent = use_persistent(io.n, c.S, record);
+  const bool pair = use_pair(io.n, record);
+  const int blocks = (int)(pair ? (io.n + 31) / 32 : (io.n + kThreads - 1) / kThreads);
+  const bool persistent = !pair && use_persistent(io.n, c.S, record);
   const size_t part_bytes = align256((size_t)blocks * NV * sizeof(double));
   const size_t ring_bytes = persistent ? align256((size_t)blocks * ((c.S + kChunkSteps - 1) / kChunkSteps) * 4) : 0;
   size_t need = part_bytes + (persistent ? persistent_bytes(io.n, io.D) : 0);
@@ -183,6 +197,9 @@ static int run(const NqLangevinDesc* desc, const LangevinIO& io_in, double* mome
     if (per_sm < 1) per_sm = 1;
     rc = launchers(c.potential).persistent(c, io, ctl, (int)(per_sm * sms), fast, st, nullptr);
     NQ_CHECK_ARG(rc == 0, "no persistent kernel for D=%d", io.D);
+  } else if (pair) {
+    rc = launchers(c.potential).pair(c, io, blocks, fast, st);
+    NQ_CHECK_ARG(rc == 0, "no kernel for D=%d", io.D);
   } else {
     rc = launchers(c.potential).main(c, io, blocks, fast, record, st);
     NQ_CHECK_ARG(rc == 0, "no kernel for D=%d", io.D);
@@ -210,7 +227,9 @@ extern "C" size_t nq_langevin_workspace_bytes(int64_t n, int32_t D) {
   if (D > 32) D = 32;
   const size_t blocks = (size_t)((n + kThreads - 1) / kThreads);
   // + ring of work items for up to 256 chunks of kChunkSteps steps (S <= 131072); longer runs use the static kernel
-  return align256(blocks * partial_row(D) * sizeof(double)) + persistent_bytes(n, D) + align256(blocks * 256 * 4);
+  // block partial rows: small ensembles may run the pair kernel (32 trajectories per CTA)
+  const size_t pblocks = n <= kPairLimit ? (size_t)((n + 31) / 32) : blocks;
+  return align256(pblocks * partial_row(D) * sizeof(double)) + persistent_bytes(n, D) + align256(blocks * 256 * 4);
 }
 
 extern "C" int nq_langevin_forward(const NqLangevinDesc* desc, const float* r_table, const float* x0,

@@ -185,13 +185,12 @@ struct RngPipe {
 // One apply_fn (barrier_crossing.py:77-92) given the landscape already evaluated at x and the raw
 // bits of this step's normal draw.  Returns dR; updates x; writes z (standardised noise) and lp.
 template <int POT, bool FAST>
-__device__ __forceinline__ float brownian_apply(const LangevinConsts& c, const Landscape<POT, FAST>& land, float& x,
-                                                uint32_t bits, float r, float& z, float& lp) {
+__device__ __forceinline__ float brownian_apply_xi(const LangevinConsts& c, const Landscape<POT, FAST>& land, float& x,
+                                                   float xi, float r, float& z, float& lp) {
   const float u = fsub<FAST>(x, r);
   const float dEs = fmul<FAST>(c.hk, fmul<FAST>(2.0f, u));
   const float F = POT == NQ_POT_SPRING ? -dEs : -fadd<FAST>(land.dEm(c), dEs);
   const float mean = FAST ? F * c.nudt : __fmul_rn(__fmul_rn(F, c.nu), c.dt);
-  const float xi = normal_from_bits<FAST>(bits);
   const float dR = fadd<FAST>(fmul<FAST>(xi, c.sigma), mean);  // sampled * scale + loc
   // Normal.log_prob's z = x/scale - loc/scale equals xi up to one rounding of dR: using xi changes
   // each log-prob by < 1e-6 absolute (tolerance 1e-5 relative of ~9) and is 7 instructions cheaper
@@ -201,6 +200,12 @@ __device__ __forceinline__ float brownian_apply(const LangevinConsts& c, const L
   x = fadd<FAST>(x, dR);
   if (c.shift_kind == NQ_SHIFT_PERIODIC) x = py_mod(x, c.box);
   return dR;
+}
+
+template <int POT, bool FAST>
+__device__ __forceinline__ float brownian_apply(const LangevinConsts& c, const Landscape<POT, FAST>& land, float& x,
+                                                uint32_t bits, float r, float& z, float& lp) {
+  return brownian_apply_xi<POT, FAST>(c, land, x, normal_from_bits<FAST>(bits), r, z, lp);
 }
 
 // ------------------------------------------------------------------------------ FAST-math step
@@ -289,18 +294,27 @@ __device__ __forceinline__ float fast_mean(const LangevinConsts& c, float x, flo
 #endif
 }
 
-template <int POT>
-__device__ __forceinline__ float fast_step(const LangevinConsts& c, float& x, uint32_t bits, float r, float& z) {
-  const float mean = fast_mean<POT>(c, x, r);
+__device__ __forceinline__ float fast_normal(uint32_t bits) {
 #if NQ_FAST_NORMAL == 1
-  z = normal_from_bits<false>(bits);
+  return normal_from_bits<false>(bits);
 #else
-  z = normal_from_bits_fast(bits);
+  return normal_from_bits_fast(bits);
 #endif
+}
+
+template <int POT>
+__device__ __forceinline__ float fast_step_z(const LangevinConsts& c, float& x, float z, float r) {
+  const float mean = fast_mean<POT>(c, x, r);
   const float dR = fmaf(z, c.sigma, mean);
   x += dR;
   if (c.shift_kind == NQ_SHIFT_PERIODIC) x = py_mod(x, c.box);
   return dR;
+}
+
+template <int POT>
+__device__ __forceinline__ float fast_step(const LangevinConsts& c, float& x, uint32_t bits, float r, float& z) {
+  z = fast_normal(bits);
+  return fast_step_z<POT>(c, x, z, r);
 }
 
 // ------------------------------------------------------------------------------ main kernel
@@ -545,6 +559,204 @@ __global__ void __launch_bounds__(kThreads, min_blocks(D)) langevin_kernel(const
   langevin_chunk<POT, FAST, D, RECORD>(c, io, blockIdx.x, 1, c.S, true, true, nullptr, 0);
 }
 
+// ------------------------------------------------------------------------------ small ensembles
+// Below ~10^4 trajectories a warp is alone on its SM sub-partition and the main kernel is
+// latency-bound: one step costs ~1050 cycles (STRICT) because the three threefry blocks + normal draw
+// and the force / work chain are issued back to back from ONE in-order instruction stream, although
+// the random stream does not depend on the positions.  Here every group of 32 trajectories gets
+// TWO warps: a producer that runs the key chain and turns each step's bits into the standard normal
+// draw, and a consumer that integrates.  They meet in a shared-memory ring of two 32-step halves
+// guarded by four named barriers (FULL / EMPTY per half), so the two dependent chains of a step
+// overlap in time.  Per-trajectory results are bit-identical to langevin_kernel (same functions,
+// same order).  Measured (scripts/latency_scan.py): 1050 -> 670 cycles per step STRICT, 740 -> 555
+// FAST; the producer alone needs 665 / 550 (three interleaved threefry blocks are ALU-pipe bound even
+// for a single warp), the consumer alone 595 / 455.
+constexpr int kPairThreads = 64;  // warp 0: consumer, warp 1: producer
+constexpr int kRingHalf = 32;     // steps per ring half
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+template <int POT, bool FAST, int D>
+__global__ void __launch_bounds__(kPairThreads) langevin_pair_kernel(const LangevinConsts c, const LangevinIO io) {
+  constexpr bool GRAD = D > 0;
+  constexpr int DA = GRAD ? D : 1;
+  constexpr int DPS = GRAD ? pad4(D) : 4;
+  constexpr int kFull = 1, kEmpty = 3;   // barrier ids kFull + h, kEmpty + h (0 is __syncthreads)
+  __shared__ float ring_s[2][kRingHalf][32];
+  __shared__ float r_s[kTile + 1];
+  __shared__ __align__(16) float4 tab_s[FAST ? kTile : 1];
+  __shared__ __align__(16) float phi_s[GRAD ? kTile * DPS : 4];
+
+  const int lane = threadIdx.x & 31;
+  const bool producer = threadIdx.x >= 32;
+  const long long gid = (long long)blockIdx.x * 32 + lane;
+  const bool live = gid < io.n;
+  const long long idx = live ? gid : io.n - 1;
+  const long long total = c.Neq + c.S;
+  const long long n_chunks = (total + kRingHalf - 1) / kRingHalf;
+
+  if (producer) {
+    RngPipe rng;
+    {
+      uint32_t n0, n1, r0, r1;
+      split2(io.seeds[2 * idx], io.seeds[2 * idx + 1], n0, n1, r0, r1);   // barrier_crossing.py:133,138
+      rng.prime(r0, r1);
+    }
+    for (long long ch = 0; ch < n_chunks; ++ch) {
+      const int h = (int)(ch & 1);
+      if (ch >= 2) named_bar_sync(kEmpty + h, kPairThreads);   // the consumer is done with this half
+      const int len = (int)min((long long)kRingHalf, total - ch * kRingHalf);
+      for (int i = 0; i < len; ++i) {
+        const uint32_t bits = rng.next(c.one, c.pow2);
+        ring_s[h][i][lane] = FAST ? fast_normal(bits) : normal_from_bits<false>(bits);
+      }
+      __threadfence_block();
+      named_bar_arrive(kFull + h, kPairThreads);
+    }
+    return;
+  }
+
+  // ---- consumer
+  long long chunk = 0;
+  int pos = 0;
+  auto next_z = [&]() -> float {
+    const int h = (int)(chunk & 1);
+    if (pos == 0) {
+      // release the half finished last (its values have all been used) once a later chunk needs it
+      if (chunk >= 1 && chunk + 1 < n_chunks) named_bar_arrive(kEmpty + (h ^ 1), kPairThreads);
+      named_bar_sync(kFull + h, kPairThreads);
+    }
+    const float z = ring_s[h][pos][lane];
+    if (++pos == kRingHalf) {
+      pos = 0;
+      ++chunk;
+    }
+    return z;
+  };
+
+  float x = io.x0[idx];
+  double W = 0.0, LP = 0.0;
+  float gA[DA], gB[DA];
+#pragma unroll
+  for (int j = 0; j < DA; ++j) gA[j] = gB[j] = 0.f;
+  Landscape<POT, FAST> land;
+  float z, lp;
+  {
+    const float r_eq = io.r_table[0];
+    for (long long e = 0; e < c.Neq; ++e) {  // equilibrate :115-121
+      if (FAST) {
+        fast_step_z<POT>(c, x, next_z(), r_eq);
+      } else {
+        land.eval(c, x);
+        brownian_apply_xi<POT, FAST>(c, land, x, next_z(), r_eq, z, lp);
+      }
+    }
+  }
+  for (long long t0 = 1; t0 <= c.S; t0 += kTile) {
+    const int len = (int)min((long long)kTile, c.S - t0 + 1);
+    __syncwarp();
+    for (int i = lane; i <= len; i += 32) r_s[i] = io.r_table[t0 - 1 + i];
+    if (FAST) {
+      for (int i = lane; i < len; i += 32) {
+        const float r0 = io.r_table[t0 - 1 + i], r1 = io.r_table[t0 + i];
+        const float a = 2.0f * c.hk * (r0 - r1);
+        tab_s[i] = make_float4(r1, a, -0.5f * a * (r0 + r1), 0.f);
+      }
+    }
+    if (GRAD) {
+      for (int i = lane; i < len * DPS; i += 32) {
+        const int row = i / DPS, col = i - row * DPS;
+        const long long k = t0 + row;
+        phi_s[i] = (col < io.D && k <= c.S - 1) ? io.phi[(k - 1) * io.D + col] : 0.f;
+      }
+    }
+    __syncwarp();
+    float Wt = 0.f, LPt = 0.f;
+    uint32_t r_addr = (uint32_t)__cvta_generic_to_shared(r_s);
+    uint32_t phi_addr = (uint32_t)__cvta_generic_to_shared(phi_s);
+    uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(tab_s);
+    for (int i = 0; i < len; ++i, r_addr += 4, phi_addr += 4 * DPS, tab_addr += 16) {
+      float dW, dR;
+      const float x_before = x;
+      if (FAST) {
+        const float4 tab = lds_f32x4(tab_addr);
+        dW = fmaf(tab.y, x, tab.z);
+        z = next_z();
+        dR = fast_step_z<POT>(c, x, z, tab.x);
+      } else {
+        const float r_prev = lds_f32(r_addr), r_cur = lds_f32(r_addr + 4);
+        land.eval(c, x);
+        dW = work_increment<POT, FAST>(c, land, x, r_prev, r_cur);
+        dR = brownian_apply_xi<POT, FAST>(c, land, x, next_z(), r_cur, z, lp);
+      }
+      Wt += dW;
+      if (FAST) {
+        LPt = fmaf(z, z, LPt);
+      } else {
+        LPt += lp;
+      }
+      if (GRAD) {
+        const float a = z, b = c.shift_kind == NQ_SHIFT_PERIODIC ? x - x_before : dR;
+#pragma unroll
+        for (int q = 0; q < DPS / 4; ++q) {
+          const float4 p = lds_f32x4(phi_addr + 16 * q);
+          const float pv[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (4 * q + e < D) {
+              gA[4 * q + e] = fmaf(a, pv[e], gA[4 * q + e]);
+              gB[4 * q + e] = fmaf(b, pv[e], gB[4 * q + e]);
+            }
+          }
+        }
+      }
+    }
+    W += (double)Wt;
+    if (FAST) {
+      LP += -0.5 * (double)LPt - (double)len * (double)c.log_norm;
+    } else {
+      LP += (double)LPt;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < DA; ++j) {
+    gA[j] *= c.ca;
+    gB[j] *= c.k_s;
+  }
+  const float Wf = (float)W, LPf = (float)LP;
+  const float est = __fadd_rn(__fmul_rn(LPf, Wf), Wf);
+  if (live) {
+    io.work[gid] = Wf;
+    io.logp[gid] = LPf;
+    if (io.estimator) io.estimator[gid] = est;
+    if (io.x_final) io.x_final[gid] = x;
+  }
+  const double m = live ? 1.0 : 0.0;
+  const double Wd = (double)Wf, Ld = (double)LPf;
+  constexpr int NV = 8 + 2 * DPS;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    double val = 0.0;
+    if (v == NQ_MOM_N) val = m;
+    else if (v == NQ_MOM_W) val = m * Wd;
+    else if (v == NQ_MOM_W2) val = m * Wd * Wd;
+    else if (v == NQ_MOM_LOGP) val = m * Ld;
+    else if (v == NQ_MOM_WLOGP) val = m * Wd * Ld;
+    else if (v == NQ_MOM_EST) val = m * (double)est;
+    else if (v >= 8 && GRAD) {
+      const int j = (v - 8) % DPS, which = (v - 8) / DPS;
+      if (j < D) val = which == 0 ? m * Wd * (double)gA[j < DA ? j : 0] : m * (double)gB[j < DA ? j : 0];
+    }
+    const double s = warp_sum(val);
+    if (lane == 0) io.partials[(long long)blockIdx.x * NV + v] = s;
+  }
+}
+
 // Persistent variant with a FIFO ready-queue of trajectory groups ("chains").  With 1e5
 // trajectories there are 3125 warps for 592 SM sub-partitions: a static launch leaves some with 6
 // warps and some with 5 for the whole run (makespan 6 units for an average of 5.28).  Here fewer
@@ -739,6 +951,7 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const LangevinConsts c,
 
 // per-potential launchers (defined in langevin_pot*.cu through NQ_DEFINE_POT_LAUNCHERS)
 using MainLauncher = int (*)(const LangevinConsts&, const LangevinIO&, int blocks, bool fast, bool record, cudaStream_t);
+using PairLauncher = int (*)(const LangevinConsts&, const LangevinIO&, int blocks, bool fast, cudaStream_t);
 using PersistentLauncher = int (*)(const LangevinConsts&, const LangevinIO&, const PersistentCtl&, int blocks, bool fast,
                                    cudaStream_t, int* max_blocks_per_sm);
 using ReplayLauncher = int (*)(const LangevinConsts&, const ReplayIO&, dim3 grid, size_t smem, bool fast, cudaStream_t);
@@ -751,6 +964,12 @@ using ApplyLauncher = int (*)(const LangevinConsts&, float r0, float*, uint32_t*
   case DD:                                                                                             \
     if (fast) langevin_kernel<POT, true, DD, false><<<blocks, kThreads, 0, st>>>(c, io);               \
     else langevin_kernel<POT, false, DD, false><<<blocks, kThreads, 0, st>>>(c, io);                   \
+    break;
+
+#define NQ_PAIR_CASE(POT, DD)                                                                          \
+  case DD:                                                                                             \
+    if (fast) langevin_pair_kernel<POT, true, DD><<<blocks, kPairThreads, 0, st>>>(c, io);             \
+    else langevin_pair_kernel<POT, false, DD><<<blocks, kPairThreads, 0, st>>>(c, io);                 \
     break;
 
 // occ != nullptr: only report resident CTAs per SM (no launch)
@@ -780,6 +999,15 @@ using ApplyLauncher = int (*)(const LangevinConsts&, float r0, float*, uint32_t*
       NQ_MAIN_CASE(POT, 4) NQ_MAIN_CASE(POT, 8) NQ_MAIN_CASE(POT, 12) NQ_MAIN_CASE(POT, 13)            \
       NQ_MAIN_CASE(POT, 16) NQ_MAIN_CASE(POT, 20) NQ_MAIN_CASE(POT, 24) NQ_MAIN_CASE(POT, 28)          \
       NQ_MAIN_CASE(POT, 32)                                                                            \
+      default: return -1;                                                                              \
+    }                                                                                                  \
+    return 0;                                                                                          \
+  }                                                                                                    \
+  int NAME##_pair(const LangevinConsts& c, const LangevinIO& io, int blocks, bool fast, cudaStream_t st) { \
+    switch (io.D == 0 ? 0 : (io.D <= 13 && io.D > 12 ? 13 : pad4(io.D))) {                             \
+      NQ_PAIR_CASE(POT, 0) NQ_PAIR_CASE(POT, 4) NQ_PAIR_CASE(POT, 8) NQ_PAIR_CASE(POT, 12)             \
+      NQ_PAIR_CASE(POT, 13) NQ_PAIR_CASE(POT, 16) NQ_PAIR_CASE(POT, 20) NQ_PAIR_CASE(POT, 24)          \
+      NQ_PAIR_CASE(POT, 28) NQ_PAIR_CASE(POT, 32)                                                      \
       default: return -1;                                                                              \
     }                                                                                                  \
     return 0;                                                                                          \
@@ -815,6 +1043,7 @@ using ApplyLauncher = int (*)(const LangevinConsts&, float r0, float*, uint32_t*
 
 #define NQ_DECLARE_POT_LAUNCHERS(NAME)                                                                 \
   int NAME##_main(const LangevinConsts&, const LangevinIO&, int, bool, bool, cudaStream_t);            \
+  int NAME##_pair(const LangevinConsts&, const LangevinIO&, int, bool, cudaStream_t);                  \
   int NAME##_persistent(const LangevinConsts&, const LangevinIO&, const PersistentCtl&, int, bool,    \
                         cudaStream_t, int*);                                                          \
   int NAME##_replay(const LangevinConsts&, const ReplayIO&, dim3, size_t, bool, cudaStream_t);         \

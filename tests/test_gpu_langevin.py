@@ -492,3 +492,46 @@ def test_periodic_shift_gradient_vs_oracle(cuda):
   grad, (_, (_, lp, w)) = est(coeffs, x0.reshape(B, 1, 1), J.PRNGKey(13))
   assert rel(grad.cpu().numpy(), o['grad']) < 2e-4          # wrap seams are where f32 rounding of fmod differs
   assert rel(w.cpu().numpy(), o['total_work']) < 1e-4
+
+
+@pytest.mark.parametrize('n,D,potential', [(1, 13, 'shifted'), (37, 5, 'spring'), (1000, 13, 'shifted'), (530, 32, 'biomolecule'),
+                                           (200, 1, 'spring'), (64, 20, 'shifted'), (90, 0, 'shifted')])
+def test_small_ensemble_pair_kernel_equals_main_kernel(cuda, monkeypatch, n, D, potential):
+  """Ensembles up to 8192 trajectories run a producer warp (key chain + normal draws) and a consumer
+  warp (integration) per 32 trajectories, meeting in a shared-memory ring (langevin_pair_kernel).
+  STRICT results per trajectory are bit-identical to the one-warp kernel; the float64 sums differ only
+  by grouping."""
+  from noneq_opt_b200 import barrier_crossing as bc, random as nqr, space
+  pot = {'shifted': bc.V_biomolecule_shifted(KAPPA, KAPPA, XM, 0., 1.5, BETA),
+         'biomolecule': bc.V_biomolecule(KAPPA, KAPPA, XM / 2, 0.5, 1.5, BETA), 'spring': bc.V_spring(1.3)}[potential]
+  shift = space.periodic(45.0)[1] if potential == 'biomolecule' else space.free()[1]
+  S, Neq = 333, 7
+  rng = np.random.RandomState(D)
+  seeds = nqr.split(J.PRNGKey(5), n)
+  x0 = np.full(n, 0.5, np.float32)
+  if D:
+    coeffs = np.concatenate([[20., 19.96], 0.2 * rng.normal(size=max(D - 2, 0))]).astype(np.float32)[:D]
+    run = lambda: bc.gradient_terms(pot, coeffs, x0, seeds, 0., 40., Neq, shift, S, 1e-8, KT, 1.0, KT / 1e7)
+  else:
+    r = np.linspace(0, 40, S + 1).astype(np.float32)
+    run = lambda: bc._simulate(pot, shift, r, None, torch.from_numpy(x0).cuda(), seeds, S, Neq, 1e-8, KT, 1.0, KT / 1e7)
+  pair = {k: v.clone() for k, v in run().items() if isinstance(v, torch.Tensor)}
+  monkeypatch.setenv('NQ_PAIR_MAX', '0')
+  main = run()
+  monkeypatch.delenv('NQ_PAIR_MAX')
+  for k in ('work', 'logp', 'x_final') + (('estimator',) if D else ()):
+    assert torch.equal(pair[k], main[k]), k
+  np.testing.assert_allclose(pair['moments'].cpu().numpy(), main['moments'].cpu().numpy(), rtol=1e-13)
+  if D:
+    np.testing.assert_allclose(pair['grad_sums'].cpu().numpy(), main['grad_sums'].cpu().numpy(), rtol=1e-11, atol=1e-9)
+  bc.set_math_mode('fast')
+  try:
+    monkeypatch.setenv('NQ_PAIR_MAX', '0')
+    main_f = {k: v.clone() for k, v in run().items() if isinstance(v, torch.Tensor)}
+    monkeypatch.delenv('NQ_PAIR_MAX')
+    pair_f = run()
+  finally:
+    bc.set_math_mode('strict')
+  assert rel(pair_f['work'].cpu().numpy(), main_f['work'].cpu().numpy()) < 1e-4
+  if D:
+    assert rel(pair_f['grad_sums'].cpu().numpy(), main_f['grad_sums'].cpu().numpy()) < 1e-4
