@@ -337,12 +337,59 @@ def run_native(args):
   ising_res = None if args.no_ising else bench_ising(args, dev, rank, ws)
   if rank == 0:
     line['ising'] = ising_res
+    if ws == 1 and not args.no_ising:
+      line['config1_training'] = bench_config1_training(dev)
     if ws == 1 and not args.no_cpu:
       line['cpu_baseline'] = cpu_baseline()
     print(json.dumps(line), flush=True)
   if ws > 1:
     dist.barrier()
     dist.destroy_process_group()
+
+
+def bench_config1_training(dev):
+  """configs[0] (10^3 trajectories x 10^3 steps, spring, the reference's CPU-sized case): a latency-bound
+  regime.  One whole optimisation step (key split, equilibration-free start, gradient, Adam) through
+  the step-by-step host loop and as one CUDA-graph replay (training.LangevinTrainer)."""
+  import torch
+  from noneq_opt_b200 import barrier_crossing as bc, optimizers, random as nqr, space, training
+  _, shift = space.free()
+  B, S, Neq, dt, n = 1000, 1000, 100, 1e-3, 100
+  energy = bc.V_spring(1.0)
+  coeffs0 = bc.fit_linear_to_cheby(1.0, dt, 5., 10., 12)
+  key = np.array([0, 7], np.uint32)
+  opt = optimizers.adam(optimizers.exponential_decay(0.1, n, 0.001))
+  grad_fn = bc.estimate_gradient_boltzinit(B, energy, 5., 10., Neq, shift, S, dt, 1.0, 1.0, 1.0)
+  x0 = np.full((B, 1, 1), 5., np.float32)
+
+  def host_loop(k, steps):
+    state = opt.init_fn(coeffs0)
+    for j in range(steps):
+      k, _, k2 = nqr.split_host(k, 3)
+      grad, _ = grad_fn(opt.params_fn(state), x0, k2)
+      state = opt.update_fn(j, grad, state)
+    torch.cuda.synchronize()
+  host_loop(key, 5)
+  t0 = time.perf_counter()
+  host_loop(key, n)
+  host_ms = 1e3 * (time.perf_counter() - t0) / n
+  tr = training.LangevinTrainer(B, energy, coeffs0, 5., 10., Neq, shift, S, dt, 1.0, 1.0, 1.0, key,
+                                step_size=0.1, decay_steps=n, decay_rate=0.001)
+  tr.run(5)
+  torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  t0 = time.perf_counter()
+  e0.record()
+  for _ in range(n):
+    tr.step()
+  e1.record()
+  torch.cuda.synchronize()
+  wall_ms = 1e3 * (time.perf_counter() - t0) / n
+  return dict(workload='spring, 1000 trajectories x (100 + 1000) steps, 13 coefficients, one Adam step per gradient',
+              host_loop_ms_per_step=host_ms, graph_replay_ms_per_step=wall_ms,
+              graph_replay_device_ms_per_step=e0.elapsed_time(e1) / n, launches_per_step=tr.launches_per_step,
+              traj_steps_per_s=B * (S + Neq) / (wall_ms * 1e-3),
+              note='latency-bound: 32 CTAs of one producer + one consumer warp (DESIGN.md 4.1, 4.5)')
 
 
 def bench_ising(args, dev, rank, ws):
