@@ -680,31 +680,64 @@ __global__ void random_spins_kernel(uint32_t k0, uint32_t k1, long long n_sites,
   bits[w] = word;
 }
 
-// out[r] = {sum of spins, sum over bonds of s_i s_j} of a d0 x d1 x d2 periodic lattice
-__global__ void measure_kernel(const uint32_t* bits, int ndim, int d0, int d1, int d2, long long* out) {
-  const long long rep = blockIdx.x;
+// out[r] += {sum of spins, sum over bonds of s_i s_j} of a d0 x d1 x d2 periodic lattice (out zeroed by
+// the caller; blockIdx.y = replica, blockIdx.x strides over the lattice).  One neighbour per axis
+// counts every bond once.
+__device__ __forceinline__ void measure_flush(long long m, long long b, long long* out, long long rep) {
+  m = __reduce_add_sync(0xffffffffu, (int)m);   // per-thread partial sums fit 32 bits (see the callers' grids)
+  b = __reduce_add_sync(0xffffffffu, (int)b);
+  __shared__ long long acc[2];
+  if (threadIdx.x < 2) acc[threadIdx.x] = 0;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd((unsigned long long*)&acc[0], (unsigned long long)m);
+    atomicAdd((unsigned long long*)&acc[1], (unsigned long long)b);
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) atomicAdd((unsigned long long*)&out[2 * rep + threadIdx.x], (unsigned long long)acc[threadIdx.x]);
+}
+
+// Contiguous axis a multiple of 32: 32 sites per step.  A bond joins equal spins (+1) or different
+// spins (-1): per word and axis, 32 - 2 popc(word ^ neighbour word).
+__global__ void __launch_bounds__(256) measure_words_kernel(const uint32_t* bits, int ndim, int nA, int nB, int wpl,
+                                                            long long* out) {
+  const long long rep = blockIdx.y;
+  const long long words = (long long)nA * nB * wpl;
+  const uint32_t* x = bits + rep * words;
+  int m = 0, b = 0;
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (long long)gridDim.x * blockDim.x) {
+    const int wi = (int)(w % wpl);
+    const long long line = w / wpl;
+    const int lb = (int)(line % nB), la = (int)(line / nB);
+    const uint32_t v = x[w];
+    m += 2 * __popc(v) - 32;
+    const uint32_t nxt = x[line * wpl + (wi + 1 == wpl ? 0 : wi + 1)];
+    b += 32 - 2 * __popc(v ^ ((v >> 1) | (nxt << 31)));
+    if (ndim >= 2) b += 32 - 2 * __popc(v ^ x[((long long)la * nB + (lb + 1 == nB ? 0 : lb + 1)) * wpl + wi]);
+    if (ndim >= 3) b += 32 - 2 * __popc(v ^ x[((long long)(la + 1 == nA ? 0 : la + 1) * nB + lb) * wpl + wi]);
+  }
+  measure_flush(m, b, out, rep);
+}
+
+__global__ void __launch_bounds__(256) measure_sites_kernel(const uint32_t* bits, int ndim, int d0, int d1, int d2,
+                                                            long long* out) {
+  const long long rep = blockIdx.y;
   const int N = d0 * d1 * d2;
   const size_t ext_words = ((size_t)N + 31) / 32;
   const uint32_t* x = bits + rep * ext_words;
   auto spin = [&](int p) { return ((x[p >> 5] >> (p & 31)) & 1u) ? 1 : -1; };
-  long long m = 0, b = 0;
-  for (int p = threadIdx.x; p < N; p += blockDim.x) {
-    const int k = p % d2, ij = p / d2, j = ij % d1, i = ij / d1;
-    const int s = spin(p);
+  int m = 0, b = 0;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(p % d2), ij = (int)(p / d2), j = ij % d1, i = ij / d1;
+    const int s = spin((int)p);
     m += s;
-    int fwd = 0;   // one neighbour per axis counts every bond once
+    int fwd = 0;
     if (ndim >= 1) fwd += spin(((i == d0 - 1 ? 0 : i + 1) * d1 + j) * d2 + k);
     if (ndim >= 2) fwd += spin((i * d1 + (j == d1 - 1 ? 0 : j + 1)) * d2 + k);
     if (ndim >= 3) fwd += spin((i * d1 + j) * d2 + (k == d2 - 1 ? 0 : k + 1));
     b += s * fwd;
   }
-  __shared__ long long acc[2];
-  if (threadIdx.x < 2) acc[threadIdx.x] = 0;
-  __syncthreads();
-  atomicAdd((unsigned long long*)&acc[0], (unsigned long long)m);
-  atomicAdd((unsigned long long*)&acc[1], (unsigned long long)b);
-  __syncthreads();
-  if (threadIdx.x < 2) out[2 * rep + threadIdx.x] = acc[threadIdx.x];
+  measure_flush(m, b, out, rep);
 }
 
 static bool fast_path(int L) { return L % 64 == 0; }
@@ -925,7 +958,28 @@ extern "C" int nq_ising_measure(const uint32_t* bits, int32_t ndim, const int32_
   NQ_CHECK_ARG(bits && out_MB && dims && ndim >= 1 && ndim <= 3 && R > 0, "bad arguments");
   const int d0 = dims[0], d1 = ndim >= 2 ? dims[1] : 1, d2 = ndim >= 3 ? dims[2] : 1;
   NQ_CHECK_ARG(d0 > 0 && d1 > 0 && d2 > 0, "bad lattice shape");
-  measure_kernel<<<(unsigned)R, 256, 0, (cudaStream_t)stream>>>(bits, ndim, d0, d1, d2, (long long*)out_MB);
+  const long long N = (long long)d0 * d1 * d2;
+  NQ_CHECK_ARG(N <= 0x3fffffffll, "lattice too large (N=%lld)", N);
+  cudaStream_t st = (cudaStream_t)stream;
+  NQ_CUDA(cudaMemsetAsync(out_MB, 0, (size_t)R * 2 * sizeof(int64_t), st));
+  const int last = ndim == 1 ? d0 : (ndim == 2 ? d1 : d2);
+  const size_t ext_words = ((size_t)N + 31) / 32;
+  for (int64_t r0 = 0; r0 < R; r0 += 65535) {   // gridDim.y limit
+    const unsigned nr = (unsigned)(R - r0 < 65535 ? R - r0 : 65535);
+    const uint32_t* src = bits + (size_t)r0 * ext_words;
+    long long* dst = (long long*)out_MB + 2 * r0;
+    if (last % 32 == 0) {
+      // axes padded at the front: (nA, nB, last); a thread sums at most ~2^7 words of 32 sites x 3 axes
+      const int nA = ndim == 3 ? d0 : 1, nB = ndim == 3 ? d1 : (ndim == 2 ? d0 : 1);
+      long long bx = (N / 32 + 255) / 256;
+      if (bx > 1024) bx = 1024;
+      measure_words_kernel<<<dim3((unsigned)bx, nr), 256, 0, st>>>(src, ndim, nA, nB, last / 32, dst);
+    } else {
+      long long bx = (N + 255) / 256;
+      if (bx > 1024) bx = 1024;
+      measure_sites_kernel<<<dim3((unsigned)bx, nr), 256, 0, st>>>(src, ndim, d0, d1, d2, dst);
+    }
+  }
   NQ_LAUNCHED();
   return NQ_OK;
 }

@@ -450,3 +450,23 @@ def test_config4_ensemble_carries_energy_and_magnetization_through_segments(cuda
   tele = summary.work.double().sum(1) - summary.dissipated_heat.double().sum(1)
   np.testing.assert_allclose((e_meas - e0).cpu().numpy(), tele.cpu().numpy(), rtol=0, atol=2e-5 * L * L)
   assert len(set(np.round(m_meas.cpu().numpy(), 9))) > R // 2          # replicas are distinct trajectories
+
+
+@pytest.mark.parametrize('shape', [(64, 64), (10, 10), (6, 96), (1024, 1024), (64,), (10000,), (4, 6, 32), (8, 6, 4), (2, 2), (2, 32)])
+def test_measure_entry_point_matches_numpy(cuda, shape):
+  """nq_ising_measure: {sum of spins, sum over bonds of s_i s_j} per lattice, word-parallel when the
+  contiguous axis is a multiple of 32 and per site otherwise; periodic in every axis (an axis of length
+  2 counts its bond twice, as sum_neighbors does)."""
+  import ctypes as C
+  from noneq_opt_b200 import _lib, ising
+  R = 3
+  rs = np.random.RandomState(sum(shape))
+  spins = np.where(rs.uniform(size=(R,) + shape) < 0.4, 1, -1).astype(np.int32)
+  bits = ising._pack(torch.from_numpy(spins).cuda(), lattice_ndim=len(shape))
+  out = torch.empty((R, 2), dtype=torch.int64, device='cuda')
+  dims = (C.c_int32 * 3)(*(list(shape) + [1] * (3 - len(shape))))
+  _lib.check(_lib.lib().nq_ising_measure(_lib.ptr(bits), len(shape), dims, R, _lib.ptr(out), _lib.stream_arg()))
+  s64 = spins.astype(np.int64)
+  bonds = sum((s64 * np.roll(s64, -1, axis=1 + ax)).sum(axis=tuple(range(1, 1 + len(shape)))) for ax in range(len(shape)))
+  np.testing.assert_array_equal(out.cpu().numpy()[:, 0], s64.reshape(R, -1).sum(1))
+  np.testing.assert_array_equal(out.cpu().numpy()[:, 1], bonds)
