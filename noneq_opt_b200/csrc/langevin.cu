@@ -64,13 +64,17 @@ int make_langevin_consts(const NqLangevinDesc* d, LangevinConsts* c) {
   return NQ_OK;
 }
 
-// sums block partials in block order; out_mom[8], out_grad[2][D]
-__global__ void langevin_finalize_kernel(const double* partials, int nblocks, int NV, int DPS, int D, double* out_mom,
-                                         double* out_grad) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+// Sums the block partials; out_mom[8], out_grad[2][D].  One warp per column: lane l adds blocks
+// l, l+32, ... in order and the lanes are combined by a fixed shuffle tree, so the result does not
+// depend on scheduling (bit-deterministic gradients).
+__global__ void __launch_bounds__(256) langevin_finalize_kernel(const double* partials, int nblocks, int NV, int DPS,
+                                                                 int D, double* out_mom, double* out_grad) {
+  const int q = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (q >= NV) return;
   double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += partials[(long long)b * NV + q];
+  for (int b = lane; b < nblocks; b += 32) s += partials[(long long)b * NV + q];
+  s = warp_sum(s);
+  if (lane != 0) return;
   if (q < 8) {
     if (out_mom) out_mom[q] = s;
   } else if (out_grad) {
@@ -206,7 +210,7 @@ static int run(const NqLangevinDesc* desc, const LangevinIO& io_in, double* mome
   }
   NQ_LAUNCHED();
   if (moments || grad_sums) {
-    langevin_finalize_kernel<<<1, 128, 0, st>>>(io.partials, blocks, NV, (NV - 8) / 2, io.D, moments, grad_sums);
+    langevin_finalize_kernel<<<(NV + 7) / 8, 256, 0, st>>>(io.partials, blocks, NV, (NV - 8) / 2, io.D, moments, grad_sums);
     NQ_LAUNCHED();
   }
   return NQ_OK;
