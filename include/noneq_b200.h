@@ -233,6 +233,25 @@ int nq_ising_unpack(const uint32_t* bits, int64_t n_sites, int32_t is_float, voi
 int nq_ising_measure(const uint32_t* bits, int32_t ndim, const int32_t dims[3] /*host*/, int64_t R,
                      int64_t* out_MB, void* stream);
 
+/* Gradient assembly of estimate_gradient_{rev,fwd}* (ising.py:179-236, 294-599): per replica, the loss
+ * and the contractions of the per-sweep sensitivities with the schedule Jacobians (what jax.grad /
+ * jvp through the schedule pytree produce):
+ *   logP_x[r][j] = loss_r * sum_t d fwd_lp / d x_t * J_x[t][j]    (gradient of sum(fwd_lp) * stop_gradient(loss))
+ *   rep_x[r][j]  = sum_t d loss / d x_t * J_x[t][j]               (gradient of the loss itself)
+ * for x in {log_temp (J_lt [T][Dl]), field (J_h [T][Dh])}, float64, row-major.
+ *   kind 0: loss = total_work (:252-255); kind 1: loss = total_entropy_production (:239-249), both in
+ *   closed form from `summary`, `partials` (of nq_ising_run) and MB0 (nq_ising_measure of the initial
+ *   lattice(s): [R or 1][2]); kind 2: an arbitrary LossFn whose value loss_ext[R] and sensitivities
+ *   dL_dh_ext / dL_dl_ext [R][T] the caller obtained elsewhere (the Python host uses torch autograd).
+ * log_temp_ends = {log_temp[0], log_temp[T-1]}, field0 = field[0] (host floats).                    */
+int nq_ising_grad_assemble(int32_t kind, int32_t T, int64_t R, int64_t n_sites, int32_t broadcast0,
+                           const float* log_temp_ends /*host [2]*/, float field0,
+                           const float* summary, const float* partials, const int64_t* MB0,
+                           const double* J_lt, int32_t Dl, const double* J_h, int32_t Dh,
+                           const double* dL_dh_ext, const double* dL_dl_ext, const float* loss_ext,
+                           float* loss /*[R]*/, double* logP_lt /*[R][Dl]*/, double* logP_h /*[R][Dh]*/,
+                           double* rep_lt, double* rep_h, void* stream);
+
 /* ------------------------------------------------------------------ device-resident training step */
 /* The pieces that let one optimisation step of the reference's drivers
  * (run_barrier_crossing_opt.py:113-137; ising.py:263-290) run as a fixed launch sequence with

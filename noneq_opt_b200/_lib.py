@@ -73,6 +73,9 @@ SIGNATURES = {
     'nq_ising_pack': (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P]),
     'nq_ising_unpack': (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P]),
     'nq_ising_measure': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.c_int64, _P, _P]),
+    'nq_ising_grad_assemble': (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_float),
+                                         C.c_float, _P, _P, _P, _P, C.c_int32, _P, C.c_int32, _P, _P, _P, _P, _P, _P,
+                                         _P, _P, _P]),
     'nq_random_split_dev': (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, _P, _P]),
     'nq_schedule_affine': (C.c_int, [_P, _P, _P, C.c_float, C.c_float, C.c_int64, C.c_int32, _P, _P]),
     'nq_adam_step': (C.c_int, [C.POINTER(NqAdamDesc), C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -740,6 +740,141 @@ __global__ void __launch_bounds__(256) measure_sites_kernel(const uint32_t* bits
   measure_flush(m, b, out, rep);
 }
 
+// ------------------------------------------------------------------------------ gradient assembly
+// Per replica r: the loss and the four contractions of the per-sweep sensitivities with the schedule
+// Jacobians,
+//   logP_x[r][j] = loss_r * sum_t dF/dx_t J_x[t][j],   rep_x[r][j] = sum_t dLoss/dx_t J_x[t][j],   x in {log_temp, field}
+// with dF/dx_0 = 0, dF/dx_t = partials[DFWD_Dx][r][t-1].  kind 0: loss = total_work, 1: loss =
+// total_entropy_production (both closed form from summary / partials / the initial spin and bond
+// sums), 2: loss and d loss / d x_t supplied by the caller (torch autograd of an arbitrary LossFn).
+// One CTA per replica; the sweeps are tiled through shared memory and every sum over t is a fixed
+// tree (deterministic).
+struct IsingGradArgs {
+  int kind, T, Dl, Dh, broadcast0;
+  long long R;
+  double n_sites, lt0, ltf, h0;      // schedule end points as float64 of the float32 values
+  float exp_lt0, exp_ltf;            // float32(exp(log_temp)) at both ends, for the loss in reference arithmetic
+  const float* summary;              // [7][R][T-1]
+  const float* partials;             // [4][R][T-1]
+  const long long* MB0;              // [R or 1][2]
+  const double* J_lt;                // [T][Dl]
+  const double* J_h;                 // [T][Dh]
+  const double* dL_dh_ext;           // kind 2: [R][T]
+  const double* dL_dl_ext;
+  const float* loss_ext;             // kind 2: [R]
+  float* loss;                       // [R]
+  double* logP_lt;                   // [R][Dl]
+  double* logP_h;                    // [R][Dh]
+  double* rep_lt;
+  double* rep_h;
+};
+
+constexpr int kGradTile = 512;
+
+__device__ __forceinline__ double block_sum_128(double v, double* scratch) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return (scratch[0] + scratch[1]) + (scratch[2] + scratch[3]);
+}
+
+__global__ void __launch_bounds__(128) ising_grad_kernel(const IsingGradArgs a) {
+  __shared__ double sens_s[4][kGradTile];   // dF/dl, dF/dh, dL/dl, dL/dh of the current tile of sweeps
+  __shared__ double red_s[4];
+  __shared__ double acc_s[4][32];
+  const long long r = blockIdx.x;
+  const int T = a.T, Tm1 = T - 1;
+  const long long RT = a.R * Tm1;
+  const float* S = a.summary + r * Tm1;
+  const float* P = a.partials ? a.partials + r * Tm1 : nullptr;
+  const double M0 = (double)a.MB0[a.broadcast0 ? 0 : 2 * r], B0 = (double)a.MB0[(a.broadcast0 ? 0 : 2 * r) + 1];
+  auto M_after = [&](int i) { return rint((double)S[NQ_IS_MAG * RT + i] * a.n_sites); };  // spin sum after sweep i+1
+  auto M_before = [&](int i) { return i == 0 ? M0 : M_after(i - 1); };                       // before sweep i+1
+
+  // ---- loss
+  float loss;
+  if (a.kind == 2) {
+    loss = a.loss_ext[r];
+  } else {
+    const int plane = a.kind == 0 ? NQ_IS_WORK : NQ_IS_EP;
+    double s = 0.0;
+    for (int t = threadIdx.x; t < Tm1; t += blockDim.x) s += (double)S[plane * RT + t];
+    const float traj = (float)block_sum_128(s, red_s);           // exact sum of the float32 terms, rounded once
+    if (a.kind == 0) {
+      loss = traj;
+    } else {
+      const float e_init = (float)(-(B0 + a.h0 * M0));
+      const float lp_init = __fdiv_rn(-e_init, a.exp_lt0);
+      const float lp_fin = __fdiv_rn(-S[NQ_IS_ENERGY * RT + Tm1 - 1], a.exp_ltf);
+      loss = __fadd_rn(__fsub_rn(lp_init, lp_fin), traj);
+    }
+  }
+  if (threadIdx.x == 0) a.loss[r] = loss;
+  for (int j = threadIdx.x; j < 4 * 32; j += blockDim.x) acc_s[j / 32][j % 32] = 0.0;
+  const double e0 = exp(-a.lt0), ef = exp(-a.ltf);
+
+  for (int t0 = 0; t0 < T; t0 += kGradTile) {
+    const int len = min(kGradTile, T - t0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+      const int t = t0 + i;
+      double fl = 0.0, fh = 0.0, ll = 0.0, lh = 0.0;
+      if (t >= 1 && P) {
+        fh = (double)P[NQ_IS_DFWD_DH * RT + t - 1];
+        fl = (double)P[NQ_IS_DFWD_DL * RT + t - 1];
+      }
+      if (a.kind == 2) {
+        lh = a.dL_dh_ext[r * T + t];
+        ll = a.dL_dl_ext[r * T + t];
+      } else if (a.kind == 0) {                       // work_t = -(h_t - h_{t-1}) M_{t-1}
+        if (t >= 1) lh -= M_before(t - 1);
+        if (t <= T - 2) lh += M_before(t);
+      } else {
+        if (t >= 1) {
+          lh = fh - (double)P[NQ_IS_DREV_DH * RT + t - 1];
+          ll = fl - (double)P[NQ_IS_DREV_DL * RT + t - 1];
+        }
+        // end-point term log_prob(initial; params[0]) - log_prob(final; params[T-1]), log_prob = (B + h M) e^{-lt}
+        if (t == 0) {
+          lh += M0 * e0;
+          ll += -(B0 + a.h0 * M0) * e0;
+        }
+        if (t == T - 1) {
+          lh += -M_after(Tm1 - 1) * ef;
+          ll += -(double)S[NQ_IS_ENERGY * RT + Tm1 - 1] * ef;
+        }
+      }
+      sens_s[0][i] = fl; sens_s[1][i] = fh; sens_s[2][i] = ll; sens_s[3][i] = lh;
+    }
+    __syncthreads();
+    // 2 (Dl + Dh) dot products of length len: one warp per (term, column), lanes stride over the tile
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_dots = 2 * (a.Dl + a.Dh);
+    for (int d = warp; d < n_dots; d += 4) {
+      const bool is_rep = d >= a.Dl + a.Dh;
+      const int c = is_rep ? d - (a.Dl + a.Dh) : d;
+      const bool is_h = c >= a.Dl;
+      const int j = is_h ? c - a.Dl : c, D = is_h ? a.Dh : a.Dl;
+      const double* Jm = (is_h ? a.J_h : a.J_lt) + (long long)t0 * D + j;
+      const double* v = sens_s[(is_rep ? 2 : 0) + (is_h ? 1 : 0)];
+      double s = 0.0;
+      for (int i = lane; i < len; i += 32) s += v[i] * Jm[(long long)i * D];
+      s = warp_sum(s);
+      if (lane == 0) acc_s[(is_rep ? 2 : 0) + (is_h ? 1 : 0)][j] += s;
+    }
+  }
+  __syncthreads();
+  const double lw = (double)loss;
+  for (int j = threadIdx.x; j < a.Dl; j += blockDim.x) {
+    a.logP_lt[r * a.Dl + j] = lw * acc_s[0][j];
+    a.rep_lt[r * a.Dl + j] = acc_s[2][j];
+  }
+  for (int j = threadIdx.x; j < a.Dh; j += blockDim.x) {
+    a.logP_h[r * a.Dh + j] = lw * acc_s[1][j];
+    a.rep_h[r * a.Dh + j] = acc_s[3][j];
+  }
+}
+
 static bool fast_path(int L) { return L % 64 == 0; }
 static size_t fast_smem_bytes(int L, bool warp_team, int nteams, bool global_lat = false) {
   const size_t lat_words = global_lat ? 0 : 2 * (size_t)L * (L / 64);
@@ -980,6 +1115,33 @@ extern "C" int nq_ising_measure(const uint32_t* bits, int32_t ndim, const int32_
       measure_sites_kernel<<<dim3((unsigned)bx, nr), 256, 0, st>>>(src, ndim, d0, d1, d2, dst);
     }
   }
+  NQ_LAUNCHED();
+  return NQ_OK;
+}
+
+extern "C" int nq_ising_grad_assemble(int32_t kind, int32_t T, int64_t R, int64_t n_sites, int32_t broadcast0,
+                                      const float* log_temp_ends /*host [2]*/, float field0,
+                                      const float* summary, const float* partials, const int64_t* MB0,
+                                      const double* J_lt, int32_t Dl, const double* J_h, int32_t Dh,
+                                      const double* dL_dh_ext, const double* dL_dl_ext, const float* loss_ext,
+                                      float* loss, double* logP_lt, double* logP_h, double* rep_lt, double* rep_h,
+                                      void* stream) {
+  NQ_CHECK_ARG(kind >= 0 && kind <= 2, "kind must be 0 (work), 1 (entropy production) or 2 (external)");
+  NQ_CHECK_ARG(T >= 2 && R >= 1 && n_sites >= 1, "need T >= 2, R >= 1, n_sites >= 1");
+  NQ_CHECK_ARG(Dl >= 1 && Dl <= 32 && Dh >= 1 && Dh <= 32, "1 <= variables per schedule component <= 32 (got %d, %d)", Dl, Dh);
+  NQ_CHECK_ARG(log_temp_ends && summary && MB0 && J_lt && J_h && loss && logP_lt && logP_h && rep_lt && rep_h, "null pointer");
+  NQ_CHECK_ARG(kind == 2 || partials || kind == 0, "partials are required for the entropy-production loss");
+  NQ_CHECK_ARG(kind != 1 || partials, "partials are required for the entropy-production loss");
+  NQ_CHECK_ARG(kind != 2 || (dL_dh_ext && dL_dl_ext && loss_ext), "kind 2 needs loss_ext, dL_dh_ext, dL_dl_ext");
+  IsingGradArgs a{};
+  a.kind = kind; a.T = T; a.Dl = Dl; a.Dh = Dh; a.broadcast0 = broadcast0; a.R = R;
+  a.n_sites = (double)n_sites;
+  a.lt0 = (double)log_temp_ends[0]; a.ltf = (double)log_temp_ends[1]; a.h0 = (double)field0;
+  a.exp_lt0 = (float)exp((double)log_temp_ends[0]); a.exp_ltf = (float)exp((double)log_temp_ends[1]);
+  a.summary = summary; a.partials = partials; a.MB0 = (const long long*)MB0;
+  a.J_lt = J_lt; a.J_h = J_h; a.dL_dh_ext = dL_dh_ext; a.dL_dl_ext = dL_dl_ext; a.loss_ext = loss_ext;
+  a.loss = loss; a.logP_lt = logP_lt; a.logP_h = logP_h; a.rep_lt = rep_lt; a.rep_h = rep_h;
+  ising_grad_kernel<<<(unsigned)R, 128, 0, (cudaStream_t)stream>>>(a);
   NQ_LAUNCHED();
   return NQ_OK;
 }

@@ -469,8 +469,10 @@ def _generic_loss_sensitivities(loss_function, run: _Run, log_temp, field, L, in
 
 
 def _loss_and_sensitivities(kind, run: _Run, log_temp, field, L):
+  """Per replica: loss [R] (float32) and d loss / d field_t, d loss / d log_temp_t as [R, T] float64.
+  The torch form of what `nq_ising_grad_assemble` computes for the two closed-form losses; kept as the
+  checker of that kernel (tests/test_gpu_ising.py), not called by the estimators."""
   n_sites = float(np.prod(_shape_of(L)))
-  """Per replica: loss [R] (float32) and d loss / d field_t, d loss / d log_temp_t as [R, T] float64."""
   S = run.summary.to(torch.float64)                 # [7, R, T-1]
   R, Tm1 = S.shape[1], S.shape[2]
   T = Tm1 + 1
@@ -502,8 +504,11 @@ def _loss_and_sensitivities(kind, run: _Run, log_temp, field, L):
     dL_dl[:, -1] += -E_fin * ef
     # loss value in the reference's float32 arithmetic: -energy / exp(log_temp) at both ends
     e_init32 = (-(B0 + h[0] * M0)).to(torch.float32)
-    lp_init = -e_init32 / float(np.exp(np.float64(F32(log_temp[0]))).astype(F32))
-    lp_fin = -run.summary[_lib.NQ_IS_ENERGY][:, -1] / float(np.exp(np.float64(F32(log_temp[-1]))).astype(F32))
+    # tensor / tensor: IEEE division (torch turns division by a host scalar into a reciprocal multiply)
+    exp_ends = torch.tensor([np.exp(np.float64(F32(log_temp[0]))), np.exp(np.float64(F32(log_temp[-1])))],
+                            dtype=torch.float32, device=dev)
+    lp_init = -e_init32 / exp_ends[0]
+    lp_fin = -run.summary[_lib.NQ_IS_ENERGY][:, -1] / exp_ends[1]
     loss = (lp_init - lp_fin) + _sum32(run.summary[_lib.NQ_IS_EP])
   return loss, dL_dh, dL_dl
 
@@ -532,6 +537,23 @@ def _pack_grad_like(schedule: IsingSchedule, g_lt: torch.Tensor, g_h: torch.Tens
   return IsingSchedule(like(schedule.log_temp, g_lt), like(schedule.field, g_h))
 
 
+_JACOBIAN_CACHE = {}
+
+
+def _jacobian_on_device(J, dev):
+  """Schedule Jacobian [T, D] as a float64 device tensor; uploaded once per distinct table (an
+  optimisation loop evaluates the same Jacobian every step: every Parameterization is affine)."""
+  J = np.ascontiguousarray(J, np.float64)
+  key = (J.shape, str(dev), hash(J.tobytes()))
+  hit = _JACOBIAN_CACHE.get(key)
+  if hit is None:
+    hit = torch.from_numpy(J.copy()).to(dev)
+    if len(_JACOBIAN_CACHE) >= 16:
+      _JACOBIAN_CACHE.pop(next(iter(_JACOBIAN_CACHE)))
+    _JACOBIAN_CACHE[key] = hit
+  return hit
+
+
 def _gradient_terms(loss_function, schedule, times, initial_spins, seed, checkpoint_every=None):
   kind = _loss_kind(loss_function)
   times, log_temp, field, J_lt, J_h = _schedule_tables(schedule, times)
@@ -540,26 +562,33 @@ def _gradient_terms(loss_function, schedule, times, initial_spins, seed, checkpo
   if checkpoint_every is not None:
     control_flow.check_divides(len(times) - 1, checkpoint_every)
   run = _run_kernel(log_temp, field, bits, broadcast, seeds, L, want_partials=True)
+  dev = run.summary.device
+  R, T = run.summary.shape[1], len(times)
+  Jl = _jacobian_on_device(J_lt, dev)
+  Jh = _jacobian_on_device(J_h, dev)
+  Dl, Dh = Jl.shape[1], Jh.shape[1]
+  ext = (None, None, None)
   if kind == 'generic':
     final_spins = _unpack(run.final_bits, L, torch.zeros((), dtype=torch.float32))
-    loss, dL_dh, dL_dl = _generic_loss_sensitivities(loss_function, run, log_temp, field, L, spins, final_spins)
-  else:
-    loss, dL_dh, dL_dl = _loss_and_sensitivities(kind, run, log_temp, field, L)
-  P = run.partials.to(torch.float64)
-  dev = P.device
-  R = P.shape[1]
-  dF_dh = torch.zeros_like(dL_dh)
-  dF_dl = torch.zeros_like(dL_dl)
-  dF_dh[:, 1:] = P[_lib.NQ_IS_DFWD_DH]
-  dF_dl[:, 1:] = P[_lib.NQ_IS_DFWD_DL]
-  Jl = torch.from_numpy(J_lt).to(dev)
-  Jh = torch.from_numpy(J_h).to(dev)
-  lw = loss.to(torch.float64)[:, None]
-  logP = ((lw * dF_dl) @ Jl, (lw * dF_dh) @ Jh)          # grad of sum(fwd_lp) * stop_grad(loss)
-  reparam = (dL_dl @ Jl, dL_dh @ Jh)                      # grad of loss
+    loss_ext, dL_dh, dL_dl = _generic_loss_sensitivities(loss_function, run, log_temp, field, L, spins, final_spins)
+    ext = (dL_dh.to(torch.float64).contiguous(), dL_dl.to(torch.float64).contiguous(),
+           loss_ext.to(torch.float32).contiguous())
+  if Dl > 32 or Dh > 32:
+    raise ValueError(f'at most 32 variables per schedule component (got {Dl}, {Dh})')
+  loss = torch.empty(R, dtype=torch.float32, device=dev)
+  g = [torch.empty((R, d), dtype=torch.float64, device=dev) for d in (Dl, Dh, Dl, Dh)]
+  ends = (C.c_float * 2)(float(F32(log_temp[0])), float(F32(log_temp[-1])))
+  n_sites = int(np.prod(_shape_of(L)))
+  _lib.check(_lib.lib().nq_ising_grad_assemble(
+      {'work': 0, 'entropy': 1, 'generic': 2}[kind], T, R, n_sites, int(run.MB0.shape[0] == 1),
+      ends, float(F32(field[0])), _lib.ptr(run.summary), _lib.ptr(run.partials), _lib.ptr(run.MB0),
+      _lib.ptr(Jl), Dl, _lib.ptr(Jh), Dh, _lib.ptr(ext[0]), _lib.ptr(ext[1]), _lib.ptr(ext[2]),
+      _lib.ptr(loss), _lib.ptr(g[0]), _lib.ptr(g[1]), _lib.ptr(g[2]), _lib.ptr(g[3]), _lib.stream_arg()))
+  logP = (g[0], g[1])          # grad of sum(fwd_lp) * stop_grad(loss)
+  reparam = (g[2], g[3])       # grad of loss
   if not batched:
-    logP = tuple(g[0] for g in logP)
-    reparam = tuple(g[0] for g in reparam)
+    logP = tuple(x[0] for x in logP)
+    reparam = tuple(x[0] for x in reparam)
   return dict(logP=logP, reparam=reparam, loss=loss if batched else loss[0],
               summary=_summary_from(run, batched), batched=batched, schedule=schedule, run=run)
 

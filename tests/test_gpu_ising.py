@@ -470,3 +470,34 @@ def test_measure_entry_point_matches_numpy(cuda, shape):
   bonds = sum((s64 * np.roll(s64, -1, axis=1 + ax)).sum(axis=tuple(range(1, 1 + len(shape)))) for ax in range(len(shape)))
   np.testing.assert_array_equal(out.cpu().numpy()[:, 0], s64.reshape(R, -1).sum(1))
   np.testing.assert_array_equal(out.cpu().numpy()[:, 1], bonds)
+
+
+@pytest.mark.parametrize('loss_name', ['total_work', 'total_entropy_production'])
+@pytest.mark.parametrize('L,R,T', [(64, 7, 9), (10, 3, 700)])
+def test_gradient_assembly_kernel_matches_torch_contraction(cuda, loss_name, L, R, T):
+  """nq_ising_grad_assemble against the same contraction written with torch float64 ops
+  (ising._loss_and_sensitivities + matmul with the schedule Jacobians): losses bit-equal, gradients to
+  float64 rounding.  T = 700 crosses the kernel's 512-sweep tile."""
+  from noneq_opt_b200 import _lib, ising, parameterization as p10n
+  rs = np.random.RandomState(T)
+  sched = ising.IsingSchedule(
+      p10n.AddBaseline(p10n.ConstrainEndpoints(p10n.Chebyshev((0.1 * rs.normal(size=5)).astype(np.float32)), 0., 0.),
+                       ising.log_temp_baseline(0.69, 10, 1)),
+      p10n.Chebyshev(np.array([-0.4, 0.6, 0.2], np.float32)))
+  times = np.linspace(0, 1, T, dtype=np.float32)
+  s0 = I.random_spins((L, L), .5, J.PRNGKey(3))
+  loss_fn = getattr(ising, loss_name)
+  t = ising._gradient_terms(loss_fn, sched, times, s0, J.split(J.PRNGKey(1), R))
+  run = t['run']
+  _, lt, h, J_lt, J_h = ising._schedule_tables(sched, times)
+  loss, dL_dh, dL_dl = ising._loss_and_sensitivities(ising._loss_kind(loss_fn), run, lt, h, L)
+  P = run.partials.double()
+  dF_dh, dF_dl = torch.zeros_like(dL_dh), torch.zeros_like(dL_dl)
+  dF_dh[:, 1:], dF_dl[:, 1:] = P[_lib.NQ_IS_DFWD_DH], P[_lib.NQ_IS_DFWD_DL]
+  Jl, Jh = torch.from_numpy(J_lt).cuda(), torch.from_numpy(J_h).cuda()
+  assert torch.equal(t['loss'], loss)
+  lw = t['loss'].double()[:, None]
+  for got, want in ((t['logP'][0], (lw * dF_dl) @ Jl), (t['logP'][1], (lw * dF_dh) @ Jh),
+                    (t['reparam'][0], dL_dl @ Jl), (t['reparam'][1], dL_dh @ Jh)):
+    scale = float(want.abs().max()) + 1e-300
+    assert float((got - want).abs().max()) <= 1e-11 * scale + 1e-9
