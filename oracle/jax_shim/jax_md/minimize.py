@@ -1,0 +1,1 @@
+"""placeholder: imported by the reference, not called on the hot path"""

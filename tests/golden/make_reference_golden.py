@@ -1,0 +1,100 @@
+"""Generate tests/golden/reference_*.npz by executing the REFERENCE's own source
+(/root/reference/noneq_opt/*.py, imported verbatim, never copied) on top of oracle/jax_shim -- a
+torch-CPU float32 stand-in for jax / jax_md / tensorflow_probability / distrax whose random streams
+come from oracle/jaxlike.py (KAT-pinned threefry).  Run in the build container only:
+
+    python tests/golden/make_reference_golden.py
+
+The fixtures pin the oracle (tests/test_oracle_reference.py) and the CUDA path (tests/test_gpu_reference.py)
+to the reference's source: step order, key plumbing, work / log-prob bookkeeping, estimator objectives.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REFERENCE = os.environ.get('NQ_REFERENCE_ROOT', '/root/reference')
+sys.path[:0] = [os.path.join(ROOT, 'oracle', 'jax_shim'), REFERENCE, ROOT]
+
+import jax  # noqa: E402  (the shim)
+import jax.numpy as jnp  # noqa: E402
+from jax_md import space  # noqa: E402
+from noneq_opt import barrier_crossing as ref_bc  # noqa: E402  (the reference, verbatim)
+from noneq_opt import ising as ref_ising  # noqa: E402
+from noneq_opt import parameterization as ref_p10n  # noqa: E402
+from noneq_opt import potentials as ref_potentials  # noqa: E402
+
+
+def to_np(x):
+  return jax.tree_map(lambda l: l.detach().numpy() if hasattr(l, 'detach') else np.asarray(l), x)
+
+
+def langevin_cases():
+  out = {}
+  _, shift = space.free()
+  kT = 4.183
+  beta, x_m = 1.0 / kT, 14.0
+  kappa = 21.3863 / (beta * x_m ** 2)
+  cases = {
+      'spring': dict(energy=ref_potentials.V_spring(1.0), coeffs=np.asarray(ref_bc.fit_linear_to_cheby(1.0, 1e-3, 5., 10., 12)),
+                     r0=(5., 10.), x0=5.0, Neq=20, S=300, dt=1e-3, kT=1.0, mass=1.0, gamma=1.0),
+      'shifted': dict(energy=ref_bc.V_biomolecule_shifted(kappa, kappa, x_m, 0., 1.5, beta),
+                      coeffs=np.array([20., 19.95996, 0.3, -0.2, 0.1] + [0.] * 8, np.float32),
+                      r0=(0., 40.), x0=0.0, Neq=0, S=400, dt=1e-8, kT=kT, mass=1.0, gamma=kT / 1e7),
+  }
+  for name, c in cases.items():
+    B = 6
+    coeffs = jnp.array(np.asarray(c['coeffs'], np.float32))
+    init_pos = jnp.array(np.full((B, 1, 1), c['x0'], np.float32))
+    seed = jax.random.PRNGKey(3)
+    # forward trajectories, one call per key, exactly as the estimators vmap it (barrier_crossing.py:221)
+    seeds = jax.random.split(seed, B)
+    pos, lps, works = [], [], []
+    for b in range(B):
+      p, l, w = ref_bc.run_brownian_opt(c['energy'], coeffs, init_pos[b], c['r0'][0], c['r0'][1], c['Neq'], shift,
+                                        seeds[b], c['S'], c['dt'], c['kT'], c['mass'], c['gamma'])
+      pos.append(to_np(p)); lps.append(to_np(l)); works.append(to_np(w))
+    est = ref_bc.estimate_gradient_boltzinit(B, c['energy'], c['r0'][0], c['r0'][1], c['Neq'], shift, c['S'], c['dt'],
+                                             c['kT'], c['mass'], c['gamma'])
+    grad, (estimator, (positions, tot_lp, tot_w)) = est(coeffs, init_pos, seed)
+    out[name] = dict(coeffs=np.asarray(c['coeffs'], np.float32), r0=np.array(c['r0'], np.float32), x0=np.float32(c['x0']),
+                     Neq=c['Neq'], S=c['S'], dt=c['dt'], kT=c['kT'], mass=c['mass'], gamma=c['gamma'], seed=np.asarray(seed),
+                     positions=np.stack(pos), log_probs=np.stack(lps), works=np.stack(works),
+                     grad=to_np(grad), estimator=to_np(estimator), tot_log_prob=to_np(tot_lp), total_work=to_np(tot_w),
+                     est_positions=to_np(positions))
+  return out
+
+
+def ising_cases():
+  out = {}
+  for name, L, T, R in (('small', 16, 12, 3), ('fastpath', 64, 5, 2)):
+    w_lt = np.array([0.3, -0.2, 0.1], np.float32)
+    w_h = np.array([-0.4, 0.6, 0.2], np.float32)
+    schedule = ref_ising.IsingSchedule(ref_p10n.Chebyshev(jnp.array(w_lt)), ref_p10n.Chebyshev(jnp.array(w_h)))
+    times = jnp.linspace(0, 1, T)
+    params = schedule(times)
+    spins0 = ref_ising.random_spins((L, L), 0.5, jax.random.PRNGKey(11))
+    seeds = jax.random.split(jax.random.PRNGKey(7), R)
+    finals, summaries, grads = [], [], {'total_entropy_production': [], 'total_work': []}
+    for r in range(R):
+      final_state, summary = ref_ising.simulate_ising(params, spins0, seeds[r])
+      finals.append(to_np(final_state.spins))
+      summaries.append(np.stack([to_np(getattr(summary, f)) for f in summary._fields]))
+      for loss in grads:
+        g, _ = ref_ising.estimate_gradient_rev(getattr(ref_ising, loss))(schedule, times, spins0, seeds[r])
+        grads[loss].append(np.stack([to_np(g.log_temp.weights), to_np(g.field.weights)]))
+    out[name] = dict(L=L, T=T, w_lt=w_lt, w_h=w_h, times=to_np(times), log_temp=to_np(params.log_temp),
+                     field=to_np(params.field), spins0=to_np(spins0), seeds=np.asarray(seeds),
+                     final_spins=np.stack(finals), summary=np.stack(summaries),
+                     grad_entropy=np.stack(grads['total_entropy_production']), grad_work=np.stack(grads['total_work']),
+                     summary_fields=np.array(list(ref_ising.IsingSummary._fields)))
+  return out
+
+
+if __name__ == '__main__':
+  for prefix, cases in (('reference_langevin', langevin_cases()), ('reference_ising', ising_cases())):
+    flat = {f'{k}/{f}': v for k, d in cases.items() for f, v in d.items()}
+    np.savez_compressed(os.path.join(HERE, prefix + '.npz'), **flat)
+    print(prefix, {k: {f: np.shape(v) for f, v in d.items()} for k, d in cases.items()})

@@ -1,0 +1,81 @@
+"""The oracle against the REFERENCE'S OWN SOURCE.
+
+tests/golden/reference_*.npz hold outputs of /root/reference/noneq_opt/{barrier_crossing,ising}.py,
+imported verbatim and executed over oracle/jax_shim (torch-CPU float32 stand-ins for jax, jax_md,
+tensorflow_probability and distrax; threefry streams from oracle/jaxlike.py) by
+tests/golden/make_reference_golden.py.  This pins the oracle's reading of the reference -- step order,
+key plumbing, work / log-prob bookkeeping, the estimator objectives and what autodiff makes of them --
+to the reference's code rather than to a restatement of it.  Tolerances cover only the last bits of
+exp / log / erf_inv / sigmoid and reduction order (torch kernels vs the oracle's float64-then-round).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ising_ref as I, jaxlike as J, langevin_ref as L, parameterization_ref as P
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+KT = 4.183; BETA = 1 / KT; XM = 14.; KAPPA = 21.3863 / (BETA * XM ** 2)
+
+
+def case(file, name):
+  g = np.load(os.path.join(GOLD, file))
+  return {k.split('/')[1]: g[k] for k in g.files if k.startswith(name + '/')}
+
+
+def rel(a, b):
+  return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max() / np.abs(b).max())
+
+
+@pytest.mark.parametrize('name', ['spring', 'shifted'])
+def test_langevin_oracle_reproduces_the_reference_source(name):
+  c = case('reference_langevin.npz', name)
+  pot = L.V_spring(1.0) if name == 'spring' else L.V_biomolecule_shifted(KAPPA, KAPPA, XM, 0., 1.5, BETA)
+  B = c['positions'].shape[0]
+  o = L.estimate_gradient(pot, c['coeffs'], np.full(B, c['x0'], np.float32), c['seed'], float(c['r0'][0]), float(c['r0'][1]),
+                          int(c['Neq']), int(c['S']), float(c['dt']), float(c['kT']), float(c['mass']), float(c['gamma']),
+                          record=True)
+  # run_brownian_opt (barrier_crossing.py:97-143), one call per row of split(seed, B)
+  assert rel(o['traj']['positions'], c['positions'][:, :, 0, 0]) < 1e-6
+  assert rel(o['traj']['log_probs'], c['log_probs']) < 1e-6
+  assert np.abs(o['traj']['works'] - c['works']).max() < 2e-6 * np.abs(c['total_work']).max()
+  assert np.all(c['works'][:, 0] == 0) and c['positions'].shape[1] == int(c['S']) + 1
+  if name == 'spring':   # no transcendental on the path except erf_inv: the two agree bit for bit
+    np.testing.assert_array_equal(o['traj']['positions'], c['positions'][:, :, 0, 0])
+    np.testing.assert_array_equal(o['traj']['works'], c['works'])
+  # estimate_gradient_boltzinit (:204-224): jax.value_and_grad of sum(logp) sg(W) + W through the scan
+  np.testing.assert_allclose(c['est_positions'], c['positions'])
+  assert rel(o['total_work'], c['total_work']) < 1e-6 and rel(o['tot_log_prob'], c['tot_log_prob']) < 1e-6
+  assert rel(o['grad'], c['grad']) < 1e-5
+  assert rel(o['tot_log_prob'] * o['total_work'] + o['total_work'], c['estimator']) < 1e-6
+
+
+@pytest.mark.parametrize('name', ['small', 'fastpath'])
+def test_ising_oracle_reproduces_the_reference_source(name):
+  c = case('reference_ising.npz', name)
+  T, shape = int(c['T']), c['spins0'].shape
+  times = np.linspace(0, 1, T, dtype=np.float32)
+  np.testing.assert_array_equal(times, c['times'])
+  # IsingSchedule(Chebyshev, Chebyshev)(times) (ising.py:19-25, parameterization.py:144-179)
+  np.testing.assert_allclose(P.Chebyshev(c['w_lt'])(times), c['log_temp'], atol=1e-7)
+  np.testing.assert_allclose(P.Chebyshev(c['w_h'])(times), c['field'], atol=1e-7)
+  # random_spins (:71-72)
+  np.testing.assert_array_equal(I.random_spins(shape, 0.5, J.PRNGKey(11)), c['spins0'])
+  fields = [str(f) for f in c['summary_fields']]
+  n = float(np.prod(shape))
+  for r in range(c['seeds'].shape[0]):
+    fin, summ = I.simulate_ising(c['log_temp'], c['field'], c['spins0'], c['seeds'][r])
+    np.testing.assert_array_equal(fin, c['final_spins'][r])          # spin history bit-exact
+    for i, f in enumerate(fields):
+      got, want = getattr(summ, f), c['summary'][r, i]
+      if f == 'magnetization':
+        np.testing.assert_array_equal(got, want)
+      else:   # float32 sums over L^2 sites: a few ulp of the largest partial sum
+        assert np.abs(got - want).max() <= 8 * np.spacing(np.float32(max(n, np.abs(want).max()))), f
+    # estimate_gradient_rev (:179-198): jax.grad of sum(fwd_lp) sg(loss) + loss wrt the schedule weights
+    so = P.Chebyshev(c['w_lt']), P.Chebyshev(c['w_h'])
+    for loss, key in (('total_entropy_production', 'grad_entropy'), ('total_work', 'grad_work')):
+      cf = I.closed_form_gradient(loss, so[0](times), so[1](times), so[0].jacobian(times), so[1].jacobian(times),
+                                  c['spins0'], c['seeds'][r])
+      assert rel(cf['grad'][0], c[key][r, 0]) < 2e-5 and rel(cf['grad'][1], c[key][r, 1]) < 2e-5, (loss, r)
