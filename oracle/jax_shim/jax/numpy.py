@@ -134,13 +134,18 @@ def einsum(spec, *ops):
   return _w(_torch.einsum(spec, *ts))
 
 
-def interp(x, xp, fp):
-  """numpy.interp semantics (clamped ends), differentiable in fp."""
+def interp(x, xp, fp, left=None, right=None):
+  """numpy.interp semantics (clamped ends unless left / right are given), differentiable in fp."""
   x, xp, fp = asarray(x), asarray(xp), asarray(fp)
   idx = _torch.clamp(_torch.searchsorted(xp.contiguous(), x.contiguous(), right=True) - 1, 0, xp.shape[0] - 2)
   x0, x1, y0, y1 = xp[idx], xp[idx + 1], fp[idx], fp[idx + 1]
   t = _torch.clamp((x - x0) / (x1 - x0), 0., 1.)
-  return _w(y0 + t * (y1 - y0))
+  out = y0 + t * (y1 - y0)
+  if left is not None:
+    out = _torch.where(x < xp[0], asarray(left).to(out.dtype), out)
+  if right is not None:
+    out = _torch.where(x > xp[-1], asarray(right).to(out.dtype), out)
+  return _w(out)
 
 
 def float64(x):

@@ -59,7 +59,15 @@ def langevin_cases():
     est = ref_bc.estimate_gradient_boltzinit(B, c['energy'], c['r0'][0], c['r0'][1], c['Neq'], shift, c['S'], c['dt'],
                                              c['kT'], c['mass'], c['gamma'])
     grad, (estimator, (positions, tot_lp, tot_w)) = est(coeffs, init_pos, seed)
-    out[name] = dict(coeffs=np.asarray(c['coeffs'], np.float32), r0=np.array(c['r0'], np.float32), x0=np.float32(c['x0']),
+    # the log-prob-only and reparameterisation-only estimators (:262-311) and the Boltzmann pre-pass (:227-256)
+    g_logp, _ = ref_bc.estimate_gradient_boltzinit_logP(B, c['energy'], c['r0'][0], c['r0'][1], c['Neq'], shift, c['S'],
+                                                        c['dt'], c['kT'], c['mass'], c['gamma'])(coeffs, init_pos, seed)
+    g_rep, _ = ref_bc.estimate_gradient_boltzinit_reparam(B, c['energy'], c['r0'][0], c['r0'][1], c['Neq'], shift, c['S'],
+                                                          c['dt'], c['kT'], c['mass'], c['gamma'])(coeffs, init_pos, seed)
+    eqm = ref_bc.mapped_brownian_eqm(B, c['energy'], init_pos[0], c['r0'][0], shift, 40, c['dt'], c['kT'], c['mass'],
+                                     c['gamma'])(jax.random.PRNGKey(5))
+    out[name] = dict(grad_logP=to_np(g_logp), grad_reparam=to_np(g_rep), eqm=to_np(eqm),
+                     coeffs=np.asarray(c['coeffs'], np.float32), r0=np.array(c['r0'], np.float32), x0=np.float32(c['x0']),
                      Neq=c['Neq'], S=c['S'], dt=c['dt'], kT=c['kT'], mass=c['mass'], gamma=c['gamma'], seed=np.asarray(seed),
                      positions=np.stack(pos), log_probs=np.stack(lps), works=np.stack(works),
                      grad=to_np(grad), estimator=to_np(estimator), tot_log_prob=to_np(tot_lp), total_work=to_np(tot_w),
@@ -93,8 +101,27 @@ def ising_cases():
   return out
 
 
+def schedule_cases():
+  """The protocol algebra of parameterization.py and the baselines of ising.py:45-55, evaluated by the reference."""
+  x = jnp.linspace(0, 1, 33)
+  rs = np.random.RandomState(4)
+  w = (0.3 * rs.normal(size=7)).astype(np.float32)
+  knots = (np.linspace(-1, 2, 8)[1:-1] + 0.2 * rs.normal(size=6)).astype(np.float32)
+  cheb = ref_p10n.Chebyshev(jnp.array(w))
+  pwl = ref_p10n.PiecewiseLinear(jnp.array(knots), jnp.array(0.), jnp.array(1.), jnp.array(-1.), jnp.array(2.))
+  lt_base, h_base = ref_ising.log_temp_baseline(0.69, 10., 1), ref_ising.field_baseline(-1., 1.)
+  composed = ref_p10n.AddBaseline(ref_p10n.ConstrainEndpoints(cheb, 0., 0.), lt_base)
+  moved = ref_p10n.ChangeDomain(cheb, jnp.array(2.), jnp.array(5.))
+  x25 = jnp.linspace(2, 5, 33)
+  return dict(all=dict(x=to_np(x), w=w, knots=knots, chebyshev=to_np(cheb(x)), piecewise=to_np(pwl(x)),
+                       log_temp_baseline=to_np(lt_base(x)), field_baseline=to_np(h_base(x)), composed=to_np(composed(x)),
+                       x25=to_np(x25), change_domain=to_np(moved(x25)),
+                       constant=to_np(ref_p10n.Constant(jnp.array(0.7))(x))))
+
+
 if __name__ == '__main__':
-  for prefix, cases in (('reference_langevin', langevin_cases()), ('reference_ising', ising_cases())):
+  for prefix, cases in (('reference_langevin', langevin_cases()), ('reference_ising', ising_cases()),
+                        ('reference_schedules', schedule_cases())):
     flat = {f'{k}/{f}': v for k, d in cases.items() for f, v in d.items()}
     np.savez_compressed(os.path.join(HERE, prefix + '.npz'), **flat)
     print(prefix, {k: {f: np.shape(v) for f, v in d.items()} for k, d in cases.items()})

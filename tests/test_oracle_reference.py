@@ -79,3 +79,36 @@ def test_ising_oracle_reproduces_the_reference_source(name):
       cf = I.closed_form_gradient(loss, so[0](times), so[1](times), so[0].jacobian(times), so[1].jacobian(times),
                                   c['spins0'], c['seeds'][r])
       assert rel(cf['grad'][0], c[key][r, 0]) < 2e-5 and rel(cf['grad'][1], c[key][r, 1]) < 2e-5, (loss, r)
+
+
+@pytest.mark.parametrize('name', ['spring', 'shifted'])
+def test_langevin_estimator_variants_and_eqm_prepass(name):
+  """estimate_gradient_boltzinit_logP / _reparam (barrier_crossing.py:262-311) and mapped_brownian_eqm
+  (:249-256, which hard-codes dt = 1e-6, kT = 1e-5, mass = gamma = 1 whatever it is given)."""
+  c = case('reference_langevin.npz', name)
+  pot = L.V_spring(1.0) if name == 'spring' else L.V_biomolecule_shifted(KAPPA, KAPPA, XM, 0., 1.5, BETA)
+  B = c['positions'].shape[0]
+  o = L.estimate_gradient(pot, c['coeffs'], np.full(B, c['x0'], np.float32), c['seed'], float(c['r0'][0]), float(c['r0'][1]),
+                          int(c['Neq']), int(c['S']), float(c['dt']), float(c['kT']), float(c['mass']), float(c['gamma']))
+  assert rel(o['grad_logP'], c['grad_logP']) < 1e-5 and rel(o['grad_reparam'], c['grad_reparam']) < 1e-5
+  assert rel(o['grad_logP'] + o['grad_reparam'], c['grad']) < 1e-5
+  xs = L.mapped_brownian_eqm(pot, B, float(c['x0']), float(c['r0'][0]), J.PRNGKey(5), 40, 1e-6, 1e-5, 1.0, 1.0)
+  assert np.abs(xs - c['eqm'][:, 0, 0]).max() < 1e-6 * max(1.0, np.abs(c['eqm']).max())
+
+
+def test_protocol_algebra_matches_the_reference_source():
+  """parameterization.py:67-179, 268-344 and the baselines of ising.py:45-55, for the oracle and for the
+  product's host-side classes."""
+  from noneq_opt_b200 import ising as nq_ising, parameterization as p10n
+  c = case('reference_schedules.npz', 'all')
+  x, x25 = c['x'], c['x25']
+  for mod, lt_base, h_base in ((P, P.log_temp_baseline(0.69, 10., 1), P.field_baseline(-1., 1.)),
+                               (p10n, nq_ising.log_temp_baseline(0.69, 10., 1), nq_ising.field_baseline(-1., 1.))):
+    cheb = mod.Chebyshev(c['w'])
+    np.testing.assert_allclose(cheb(x), c['chebyshev'], atol=2e-7)
+    np.testing.assert_allclose(mod.PiecewiseLinear(c['knots'], 0., 1., -1., 2.)(x), c['piecewise'], atol=3e-7)
+    np.testing.assert_allclose(lt_base(x), c['log_temp_baseline'], atol=3e-7)
+    np.testing.assert_allclose(h_base(x), c['field_baseline'], atol=1e-7)
+    np.testing.assert_allclose(mod.AddBaseline(mod.ConstrainEndpoints(cheb, 0., 0.), lt_base)(x), c['composed'], atol=3e-7)
+    np.testing.assert_allclose(mod.ChangeDomain(cheb, 2., 5.)(x25), c['change_domain'], atol=2e-7)
+    np.testing.assert_allclose(mod.Constant(np.float32(0.7))(x), c['constant'], atol=0)
