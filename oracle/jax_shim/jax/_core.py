@@ -5,6 +5,18 @@ import numpy as np
 import torch
 
 torch.set_grad_enabled(True)
+torch.set_flush_denormal(True)   # XLA:CPU runs with denormals flushed to zero (ising_test.py:36 expects exp(-100) == 0)
+
+
+class _Size(int):
+  """`x.size` is an int for jax arrays and a method for torch tensors: be both."""
+  def __new__(cls, tensor):
+    obj = int.__new__(cls, tensor.numel())
+    obj._tensor = tensor
+    return obj
+
+  def __call__(self, *a, **k):
+    return torch.Tensor.size(self._tensor, *a, **k)
 
 
 class Array(torch.Tensor):
@@ -21,6 +33,10 @@ class Array(torch.Tensor):
 
   def astype(self, dtype):
     return self.to(_torch_dtype(dtype))
+
+  @property
+  def size(self):
+    return _Size(self)
 
   @property
   def at(self):
@@ -137,11 +153,11 @@ def checkpoint(fun=None, **unused):
   return jit(fun)
 
 
-def _stack(items):
+def _stack(items, axis=0):
   first = items[0]
   if isinstance(first, np.ndarray):
-    return np.stack(items)
-  return torch.stack([asarray(i) for i in items]).as_subclass(Array)
+    return np.stack(items, axis)
+  return torch.stack([asarray(i) for i in items], dim=axis).as_subclass(Array)
 
 
 def vmap(fun, in_axes=0, out_axes=0):
@@ -159,7 +175,7 @@ def vmap(fun, in_axes=0, out_axes=0):
       outs.append(fun(*call))
     leaves0, treedef = tree_flatten(outs[0])
     cols = [[tree_flatten(o)[0][j] for o in outs] for j in range(len(leaves0))]
-    return tree_unflatten(treedef, [_stack(c) for c in cols])
+    return tree_unflatten(treedef, [_stack(c, out_axes) for c in cols])
   return mapped
 
 
@@ -172,17 +188,29 @@ def _require_grad(leaf):
   return t.detach().clone().requires_grad_(True).as_subclass(Array)
 
 
+_DEPTH = [0]   # nesting of value_and_grad calls: inner ones keep their graph for the outer one
+
+
+def _detach_tree(x):
+  return tree_map(lambda l: l.detach().as_subclass(Array) if isinstance(l, torch.Tensor) else l, x)
+
+
 def value_and_grad(fun, argnums=0, has_aux=False):
   def wrapped(*args, **kwargs):
     args = list(args)
     leaves, treedef = tree_flatten(args[argnums])
     leaves = [_require_grad(l) for l in leaves]
     args[argnums] = tree_unflatten(treedef, leaves)
-    out = fun(*args, **kwargs)
+    outermost = _DEPTH[0] == 0
+    _DEPTH[0] += 1
+    try:
+      out = fun(*args, **kwargs)
+    finally:
+      _DEPTH[0] -= 1
     value, aux = out if has_aux else (out, None)
     diff = [l for l in leaves if l.is_floating_point()]
     if isinstance(value, torch.Tensor) and value.requires_grad:
-      grads = torch.autograd.grad(value, diff, create_graph=True, allow_unused=True)
+      grads = torch.autograd.grad(value, diff, create_graph=not outermost, allow_unused=True)
     else:
       grads = [None] * len(diff)
     it = iter(grads)
@@ -191,6 +219,8 @@ def value_and_grad(fun, argnums=0, has_aux=False):
       g = next(it) if l.is_floating_point() else None
       full.append((torch.zeros_like(l) if g is None else g).as_subclass(Array))
     grad_tree = tree_unflatten(treedef, full)
+    if outermost:
+      value, aux, grad_tree = _detach_tree(value), _detach_tree(aux), _detach_tree(grad_tree)
     return ((value, aux), grad_tree) if has_aux else (value, grad_tree)
   return wrapped
 
@@ -202,6 +232,36 @@ def grad(fun, argnums=0, has_aux=False):
     (value, g) = vg(*args, **kwargs)
     return (g, value[1]) if has_aux else g
   return wrapped
+
+
+def jvp(fun, primals, tangents):
+  """Forward-mode derivative along `tangents` (pytrees like `primals`): torch forward AD on the leaves."""
+  import torch.autograd.forward_ad as fwad
+  with fwad.dual_level():
+    duals = []
+    for p, t in zip(primals, tangents):
+      pl, treedef = tree_flatten(p)
+      tl = tree_leaves(t)
+      dl = []
+      for a, b in zip(pl, tl):
+        a = asarray(a)
+        if a.is_floating_point():
+          dl.append(fwad.make_dual(a.detach(), asarray(b).to(a.dtype).reshape(a.shape)).as_subclass(Array))
+        else:
+          dl.append(a)
+      duals.append(tree_unflatten(treedef, dl))
+    out = fun(*duals)
+    leaves, outdef = tree_flatten(out)
+    prim, tang = [], []
+    for l in leaves:
+      if isinstance(l, torch.Tensor):
+        u = fwad.unpack_dual(l)
+        prim.append(u.primal.detach().as_subclass(Array))
+        tang.append((torch.zeros_like(u.primal) if u.tangent is None else u.tangent.detach()).as_subclass(Array))
+      else:
+        prim.append(l)
+        tang.append(l)
+    return tree_unflatten(outdef, prim), tree_unflatten(outdef, tang)
 
 
 def stop_gradient(x):

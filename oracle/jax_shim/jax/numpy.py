@@ -150,3 +150,23 @@ def interp(x, xp, fp, left=None, right=None):
 
 def float64(x):
   return asarray(x, _np.float32)   # x64 is disabled: jnp.float64(x) yields a float32
+
+
+sin, cos = _unary(_torch.sin), _unary(_torch.cos)
+
+
+def add(a, b):
+  return _w(asarray(a) + asarray(b))
+
+
+def multiply(a, b):
+  return _w(asarray(a) * asarray(b))
+
+
+def cumsum(x, axis=None):
+  t = asarray(x)
+  return _w(_torch.cumsum(t.reshape(-1) if axis is None else t, 0 if axis is None else axis))
+
+
+def allclose(a, b, rtol=1e-5, atol=1e-8):
+  return bool(_torch.allclose(asarray(a).to(_torch.float32), asarray(b).to(_torch.float32), rtol=rtol, atol=atol))
