@@ -44,11 +44,6 @@ int make_langevin_consts(const NqLangevinDesc* d, LangevinConsts* c) {
   c->box = (float)d->box;
   c->ca = (float)((double)nu * (double)c->dt * (double)c->k_s / (double)c->sigma);
   c->nudt = (float)((double)nu * (double)c->dt);
-  c->one = 1u;
-  {
-    const int R[8] = {13, 15, 26, 6, 17, 29, 16, 24};
-    for (int j = 0; j < 8; ++j) c->pow2[j] = 1u << R[j];
-  }
   {
     const double log2e = 1.4426950408889634, nudt = (double)nu * (double)c->dt;
     const double ib = d->potential == NQ_POT_SPRING ? 0.0 : 1.0 / d->beta;

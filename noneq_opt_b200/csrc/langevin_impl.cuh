@@ -19,9 +19,6 @@
 #pragma once
 #include <math.h>
 
-#ifndef NQ_TF_FORCE_IMAD
-#define NQ_TF_FORCE_IMAD 0
-#endif
 #ifndef NQ_FAST_EXP   // precision-study toggles of the FAST path (scripts/precision_study.py)
 #define NQ_FAST_EXP 0
 #endif
@@ -30,9 +27,6 @@
 #endif
 #ifndef NQ_FAST_NORMAL
 #define NQ_FAST_NORMAL 0
-#endif
-#ifndef NQ_TF_WIDE_MASK
-#define NQ_TF_WIDE_MASK 0
 #endif
 
 #include "nq_common.cuh"
@@ -54,8 +48,6 @@ struct LangevinConsts {
   float nu, dt, sigma, inv_sigma, log_norm, box;
   float ca;     // nu*dt*k_s/sigma : d logp_k / d r_k = z_k * ca
   float nudt;   // nu*dt (fast mode only)
-  uint32_t pow2[8];  // 2^{13,15,26,6,17,29,16,24}: run-time multipliers for the IMAD.WIDE rotates
-  uint32_t one;  // = 1 at run time: a multiplier ptxas cannot fold, used to place integer adds on the FMA pipe
   // FAST-math constants (see fast_mean): log2(e)-scaled exponents, (nu dt / beta)-scaled force terms
   float f_cl2, f_ncr2, f_nbde2, f_clm, f_crm, f_cu;
   long long S, Neq;
@@ -159,24 +151,10 @@ struct RngPipe {
   // state.rng -> pipeline (performs the split of the first step)
   __device__ __forceinline__ void prime(uint32_t r0, uint32_t r1) { split2(r0, r1, k0, k1, s0, s1); }
   // bits for this step's normal draw; advances the chain by one step
-  __device__ __forceinline__ uint32_t next(uint32_t one = 1u, const uint32_t* pow2 = nullptr) {
-    (void)pow2;
+  __device__ __forceinline__ uint32_t next() {
     uint32_t bits, unused, n0, n1, t0, t1;
-#if NQ_TF_WIDE_MASK
-    threefry2x32_wide<NQ_TF_WIDE_MASK>(key_schedule(s0, s1), 0u, 0u, bits, unused, pow2);
-    const KeySchedule ks = key_schedule(k0, k1);
-    threefry2x32_wide<NQ_TF_WIDE_MASK>(ks, 0u, 2u, n0, t0, pow2);
-    threefry2x32_wide<NQ_TF_WIDE_MASK>(ks, 1u, 3u, n1, t1, pow2);
-#elif NQ_TF_FORCE_IMAD
-    threefry2x32_mad(key_schedule(s0, s1), 0u, 0u, bits, unused, one);
-    const KeySchedule ks = key_schedule(k0, k1);
-    threefry2x32_mad(ks, 0u, 2u, n0, t0, one);
-    threefry2x32_mad(ks, 1u, 3u, n1, t1, one);
-#else
-    (void)one;
     threefry2x32(key_schedule(s0, s1), 0u, 0u, bits, unused);  // normal(split, [1,1,1]) :88
     split2(k0, k1, n0, n1, t0, t1);                            // key, split = split(state.rng) of the NEXT step :79
-#endif
     k0 = n0; k1 = n1; s0 = t0; s1 = t1;
     return bits;
   }
@@ -313,8 +291,12 @@ __device__ __forceinline__ float fast_step_z(const LangevinConsts& c, float& x, 
 
 template <int POT>
 __device__ __forceinline__ float fast_step(const LangevinConsts& c, float& x, uint32_t bits, float r, float& z) {
+  const float mean = fast_mean<POT>(c, x, r);   // (this statement order gives the better ptxas schedule)
   z = fast_normal(bits);
-  return fast_step_z<POT>(c, x, z, r);
+  const float dR = fmaf(z, c.sigma, mean);
+  x += dR;
+  if (c.shift_kind == NQ_SHIFT_PERIODIC) x = py_mod(x, c.box);
+  return dR;
 }
 
 // ------------------------------------------------------------------------------ main kernel
@@ -444,13 +426,13 @@ __device__ __forceinline__ void langevin_chunk(const LangevinConsts& c, const La
       if (FAST) {
         const float4 tab = lds_f32x4(tab_addr);
         dW = fmaf(tab.y, x, tab.z);
-        dR = fast_step<POT>(c, x, rng.next(c.one, c.pow2), tab.x, z);
+        dR = fast_step<POT>(c, x, rng.next(), tab.x, z);
         if (RECORD) lp = fmaf(-0.5f * z, z, -c.log_norm);
       } else {
         const float r_prev = lds_f32(r_addr), r_cur = lds_f32(r_addr + 4);
         land.eval(c, x);
         dW = work_increment<POT, FAST>(c, land, x, r_prev, r_cur);
-        dR = brownian_apply<POT, FAST>(c, land, x, rng.next(c.one, c.pow2), r_cur, z, lp);
+        dR = brownian_apply<POT, FAST>(c, land, x, rng.next(), r_cur, z, lp);
       }
       Wt += dW;
       if (FAST && !RECORD) {
@@ -612,7 +594,7 @@ __global__ void __launch_bounds__(kPairThreads) langevin_pair_kernel(const Lange
       if (ch >= 2) named_bar_sync(kEmpty + h, kPairThreads);   // the consumer is done with this half
       const int len = (int)min((long long)kRingHalf, total - ch * kRingHalf);
       for (int i = 0; i < len; ++i) {
-        const uint32_t bits = rng.next(c.one, c.pow2);
+        const uint32_t bits = rng.next();
         ring_s[h][i][lane] = FAST ? fast_normal(bits) : normal_from_bits<false>(bits);
       }
       __threadfence_block();
