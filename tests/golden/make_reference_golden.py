@@ -44,7 +44,16 @@ def langevin_cases():
                       coeffs=np.array([20., 19.95996, 0.3, -0.2, 0.1] + [0.] * 8, np.float32),
                       r0=(0., 40.), x0=0.0, Neq=0, S=400, dt=1e-8, kT=kT, mass=1.0, gamma=kT / 1e7),
   }
+  # V_biomolecule (wells at -x_m, +x_m) in a periodic box, with equilibration steps
+  cases['biomolecule_periodic'] = dict(energy=ref_bc.V_biomolecule(kappa, kappa, x_m / 2, 0.5, 1.5, beta),
+                                       coeffs=np.array([10., 9.5, 0.4, -0.3] + [0.] * 3, np.float32),
+                                       r0=(-7., 7.), x0=-7.0, Neq=10, S=300, dt=2e-8, kT=kT, mass=1.0, gamma=kT / 1e7,
+                                       box=45.0)
   for name, c in cases.items():
+    if 'box' in c:
+      _, shift = space.periodic(c['box'])
+    else:
+      _, shift = space.free()
     B = 6
     coeffs = jnp.array(np.asarray(c['coeffs'], np.float32))
     init_pos = jnp.array(np.full((B, 1, 1), c['x0'], np.float32))
@@ -66,7 +75,7 @@ def langevin_cases():
                                                           c['dt'], c['kT'], c['mass'], c['gamma'])(coeffs, init_pos, seed)
     eqm = ref_bc.mapped_brownian_eqm(B, c['energy'], init_pos[0], c['r0'][0], shift, 40, c['dt'], c['kT'], c['mass'],
                                      c['gamma'])(jax.random.PRNGKey(5))
-    out[name] = dict(grad_logP=to_np(g_logp), grad_reparam=to_np(g_rep), eqm=to_np(eqm),
+    out[name] = dict(grad_logP=to_np(g_logp), grad_reparam=to_np(g_rep), eqm=to_np(eqm), box=np.float32(c.get('box', 0.)),
                      coeffs=np.asarray(c['coeffs'], np.float32), r0=np.array(c['r0'], np.float32), x0=np.float32(c['x0']),
                      Neq=c['Neq'], S=c['S'], dt=c['dt'], kT=c['kT'], mass=c['mass'], gamma=c['gamma'], seed=np.asarray(seed),
                      positions=np.stack(pos), log_probs=np.stack(lps), works=np.stack(works),

@@ -28,14 +28,16 @@ def rel(a, b):
   return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max() / np.abs(b).max())
 
 
-@pytest.mark.parametrize('name', ['spring', 'shifted'])
+@pytest.mark.parametrize('name', ['spring', 'shifted', 'biomolecule_periodic'])
 def test_langevin_oracle_reproduces_the_reference_source(name):
   c = case('reference_langevin.npz', name)
-  pot = L.V_spring(1.0) if name == 'spring' else L.V_biomolecule_shifted(KAPPA, KAPPA, XM, 0., 1.5, BETA)
+  pot = {'spring': L.V_spring(1.0), 'shifted': L.V_biomolecule_shifted(KAPPA, KAPPA, XM, 0., 1.5, BETA),
+         'biomolecule_periodic': L.V_biomolecule(KAPPA, KAPPA, XM / 2, 0.5, 1.5, BETA)}[name]
+  shift = ('periodic', float(c['box'])) if float(c['box']) > 0 else 'free'
   B = c['positions'].shape[0]
   o = L.estimate_gradient(pot, c['coeffs'], np.full(B, c['x0'], np.float32), c['seed'], float(c['r0'][0]), float(c['r0'][1]),
                           int(c['Neq']), int(c['S']), float(c['dt']), float(c['kT']), float(c['mass']), float(c['gamma']),
-                          record=True)
+                          shift=shift, record=True)
   # run_brownian_opt (barrier_crossing.py:97-143), one call per row of split(seed, B)
   assert rel(o['traj']['positions'], c['positions'][:, :, 0, 0]) < 1e-6
   assert rel(o['traj']['log_probs'], c['log_probs']) < 1e-6
@@ -81,18 +83,23 @@ def test_ising_oracle_reproduces_the_reference_source(name):
       assert rel(cf['grad'][0], c[key][r, 0]) < 2e-5 and rel(cf['grad'][1], c[key][r, 1]) < 2e-5, (loss, r)
 
 
-@pytest.mark.parametrize('name', ['spring', 'shifted'])
+@pytest.mark.parametrize('name', ['spring', 'shifted', 'biomolecule_periodic'])
 def test_langevin_estimator_variants_and_eqm_prepass(name):
   """estimate_gradient_boltzinit_logP / _reparam (barrier_crossing.py:262-311) and mapped_brownian_eqm
   (:249-256, which hard-codes dt = 1e-6, kT = 1e-5, mass = gamma = 1 whatever it is given)."""
   c = case('reference_langevin.npz', name)
-  pot = L.V_spring(1.0) if name == 'spring' else L.V_biomolecule_shifted(KAPPA, KAPPA, XM, 0., 1.5, BETA)
+  pot = {'spring': L.V_spring(1.0), 'shifted': L.V_biomolecule_shifted(KAPPA, KAPPA, XM, 0., 1.5, BETA),
+         'biomolecule_periodic': L.V_biomolecule(KAPPA, KAPPA, XM / 2, 0.5, 1.5, BETA)}[name]
+  shift = ('periodic', float(c['box'])) if float(c['box']) > 0 else 'free'
   B = c['positions'].shape[0]
   o = L.estimate_gradient(pot, c['coeffs'], np.full(B, c['x0'], np.float32), c['seed'], float(c['r0'][0]), float(c['r0'][1]),
-                          int(c['Neq']), int(c['S']), float(c['dt']), float(c['kT']), float(c['mass']), float(c['gamma']))
+                          int(c['Neq']), int(c['S']), float(c['dt']), float(c['kT']), float(c['mass']), float(c['gamma']), shift=shift,
+                          record=True)
   assert rel(o['grad_logP'], c['grad_logP']) < 1e-5 and rel(o['grad_reparam'], c['grad_reparam']) < 1e-5
   assert rel(o['grad_logP'] + o['grad_reparam'], c['grad']) < 1e-5
-  xs = L.mapped_brownian_eqm(pot, B, float(c['x0']), float(c['r0'][0]), J.PRNGKey(5), 40, 1e-6, 1e-5, 1.0, 1.0)
+  _, rng0 = L.trajectory_keys(J.PRNGKey(5), B)
+  xs = L.run_brownian_stationary_trap(pot, np.full(B, c['x0'], np.float32), float(c['r0'][0]), rng0, 40, 1e-6, 1e-5, 1.0, 1.0,
+                                      shift)
   assert np.abs(xs - c['eqm'][:, 0, 0]).max() < 1e-6 * max(1.0, np.abs(c['eqm']).max())
 
 
