@@ -86,25 +86,29 @@ def langevin_cases():
 
 def ising_cases():
   out = {}
-  for name, L, T, R in (('small', 16, 12, 3), ('fastpath', 64, 5, 2)):
+  for name, shape, T, R in (('small', (16, 16), 12, 3), ('fastpath', (64, 64), 5, 2), ('chain', (48,), 7, 2),
+                            ('cube', (4, 6, 8), 6, 2)):
+    L = shape[0]
     w_lt = np.array([0.3, -0.2, 0.1], np.float32)
     w_h = np.array([-0.4, 0.6, 0.2], np.float32)
     schedule = ref_ising.IsingSchedule(ref_p10n.Chebyshev(jnp.array(w_lt)), ref_p10n.Chebyshev(jnp.array(w_h)))
     times = jnp.linspace(0, 1, T)
     params = schedule(times)
-    spins0 = ref_ising.random_spins((L, L), 0.5, jax.random.PRNGKey(11))
+    spins0 = ref_ising.random_spins(shape, 0.5, jax.random.PRNGKey(11))
     seeds = jax.random.split(jax.random.PRNGKey(7), R)
     finals, summaries, grads = [], [], {'total_entropy_production': [], 'total_work': []}
+    states = []
     for r in range(R):
-      final_state, summary = ref_ising.simulate_ising(params, spins0, seeds[r])
+      final_state, (summary, traj) = ref_ising.simulate_ising(params, spins0, seeds[r], return_states=True)
       finals.append(to_np(final_state.spins))
+      states.append(to_np(traj.spins))
       summaries.append(np.stack([to_np(getattr(summary, f)) for f in summary._fields]))
       for loss in grads:
         g, _ = ref_ising.estimate_gradient_rev(getattr(ref_ising, loss))(schedule, times, spins0, seeds[r])
         grads[loss].append(np.stack([to_np(g.log_temp.weights), to_np(g.field.weights)]))
     out[name] = dict(L=L, T=T, w_lt=w_lt, w_h=w_h, times=to_np(times), log_temp=to_np(params.log_temp),
                      field=to_np(params.field), spins0=to_np(spins0), seeds=np.asarray(seeds),
-                     final_spins=np.stack(finals), summary=np.stack(summaries),
+                     final_spins=np.stack(finals), states=np.stack(states), summary=np.stack(summaries),
                      grad_entropy=np.stack(grads['total_entropy_production']), grad_work=np.stack(grads['total_work']),
                      summary_fields=np.array(list(ref_ising.IsingSummary._fields)))
   return out

@@ -53,7 +53,7 @@ def test_langevin_oracle_reproduces_the_reference_source(name):
   assert rel(o['tot_log_prob'] * o['total_work'] + o['total_work'], c['estimator']) < 1e-6
 
 
-@pytest.mark.parametrize('name', ['small', 'fastpath'])
+@pytest.mark.parametrize('name', ['small', 'fastpath', 'chain', 'cube'])
 def test_ising_oracle_reproduces_the_reference_source(name):
   c = case('reference_ising.npz', name)
   T, shape = int(c['T']), c['spins0'].shape
@@ -67,8 +67,9 @@ def test_ising_oracle_reproduces_the_reference_source(name):
   fields = [str(f) for f in c['summary_fields']]
   n = float(np.prod(shape))
   for r in range(c['seeds'].shape[0]):
-    fin, summ = I.simulate_ising(c['log_temp'], c['field'], c['spins0'], c['seeds'][r])
-    np.testing.assert_array_equal(fin, c['final_spins'][r])          # spin history bit-exact
+    fin, summ, states = I.simulate_ising(c['log_temp'], c['field'], c['spins0'], c['seeds'][r], return_states=True)
+    np.testing.assert_array_equal(fin, c['final_spins'][r])          # spin history bit-exact, sweep by sweep
+    np.testing.assert_array_equal(states, c['states'][r])
     for i, f in enumerate(fields):
       got, want = getattr(summ, f), c['summary'][r, i]
       if f == 'magnetization':
