@@ -114,6 +114,30 @@ def ising_cases():
   return out
 
 
+def train_step_case():
+  """ising.get_train_step (:263-290) driven for three steps: batch split, vmapped reverse-mode estimator,
+  batch mean, clip_grads, Adam.  (Adam itself comes from the shim's restatement of
+  jax.example_libraries.optimizers; the step glue is the reference's.)"""
+  from jax.example_libraries import optimizers as jopt
+  w_lt, w_h = np.array([0.3, -0.2, 0.1], np.float32), np.array([-0.4, 0.6, 0.2], np.float32)
+  schedule = ref_ising.IsingSchedule(ref_p10n.Chebyshev(jnp.array(w_lt)), ref_p10n.Chebyshev(jnp.array(w_h)))
+  spins0 = -jnp.ones([16, 16])
+  B, T, lr = 5, 7, 1e-2
+  opt = jopt.adam(lr)
+  state = opt.init_fn(schedule)
+  step_fn = ref_ising.get_train_step(opt, spins0, B, T, ref_ising.total_entropy_production, 'rev')
+  key = jax.random.PRNGKey(21)
+  hist, ep = [], []
+  for j in range(3):
+    key, split = jax.random.split(key)
+    state, summary = step_fn(state, j, split)
+    p = opt.params_fn(state)
+    hist.append(np.stack([to_np(p.log_temp.weights), to_np(p.field.weights)]))
+    ep.append(to_np(summary.entropy_production))
+  return dict(train=dict(w_lt=w_lt, w_h=w_h, B=B, T=T, lr=lr, seed=np.asarray(jax.random.PRNGKey(21)),
+                         weights=np.stack(hist), entropy_production=np.stack(ep)))
+
+
 def schedule_cases():
   """The protocol algebra of parameterization.py and the baselines of ising.py:45-55, evaluated by the reference."""
   x = jnp.linspace(0, 1, 33)
@@ -134,7 +158,7 @@ def schedule_cases():
 
 if __name__ == '__main__':
   for prefix, cases in (('reference_langevin', langevin_cases()), ('reference_ising', ising_cases()),
-                        ('reference_schedules', schedule_cases())):
+                        ('reference_schedules', schedule_cases()), ('reference_train_step', train_step_case())):
     flat = {f'{k}/{f}': v for k, d in cases.items() for f, v in d.items()}
     np.savez_compressed(os.path.join(HERE, prefix + '.npz'), **flat)
     print(prefix, {k: {f: np.shape(v) for f, v in d.items()} for k, d in cases.items()})
