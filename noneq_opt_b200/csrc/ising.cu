@@ -29,8 +29,14 @@
 
 namespace nq {
 
+#ifndef NQ_ISING_TEAMS     // warp teams (replicas) per CTA of the warp-team kernel
+#define NQ_ISING_TEAMS 4
+#endif
+#ifndef NQ_ISING_SYNC      // 1: the teams of a CTA start every sweep together (one barrier per sweep)
+#define NQ_ISING_SYNC 1
+#endif
 #ifndef NQ_ISING_MINB
-#define NQ_ISING_MINB 4
+#define NQ_ISING_MINB (NQ_ISING_TEAMS == 4 ? 4 : 1)
 #endif
 #ifndef NQ_ISING_BLOCKS_PER_ITER
 #define NQ_ISING_BLOCKS_PER_ITER 8
@@ -342,7 +348,7 @@ __device__ __forceinline__ void sweep_keys(const KeySchedule& ks_rep, int t, int
 // GLOBAL_LAT: the colour planes of a replica live in global memory (L2-resident) instead of shared
 // memory -- same code, for lattices whose 2 x L x L/64 words exceed 227 KB (L >= 2048).
 template <bool WARP_TEAM, bool GLOBAL_LAT = false, bool SEG = false>
-__global__ void __launch_bounds__(WARP_TEAM ? 128 : 1024, WARP_TEAM ? NQ_ISING_MINB : 1) ising_fast_kernel(const IsingShape sh, const IsingIO io) {
+__global__ void __launch_bounds__(WARP_TEAM ? 32 * NQ_ISING_TEAMS : 1024, WARP_TEAM ? NQ_ISING_MINB : 1) ising_fast_kernel(const IsingShape sh, const IsingIO io) {
   static_assert(!SEG || (!WARP_TEAM && !GLOBAL_LAT), "segments are scheduled per CTA with the lattice in shared memory");
   extern __shared__ uint32_t smem[];
   uint32_t* spread = smem;
@@ -461,6 +467,9 @@ __global__ void __launch_bounds__(WARP_TEAM ? 128 : 1024, WARP_TEAM ? NQ_ISING_M
   const KeySchedule ks_rep = key_schedule(io.seeds[2 * rep], io.seeds[2 * rep + 1]);
   const int units = (L / 2) * NW;
   for (int t = t_first; t < t_end; ++t) {
+#if NQ_ISING_SYNC
+    if (WARP_TEAM) __syncthreads();   // keep the teams of a CTA in phase: they then run the same code (i-cache)
+#endif
     KeySchedule kh[2];
     sweep_keys(ks_rep, t, T, sh.direct_keys != 0, kh[0], kh[1]);
     const uint2* thr_cur = thr_s + (t & 1) * 256;
@@ -965,7 +974,7 @@ extern "C" size_t nq_ising_workspace_bytes(const NqIsingDesc* desc) {
   const int ndim = lattice_dims(desc, dims);
   const long long N = (long long)dims[0] * dims[1] * dims[2];
   if (ndim == 2 && dims[0] == dims[1] && fast_path(dims[0])) {
-    if (fast_smem_bytes(dims[0], dims[0] <= 128, dims[0] <= 128 ? 4 : 1) <= 227 * 1024)
+    if (fast_smem_bytes(dims[0], dims[0] <= 128, dims[0] <= 128 ? NQ_ISING_TEAMS : 1) <= 227 * 1024)
       return plan_segments(dims[0], desc->R, desc->T).bytes();  // optional: without it the run is unsegmented
     return (size_t)desc->R * 2 * dims[0] * (dims[0] / 64) * 4;   // colour planes in global memory
   }
@@ -1002,7 +1011,7 @@ extern "C" int nq_ising_run(const NqIsingDesc* desc, const uint32_t* thr, const 
   cudaStream_t st = (cudaStream_t)stream;
   const bool square2d = ndim == 2 && dims[0] == dims[1];
   const bool warp_team = L <= 128;
-  const int nteams = warp_team ? 4 : 1;
+  const int nteams = warp_team ? NQ_ISING_TEAMS : 1;
   if (square2d && fast_path(L)) {
     const int units = (L / 2) * (L / 64);
     const int threads = warp_team ? 32 * nteams : (units >= 1024 ? 1024 : ((units + 31) / 32) * 32);
