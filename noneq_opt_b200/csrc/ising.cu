@@ -474,9 +474,13 @@ __global__ void __launch_bounds__(WARP_TEAM ? 32 * NQ_ISING_TEAMS : 1024, WARP_T
     sweep_keys(ks_rep, t, T, sh.direct_keys != 0, kh[0], kh[1]);
     const uint2* thr_cur = thr_s + (t & 1) * 256;
     if (t + 1 < t_end) build_pair_table(thr_s + ((t + 1) & 1) * 256, io.thr + (size_t)t * kIsingClasses, tid, tsize);
-    int At[2][10], Ft[2][10];
-#pragma unroll
+    // warp teams share ONE copy of the half-sweep code between the colours (their phases differ, so the
+    // smaller footprint matters to the instruction cache: +1.6 %); the CTA team runs in lock step and is
+    // faster with the two colours unrolled (+2.5 %)
+    constexpr int kColourUnroll = WARP_TEAM ? 1 : 2;
+#pragma unroll kColourUnroll
     for (int c = 0; c < 2; ++c) {
+      int At[10], Ft[10];
       int hA[10], hF[10];
 #pragma unroll
       for (int k = 0; k < 10; ++k) hA[k] = hF[k] = 0;
@@ -486,19 +490,19 @@ __global__ void __launch_bounds__(WARP_TEAM ? 32 * NQ_ISING_TEAMS : 1024, WARP_T
       }
 #pragma unroll
       for (int k = 0; k < 10; ++k) {
-        At[c][k] = __reduce_add_sync(0xffffffffu, hA[k]);
-        Ft[c][k] = __reduce_add_sync(0xffffffffu, hF[k]);
+        At[k] = __reduce_add_sync(0xffffffffu, hA[k]);
+        Ft[k] = __reduce_add_sync(0xffffffffu, hF[k]);
       }
       if (lane == 0) {
         int* hs = hist_s + ((t & 1) * 2 + c) * 2 * kIsingClasses;
 #pragma unroll
         for (int k = 0; k < 10; ++k) {
           if (WARP_TEAM) {
-            hs[k] = At[c][k];
-            hs[kIsingClasses + k] = Ft[c][k];
+            hs[k] = At[k];
+            hs[kIsingClasses + k] = Ft[k];
           } else {
-            if (At[c][k]) atomicAdd(&hs[k], At[c][k]);
-            if (Ft[c][k]) atomicAdd(&hs[kIsingClasses + k], Ft[c][k]);
+            if (At[k]) atomicAdd(&hs[k], At[k]);
+            if (Ft[k]) atomicAdd(&hs[kIsingClasses + k], Ft[k]);
           }
         }
       }
