@@ -359,7 +359,7 @@ def bench_config1_training(dev):
   coeffs0 = bc.fit_linear_to_cheby(1.0, dt, 5., 10., 12)
   key = np.array([0, 7], np.uint32)
   opt = optimizers.adam(optimizers.exponential_decay(0.1, n, 0.001))
-  grad_fn = bc.estimate_gradient_boltzinit(B, energy, 5., 10., Neq, shift, S, dt, 1.0, 1.0, 1.0)
+  grad_fn = bc.estimate_gradient_boltzinit(B, energy, 5., 10., Neq, shift, S, dt, 1.0, 1.0, 1.0, record_positions=False)
   x0 = np.full((B, 1, 1), 5., np.float32)
 
   def host_loop(k, steps):

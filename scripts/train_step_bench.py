@@ -17,7 +17,7 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 def host_loop(n):
   opt = optimizers.adam(optimizers.exponential_decay(0.1, N, 0.001))
   state = opt.init_fn(coeffs0)
-  grad_fn = bc.estimate_gradient_boltzinit(B, energy, 5., 10., Neq, shift, S, dt, 1.0, 1.0, 1.0)
+  grad_fn = bc.estimate_gradient_boltzinit(B, energy, 5., 10., Neq, shift, S, dt, 1.0, 1.0, 1.0, record_positions=False)
   k = key
   for j in range(n):
     k, k1, k2 = nqr.split_host(k, 3)
