@@ -84,13 +84,38 @@ __global__ void microbench_kernel(int iters, unsigned long long* out_cycles, uin
 
 using namespace nq;
 
+// which == 12: where the hardware places warps.  out[block] = smid | warp slot of warp 0 << 16 | warp slot of
+// warp 1 << 24 (warp slot % 4 = SM sub-partition); the kernel spins `iters` x 1000 cycles so that the whole grid is
+// resident at once, with the register footprint of the Langevin kernel (80 registers, 64-thread CTAs).
+__global__ void __launch_bounds__(128) placement_kernel(int iters, unsigned long long* out, uint32_t* sink) {
+  __shared__ unsigned slots[32];
+  unsigned smid, warpid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  asm volatile("mov.u32 %0, %%warpid;" : "=r"(warpid));
+  if ((threadIdx.x & 31) == 0) slots[threadIdx.x >> 5] = warpid;
+  __syncthreads();
+  const long long t0 = clock64();
+  while (clock64() - t0 < 1000ll * iters) { }
+  if (threadIdx.x == 0) {
+    unsigned long long v = smid;
+    for (unsigned w = 0; w < blockDim.x / 32 && w < 6; ++w) v |= (unsigned long long)(slots[w] & 0xff) << (16 + 8 * w);
+    out[blockIdx.x] = v;
+  }
+  if (iters < 0) sink[0] = smid;
+}
+
 extern "C" int nq_microbench(int32_t which, int32_t blocks, int32_t threads, int32_t iters, uint64_t* out_cycles,
                              uint32_t* sink, void* stream) {
-  NQ_CHECK_ARG(which >= 0 && which <= 11, "unknown microbenchmark %d", which);
+  NQ_CHECK_ARG(which >= 0 && which <= 12, "unknown microbenchmark %d", which);
   NQ_CHECK_ARG(blocks >= 1 && threads >= 32 && threads <= 1024 && iters >= 1 && out_cycles && sink, "bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long* oc = (unsigned long long*)out_cycles;
 #define NQ_MB(W) case W: microbench_kernel<W><<<blocks, threads, 0, st>>>(iters, oc, sink); break;
+  if (which == 12) {
+    placement_kernel<<<blocks, threads, 0, st>>>(iters, oc, sink);
+    NQ_LAUNCHED();
+    return NQ_OK;
+  }
   switch (which) {
     NQ_MB(0) NQ_MB(1) NQ_MB(2) NQ_MB(3) NQ_MB(4) NQ_MB(5) NQ_MB(6) NQ_MB(7) NQ_MB(8) NQ_MB(9) NQ_MB(10) NQ_MB(11)
   }
