@@ -100,16 +100,28 @@ static PotLaunchers launchers(int potential) {
 static int kernel_D(int D) { return D == 0 ? 0 : (D == 13 ? 13 : pad4(D)); }
 static int partial_row(int D) { return 8 + 2 * (D > 0 ? pad4(kernel_D(D)) : 4); }
 
-// Dynamic (persistent) scheduling pays when a static launch would leave SM sub-partitions unevenly
-// loaded for a long run: at least a few CTAs per SM and at least two chunks of steps.
-constexpr long long kChunkSteps = 512;
-static bool use_persistent(long long n, long long S, bool record) {
-  // Measured on B200 at config 2: 11.04 ms vs 11.17 ms for the static launch (+1 %), i.e. the
-  // load imbalance it removes is mostly eaten by the per-chunk hand-off.  Kept as an opt-in
-  // (NQ_PERSISTENT=1) and covered by tests; the static single-wave launch is the default.
+// Dynamic (persistent) scheduling: a fixed number of CTAs per SM pop (trajectory group, chunk of steps)
+// items from a FIFO ring, so that work flows to whichever SM is free (langevin_persistent_kernel).
+// Measured on B200: with 8 CTAs per SM (4 warps per sub-partition) and 128-step chunks
+// config 2 runs at 7.5e10 traj-steps/s against 6.75e10 for the one-wave static launch (STRICT); FAST
+// prefers 6 CTAs per SM and 256-step chunks (1.00e11 against 8.4e10).  The static launch stays better
+// for small ensembles (hand-off overhead in the latency-bound regime) and, in STRICT mode, for
+// ensembles of many waves (it keeps 12 CTAs per SM resident).  NQ_PERSISTENT = 0 / 1 forces the choice;
+// NQ_PERSISTENT_CHUNK and NQ_PERSISTENT_PER_SM override the two parameters.
+static long long chunk_steps(bool fast) {
+  const char* env = getenv("NQ_PERSISTENT_CHUNK");
+  const long long v = env ? atoll(env) : (fast ? 256 : 128);
+  return v < 128 ? 128 : v;
+}
+static long long persistent_ctas_per_sm(bool fast) {
+  const char* env = getenv("NQ_PERSISTENT_PER_SM");
+  return env ? atoll(env) : (fast ? 6 : 8);
+}
+static bool use_persistent(long long n, long long S, bool record, bool fast) {
+  if (record || S < 2 * chunk_steps(fast)) return false;
   const char* env = getenv("NQ_PERSISTENT");
-  const bool enabled = env != nullptr && env[0] == '1';
-  return enabled && !record && n >= 148ll * kThreads * 2 && S >= 2 * kChunkSteps;
+  if (env != nullptr) return env[0] == '1' && n >= 148ll * kThreads * 2;
+  return n > 40000 && (fast || n <= 160000);
 }
 static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
@@ -146,7 +158,8 @@ static int run(const NqLangevinDesc* desc, const LangevinIO& io_in, double* mome
   const bool record = io.positions || io.step_works || io.step_logps || io.ckpt_x;
   const bool pair = use_pair(io.n, record);
   const int blocks = (int)(pair ? (io.n + 31) / 32 : (io.n + kThreads - 1) / kThreads);
-  const bool persistent = !pair && use_persistent(io.n, c.S, record);
+  const long long kChunkSteps = chunk_steps(fast);
+  const bool persistent = !pair && use_persistent(io.n, c.S, record, fast);
   const size_t part_bytes = align256((size_t)blocks * NV * sizeof(double));
   const size_t ring_bytes = persistent ? align256((size_t)blocks * ((c.S + kChunkSteps - 1) / kChunkSteps) * 4) : 0;
   size_t need = part_bytes + (persistent ? persistent_bytes(io.n, io.D) : 0);
@@ -191,7 +204,7 @@ static int run(const NqLangevinDesc* desc, const LangevinIO& io_in, double* mome
     rc = launchers(c.potential).persistent(c, io, ctl, 0, fast, st, &occ);
     NQ_CHECK_ARG(rc == 0 && occ > 0, "no persistent kernel for D=%d", io.D);
     // fewer resident CTAs than chains, the same number on every SM
-    long long per_sm = blocks / sms;
+    long long per_sm = persistent_ctas_per_sm(fast);
     if (per_sm > occ) per_sm = occ;
     if (per_sm < 1) per_sm = 1;
     rc = launchers(c.potential).persistent(c, io, ctl, (int)(per_sm * sms), fast, st, nullptr);

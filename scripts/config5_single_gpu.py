@@ -12,10 +12,12 @@ seeds = nqr.split(nqr.PRNGKey(0), B)
 x0 = torch.zeros(B, device='cuda')
 for mode in ('strict', 'fast'):
   bc.set_math_mode(mode)
-  for rep in range(2):
+  for rep in range(int(os.environ.get("NQ_REPS", "2"))):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     g = bc.gradient_terms(pot, coeffs, x0, seeds, 0., 40., 0, shift, S, 1e-8, KT, 1.0, KT / 1e7)
     e1.record(); torch.cuda.synchronize()
+    if os.environ.get('NQ_REPS'):
+      print(f'  rep {rep}: {e0.elapsed_time(e1):.2f} ms')
   ms = e0.elapsed_time(e1)
   print(f'{mode}: B={B} S={S}: {ms:.1f} ms  {B * S / ms / 1e-3:.4g} traj-steps/s  mean work {float(g["moments"][1] / g["moments"][0]):.4f}')

@@ -308,9 +308,11 @@ def test_fast_math_mode_parity_is_statistical(cuda):
   assert rel(gs[0], o['grad_logP']) < GRAD_RTOL and rel(gs[1], o['grad_reparam']) < GRAD_RTOL
 
 
-def test_persistent_scheduler_matches_static_launch(cuda):
-  """NQ_PERSISTENT=1 (FIFO ready-queue of trajectory groups, carry handed over through HBM every 512
-  steps) must reproduce the static launch bit for bit."""
+@pytest.mark.parametrize('B,S,mode', [(148 * 64 * 2 + 37, 1300, 'strict'), (100_000, 700, 'strict'), (100_000, 900, 'fast')])
+def test_persistent_scheduler_matches_static_launch(cuda, B, S, mode):
+  """The persistent scheduler (FIFO ready-queue of trajectory groups, carry handed over through HBM every
+  128 / 256 steps; the default between 40k and 160k trajectories) must reproduce the static launch bit for
+  bit: NQ_PERSISTENT=0 against NQ_PERSISTENT=1."""
   import subprocess, sys, json
   code = r"""
 import json, sys, numpy as np, torch
@@ -319,13 +321,14 @@ from noneq_opt_b200 import barrier_crossing as bc, random as nqr, space
 _, shift = space.free()
 KT = 4.183; BETA = 1 / KT; XM = 14.; KAPPA = 21.3863 / (BETA * XM ** 2)
 pot = bc.V_biomolecule_shifted(KAPPA, KAPPA, XM, 0., 1.5, BETA)
-B, S = 148 * 64 * 2 + 37, 1300
+B, S = %d, %d
+bc.set_math_mode(%r)
 coeffs = np.array([20., 19.9, 0.4, -0.2, 0.1], np.float32)
 seeds = nqr.split(nqr.PRNGKey(5), B)
 g = bc.gradient_terms(pot, coeffs, torch.zeros(B, device='cuda'), seeds, 0., 40., 3, shift, S, 1e-8, KT, 1.0, KT / 1e7)
 print(json.dumps(dict(work=g['work'].double().sum().item(), w3=g['work'][:3].tolist(), logp=g['logp'].double().sum().item(),
                       grad=g['grad_sums'].cpu().numpy().tolist(), mom=g['moments'].cpu().numpy().tolist())))
-""" % ROOT
+""" % (ROOT, B, S, mode)
   import os
   outs = []
   for flag in ('0', '1'):
