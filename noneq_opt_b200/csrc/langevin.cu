@@ -111,17 +111,17 @@ static int partial_row(int D) { return 8 + 2 * (D > 0 ? pad4(kernel_D(D)) : 4); 
 static long long chunk_steps(bool fast) {
   const char* env = getenv("NQ_PERSISTENT_CHUNK");
   const long long v = env ? atoll(env) : (fast ? 256 : 128);
-  return v < 128 ? 128 : v;
+  return v < 32 ? 32 : v;
 }
-static long long persistent_ctas_per_sm(bool fast) {
+static long long persistent_ctas_per_sm(bool fast, long long n) {
   const char* env = getenv("NQ_PERSISTENT_PER_SM");
-  return env ? atoll(env) : (fast ? 6 : 8);
+  return env ? atoll(env) : (fast ? 6 : (n <= 130000 ? 8 : 10));
 }
 static bool use_persistent(long long n, long long S, bool record, bool fast) {
   if (record || S < 2 * chunk_steps(fast)) return false;
   const char* env = getenv("NQ_PERSISTENT");
   if (env != nullptr) return env[0] == '1' && n >= 148ll * kThreads * 2;
-  return n > 40000 && (fast || n <= 160000);
+  return n > 40000 && (fast || n <= 300000);
 }
 static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
@@ -204,7 +204,7 @@ static int run(const NqLangevinDesc* desc, const LangevinIO& io_in, double* mome
     rc = launchers(c.potential).persistent(c, io, ctl, 0, fast, st, &occ);
     NQ_CHECK_ARG(rc == 0 && occ > 0, "no persistent kernel for D=%d", io.D);
     // fewer resident CTAs than chains, the same number on every SM
-    long long per_sm = persistent_ctas_per_sm(fast);
+    long long per_sm = persistent_ctas_per_sm(fast, io.n);
     if (per_sm > occ) per_sm = occ;
     if (per_sm < 1) per_sm = 1;
     rc = launchers(c.potential).persistent(c, io, ctl, (int)(per_sm * sms), fast, st, nullptr);

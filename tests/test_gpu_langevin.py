@@ -311,7 +311,7 @@ def test_fast_math_mode_parity_is_statistical(cuda):
 @pytest.mark.parametrize('B,S,mode', [(148 * 64 * 2 + 37, 1300, 'strict'), (100_000, 700, 'strict'), (100_000, 900, 'fast')])
 def test_persistent_scheduler_matches_static_launch(cuda, B, S, mode):
   """The persistent scheduler (FIFO ready-queue of trajectory groups, carry handed over through HBM every
-  128 / 256 steps; the default between 40k and 160k trajectories) must reproduce the static launch bit for
+  128 / 256 steps; the default between 40k and 300k trajectories) must reproduce the static launch bit for
   bit: NQ_PERSISTENT=0 against NQ_PERSISTENT=1."""
   import subprocess, sys, json
   code = r"""
