@@ -54,7 +54,7 @@ def profiled_dram_traffic(math_mode):
   import csv
   import glob
   files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles',
-                                        f'r*_langevin_{math_mode}_full.csv')))
+                                        f'r*_langevin*_{math_mode}_full.csv')))
   if not files:
     return None, None
   scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
@@ -309,7 +309,7 @@ def run_native(args):
     alg_bytes = 24.0 * C2_B + 4.0 * (C2_S + 1) + 4.0 * 13 * (C2_S - 1)
     traffic, traffic_src = profiled_dram_traffic(args.math)
     roofline = dict(
-        bound='issue', kernel='langevin_kernel<BIOMOLECULE_SHIFTED, DP=16>',
+        bound='issue', kernel='langevin_persistent_kernel<BIOMOLECULE_SHIFTED, D=13> (FIFO-scheduled form of langevin_kernel)',
         achieved=per_gpu * INSTR_PER_TRAJ_STEP / 1e12, peak=ISSUE_PEAK / 1e12, unit='Tinstr/s (thread-instructions)',
         frac=per_gpu * INSTR_PER_TRAJ_STEP / ISSUE_PEAK,
         note='instruction-issue bound (3 threefry2x32-20 blocks per step): 326 thread-instr/traj-step (SURVEY 8d) x '
