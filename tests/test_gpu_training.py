@@ -91,3 +91,24 @@ def test_parameterization_protocol_and_works_history(cuda):
   np.testing.assert_allclose(step0, -1e-2 * np.sign(grad.cpu().numpy()), rtol=1e-4)
   np.testing.assert_allclose(out['works'][0].cpu().numpy(), W.cpu().numpy(), rtol=1e-5, atol=1e-5)
   assert out['works'].shape == (2, B)
+
+
+def test_graph_capture_of_the_persistent_scheduler(cuda):
+  """45 000 trajectories take the persistent-scheduler launch (ring + carry in the workspace, an init
+  kernel before the main one): the captured graph must replay it exactly like the eager sequence."""
+  from noneq_opt_b200 import barrier_crossing as bc, space, training
+  _, shift = space.free()
+  B, S = 45_000, 300
+  coeffs0 = bc.fit_linear_to_cheby(1.0, 1.0 / S, 5., 10., 12)
+  key = J.PRNGKey(11)
+  runs = []
+  for graph in (False, True):
+    tr = training.LangevinTrainer(B, bc.V_spring(1.0), coeffs0, 5., 10., 0, shift, S, 1.0 / S, 1.0, 1.0, 1.0, key,
+                                  step_size=0.05, use_graph=graph)
+    out = tr.run(3)
+    torch.cuda.synchronize()
+    runs.append((out['coeffs'].cpu().numpy(), out['mean_work'].cpu().numpy(), tr.launches_per_step))
+  np.testing.assert_array_equal(runs[0][0], runs[1][0])
+  np.testing.assert_array_equal(runs[0][1], runs[1][1])
+  assert runs[0][2] == runs[1][2] == 7      # split3, split(B), schedule, ring init, persistent kernel, finalize, adam
+  assert np.all(np.diff(runs[1][1]) < 0)     # three Adam steps on the linear protocol lower the mean work
