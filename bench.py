@@ -111,9 +111,21 @@ class ClockSampler:
         pass
       time.sleep(0.005)
 
+  def prepare(self):
+    """NVML initialisation and a first query, done BEFORE the warm-up so that starting the sampler at
+    the top of the timed region costs nothing."""
+    try:
+      self._nvml = self._nvml_handle()
+      nv, h = self._nvml
+      nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+      nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+    except Exception:
+      self._nvml = None
+    return self
+
   def start(self):
     try:
-      nv, h = self._nvml_handle()
+      nv, h = self._nvml if getattr(self, '_nvml', None) else self._nvml_handle()
       self.thread = threading.Thread(target=self._poll_nvml, args=(nv, h), daemon=True)
       self.thread.start()
       self.source = 'nvml'
@@ -263,12 +275,12 @@ def run_native(args):
     return out_host['grad']
 
   def timed(fn, steps, warmup, sample_clocks=False):
+    sampler = ClockSampler(local).prepare() if sample_clocks else None
     for _ in range(warmup):
       fn()
     torch.cuda.synchronize()
     if ws > 1:
       dist.barrier()
-    sampler = ClockSampler(local) if sample_clocks else None
     if sampler:
       sampler.start()
     launches0 = lib.nq_launch_count()
