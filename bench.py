@@ -247,9 +247,8 @@ def run_native(args):
   def step_resident():
     out = bc._simulate(pot, shift, r_dev, phi_dev, x0, seeds, C2_S, 0, DT, KT, 1.0, GAMMA)
     if ws > 1:
-      gs, mom = nqd.allreduce_sums([out['grad_sums'], out['moments']])
-    else:
-      gs, mom = out['grad_sums'], out['moments']
+      dist.all_reduce(out['sums_flat'], op=dist.ReduceOp.SUM)   # [grad sums | moments]: one in-place collective
+    gs, mom = out['grad_sums'], out['moments']
     return (gs[0] + gs[1]) / B_global, mom
 
   # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region

@@ -116,7 +116,9 @@ def _simulate(energy_fn, shift, r_table, phi, x0, seeds, S, Neq, dt, kT, mass, g
     if phi_dev.shape[0] != S - 1:
       raise ValueError(f'phi must have simulation_steps-1 = {S - 1} rows, got {phi_dev.shape[0]}')
     out['estimator'] = torch.empty(n, dtype=torch.float32, device=device)
-    out['grad_sums'] = torch.zeros((2, D), dtype=torch.float64, device=device)
+    # [grad sums (2 D) | moments (8)] in ONE float64 buffer: the multi-GPU combine is a single in-place all-reduce
+    flat = torch.zeros(2 * D + _lib.NQ_MOM_COUNT, dtype=torch.float64, device=device)
+    out['sums_flat'], out['grad_sums'], out['moments'] = flat, flat[:2 * D].view(2, D), flat[2 * D:]
     _lib.check(lib.nq_langevin_grad(C.byref(desc), _lib.ptr(r_dev), _lib.ptr(phi_dev), D,
                                     _lib.ptr(x0), _lib.ptr(seeds), n,
                                     _lib.ptr(out['work']), _lib.ptr(out['logp']), _lib.ptr(out['estimator']),

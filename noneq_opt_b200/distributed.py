@@ -66,7 +66,9 @@ def langevin_gradient_sharded(batch_size, energy_fn, r0_init, r0_final, Neq, shi
     seeds = nqrandom.split(seed, batch_size, first=first, count=count)
     out = bc.gradient_terms(energy_fn, coeffs, init_pos, seeds, r0_init, r0_final, Neq, shift,
                             simulation_steps, dt, temperature, mass, gamma)
-    grad_sums, moments = allreduce_sums([out['grad_sums'], out['moments']])
+    if ws > 1:
+      dist.all_reduce(out['sums_flat'], op=dist.ReduceOp.SUM)   # in place: grad_sums and moments are views of it
+    grad_sums, moments = out['grad_sums'], out['moments']
     grad = ((grad_sums[0] + grad_sums[1]) / batch_size).to(torch.float32)
     return grad, dict(moments=moments, grad_sums=grad_sums, local=out)
   return _estimate
