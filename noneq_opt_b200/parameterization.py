@@ -225,9 +225,16 @@ class Chebyshev(Parameterization):
     return np.stack([Chebyshev(row)(x) for row in w], 0)
 
   def jacobian(self, x):
-    if np.ndim(self.weights) != 1:
-      raise NotImplementedError('jacobian of multi-row Chebyshev weights is not supported')
-    return self.basis(x)
+    """[len(x), D] for a weight vector; for weights `[ndim, D]` (one polynomial per output row,
+    parameterization.py:145) `[ndim, len(x), ndim * D]`: row i depends only on its own D weights."""
+    phi = self.basis(x)
+    if np.ndim(self.weights) == 1:
+      return phi
+    ndim, D = np.shape(self.weights)
+    jac = np.zeros((ndim, phi.shape[0], ndim * D), F32)
+    for i in range(ndim):
+      jac[i, :, i * D:(i + 1) * D] = phi
+    return jac
 
 
 class ChangeDomain(Parameterization):

@@ -247,3 +247,22 @@ def test_unknown_callables_are_rejected_not_emulated():
   with pytest.raises(NotImplementedError):
     space.as_shift(lambda R, dR: R + dR)
   assert potentials.V_spring(2.0)(np.array([[3.0]]), r0=1.0) == 4.0
+
+
+def test_multi_row_chebyshev_value_and_jacobian():
+  """Chebyshev with weights [ndim, degree + 1] (parameterization.py:145): one polynomial per row."""
+  rs = np.random.RandomState(2)
+  w = (0.5 * rs.normal(size=(3, 5))).astype(np.float32)
+  xs = np.linspace(0, 1, 17, dtype=np.float32)
+  cheb = p10n.Chebyshev(w)
+  y = cheb(xs)
+  assert y.shape == (3, 17)
+  for i in range(3):
+    np.testing.assert_array_equal(y[i], p10n.Chebyshev(w[i])(xs))
+  J = cheb.jacobian(xs)
+  assert J.shape == (3, 17, 15)
+  np.testing.assert_allclose(np.einsum('inv,v->in', J, w.reshape(-1)), y, atol=2e-6)
+  bumped = w.copy(); bumped[1, 2] += 0.25
+  dy = (p10n.Chebyshev(bumped)(xs) - y) / 0.25
+  np.testing.assert_allclose(dy, J[:, :, 1 * 5 + 2], atol=2e-6)
+  assert cheb.degree == 4 and cheb.n_variables == 15
