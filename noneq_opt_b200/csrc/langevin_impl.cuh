@@ -19,6 +19,9 @@
 #pragma once
 #include <math.h>
 
+#ifndef NQ_PIN_CONSTANTS
+#define NQ_PIN_CONSTANTS 1
+#endif
 #ifndef NQ_FAST_EXP   // precision-study toggles of the FAST path (scripts/precision_study.py)
 #define NQ_FAST_EXP 0
 #endif
@@ -332,10 +335,30 @@ constexpr int pad4(int D) { return (D + 3) / 4 * 4; }
 // group's partial sums; otherwise save the carry.  state layout: [word][npad] (coalesced).
 constexpr int state_words(int D) { return 9 + 2 * (D > 0 ? D : 1); }
 
-template <int POT, bool FAST, int D, bool RECORD>
-__device__ __forceinline__ void langevin_chunk(const LangevinConsts& c, const LangevinIO& io, long long block,
+// PIN: hold the per-step constants in registers.  ptxas otherwise re-reads them from the constant bank every
+// iteration (13 LDCU per step in the STRICT loop, 3 % of its issue slots); passing them through an opaque
+// instruction makes their values unknown to it, so they stay where they are.  Only where the register budget has room (persistent STRICT).
+__device__ __forceinline__ void pin_constants(LangevinConsts& c) {
+  // (an empty inline asm vanishes before ptxas and a shuffle of a warp-uniform value is folded away; a round
+  // trip through shared memory with a volatile load is opaque -- 11 loads per chunk of >= 128 steps)
+  __shared__ float pin_s[12];
+  float* f[11] = {&c.hk, &c.inv_beta, &c.cl, &c.cr, &c.bde, &c.xm, &c.two_xm, &c.nu, &c.dt, &c.sigma, &c.log_norm};
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < 11; ++i) pin_s[i] = *f[i];
+  }
+  __syncthreads();
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(pin_s);
+#pragma unroll
+  for (int i = 0; i < 11; ++i) *f[i] = lds_f32(base + 4 * i);
+}
+
+template <int POT, bool FAST, int D, bool RECORD, bool PIN = false>
+__device__ __forceinline__ void langevin_chunk(const LangevinConsts& c_in, const LangevinIO& io, long long block,
                                                long long k_begin, long long k_end, bool first, bool last,
                                                uint32_t* state, long long npad) {
+  LangevinConsts c = c_in;
+  if (PIN) pin_constants(c);
   constexpr bool GRAD = D > 0;
   constexpr int DA = GRAD ? D : 1;            // accumulators per term
   constexpr int DPS = GRAD ? pad4(D) : 4;     // padded row length in shared memory
@@ -803,7 +826,7 @@ __global__ void __launch_bounds__(kThreads, persistent_min_blocks(D, FAST)) lang
     const long long k_begin = ch * ctl.chunk + 1;
     const long long k_end = min(c.S, (ch + 1) * ctl.chunk);
     const bool last = ch == ctl.n_chunks - 1;
-    langevin_chunk<POT, FAST, D, false>(c, io, g, k_begin, k_end, ch == 0, last, ctl.state, ctl.npad);
+    langevin_chunk<POT, FAST, D, false, NQ_PIN_CONSTANTS && !FAST>(c, io, g, k_begin, k_end, ch == 0, last, ctl.state, ctl.npad);
     if (!last) {
       __threadfence();
       __syncthreads();
