@@ -19,6 +19,9 @@
 #pragma once
 #include <math.h>
 
+#ifndef NQ_PIN_STATIC
+#define NQ_PIN_STATIC 1
+#endif
 #ifndef NQ_PIN_CONSTANTS
 #define NQ_PIN_CONSTANTS 1
 #endif
@@ -564,7 +567,7 @@ __device__ __forceinline__ void langevin_chunk(const LangevinConsts& c_in, const
 
 template <int POT, bool FAST, int D, bool RECORD>
 __global__ void __launch_bounds__(kThreads, min_blocks(D)) langevin_kernel(const LangevinConsts c, const LangevinIO io) {
-  langevin_chunk<POT, FAST, D, RECORD>(c, io, blockIdx.x, 1, c.S, true, true, nullptr, 0);
+  langevin_chunk<POT, FAST, D, RECORD, NQ_PIN_STATIC && !FAST && !RECORD>(c, io, blockIdx.x, 1, c.S, true, true, nullptr, 0);
 }
 
 // ------------------------------------------------------------------------------ small ensembles
