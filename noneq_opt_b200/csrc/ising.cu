@@ -935,6 +935,10 @@ static SegPlan plan_segments(int L, long long R, int T) {
       p.n_seg = n;
     }
   }
+  if (const char* env = getenv("NQ_ISING_SEGMENTS")) {   // override for experiments (>= 2)
+    const int n = atoi(env);
+    if (n >= 2 && n <= T - 1) p.n_seg = n;
+  }
   if (p.n_seg == 1) return p;
   // keep a segment under ~512 sweeps: a CTA that has to wait for the previous segment of its replica
   // waits at most one segment, which must stay far below the kernel's bounded-wait limit.  Doubling
