@@ -11,7 +11,7 @@ S = 2000
 for mode in ('strict', 'fast'):
   bc.set_math_mode(mode)
   for name, (pot, coeffs, r0, r1, dt, kT, gamma) in pots.items():
-    for B in (256, 1000, 4736, 9472, 16384, 20000, 40000):
+    for B in (1000, 9472, 12288, 16384, 24000):
       seeds = nqr.split(nqr.PRNGKey(0), B)
       x0 = torch.full((B,), r0, device='cuda')
       for rep in range(3):
