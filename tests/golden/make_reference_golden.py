@@ -44,6 +44,8 @@ def langevin_cases():
                       coeffs=np.array([20., 19.95996, 0.3, -0.2, 0.1] + [0.] * 8, np.float32),
                       r0=(0., 40.), x0=0.0, Neq=0, S=400, dt=1e-8, kT=kT, mass=1.0, gamma=kT / 1e7),
   }
+  # a longer horizon across the barrier (2500 steps): rounding differences get time to act
+  cases['shifted_long'] = dict(cases['shifted'], S=2500, dt=4e-8)
   # V_biomolecule (wells at -x_m, +x_m) in a periodic box, with equilibration steps
   cases['biomolecule_periodic'] = dict(energy=ref_bc.V_biomolecule(kappa, kappa, x_m / 2, 0.5, 1.5, beta),
                                        coeffs=np.array([10., 9.5, 0.4, -0.3] + [0.] * 3, np.float32),

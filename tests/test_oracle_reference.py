@@ -28,29 +28,33 @@ def rel(a, b):
   return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max() / np.abs(b).max())
 
 
-@pytest.mark.parametrize('name', ['spring', 'shifted', 'biomolecule_periodic'])
+@pytest.mark.parametrize('name', ['spring', 'shifted', 'biomolecule_periodic', 'shifted_long'])
 def test_langevin_oracle_reproduces_the_reference_source(name):
   c = case('reference_langevin.npz', name)
   pot = {'spring': L.V_spring(1.0), 'shifted': L.V_biomolecule_shifted(KAPPA, KAPPA, XM, 0., 1.5, BETA),
+         'shifted_long': L.V_biomolecule_shifted(KAPPA, KAPPA, XM, 0., 1.5, BETA),
          'biomolecule_periodic': L.V_biomolecule(KAPPA, KAPPA, XM / 2, 0.5, 1.5, BETA)}[name]
   shift = ('periodic', float(c['box'])) if float(c['box']) > 0 else 'free'
+  # 2500 steps across the barrier amplify last-bit differences of exp / log between any two float32
+  # implementations (here torch's kernels under the reference's code vs the oracle): 5.5e-6 measured
+  tol = 1e-5 if name == 'shifted_long' else 1e-6
   B = c['positions'].shape[0]
   o = L.estimate_gradient(pot, c['coeffs'], np.full(B, c['x0'], np.float32), c['seed'], float(c['r0'][0]), float(c['r0'][1]),
                           int(c['Neq']), int(c['S']), float(c['dt']), float(c['kT']), float(c['mass']), float(c['gamma']),
                           shift=shift, record=True)
   # run_brownian_opt (barrier_crossing.py:97-143), one call per row of split(seed, B)
-  assert rel(o['traj']['positions'], c['positions'][:, :, 0, 0]) < 1e-6
-  assert rel(o['traj']['log_probs'], c['log_probs']) < 1e-6
-  assert np.abs(o['traj']['works'] - c['works']).max() < 2e-6 * np.abs(c['total_work']).max()
+  assert rel(o['traj']['positions'], c['positions'][:, :, 0, 0]) < tol
+  assert rel(o['traj']['log_probs'], c['log_probs']) < tol
+  assert np.abs(o['traj']['works'] - c['works']).max() < 2 * tol * np.abs(c['total_work']).max()
   assert np.all(c['works'][:, 0] == 0) and c['positions'].shape[1] == int(c['S']) + 1
   if name == 'spring':   # no transcendental on the path except erf_inv: the two agree bit for bit
     np.testing.assert_array_equal(o['traj']['positions'], c['positions'][:, :, 0, 0])
     np.testing.assert_array_equal(o['traj']['works'], c['works'])
   # estimate_gradient_boltzinit (:204-224): jax.value_and_grad of sum(logp) sg(W) + W through the scan
   np.testing.assert_allclose(c['est_positions'], c['positions'])
-  assert rel(o['total_work'], c['total_work']) < 1e-6 and rel(o['tot_log_prob'], c['tot_log_prob']) < 1e-6
+  assert rel(o['total_work'], c['total_work']) < tol and rel(o['tot_log_prob'], c['tot_log_prob']) < tol
   assert rel(o['grad'], c['grad']) < 1e-5
-  assert rel(o['tot_log_prob'] * o['total_work'] + o['total_work'], c['estimator']) < 1e-6
+  assert rel(o['tot_log_prob'] * o['total_work'] + o['total_work'], c['estimator']) < tol
 
 
 @pytest.mark.parametrize('name', ['small', 'fastpath', 'chain', 'cube'])
