@@ -32,9 +32,6 @@ namespace nq {
 #ifndef NQ_ISING_TEAMS     // warp teams (replicas) per CTA of the warp-team kernel
 #define NQ_ISING_TEAMS 4
 #endif
-#ifndef NQ_ISING_SYNC      // 1: the teams of a CTA start every sweep together (one barrier per sweep)
-#define NQ_ISING_SYNC 1
-#endif
 #ifndef NQ_ISING_MINB
 #define NQ_ISING_MINB (NQ_ISING_TEAMS == 4 ? 4 : 1)
 #endif
@@ -365,7 +362,12 @@ __global__ void __launch_bounds__(WARP_TEAM ? 32 * NQ_ISING_TEAMS : 1024, WARP_T
   uint32_t* team_base = smem + 4 * 256 + team * team_words;
   const long long rep_early = (long long)blockIdx.x * nteams + team;
   uint32_t* lat = GLOBAL_LAT ? sh.lat_global + (size_t)(rep_early < sh.R ? rep_early : 0) * lat_words : team_base;
-  uint2* thr_s = reinterpret_cast<uint2*>(team_base + smem_lat_words);
+  // Pair-threshold tables (two sweep-parity buffers).  They depend on the sweep only, so the warp teams of a CTA
+  // -- which start every sweep together -- share ONE copy (team 0's area) and build it cooperatively.
+  uint2* thr_s = reinterpret_cast<uint2*>((WARP_TEAM ? smem + 4 * 256 : team_base) + smem_lat_words);
+  const long long live = sh.R - (long long)blockIdx.x * nteams;
+  const int btid = WARP_TEAM ? team * 32 + lane : threadIdx.x;                                   // index among the builders
+  const int bsize = WARP_TEAM ? 32 * (int)(live < nteams ? live : nteams) : blockDim.x;
   // per-sweep class histograms [parity][half][active|flipped][16]: per team (warp teams) or per CTA
   int* hist_s = WARP_TEAM ? reinterpret_cast<int*>(team_base + smem_lat_words + kThrWords)
                           : reinterpret_cast<int*>(smem + 4 * 256 + nteams * team_words);
@@ -426,8 +428,8 @@ __global__ void __launch_bounds__(WARP_TEAM ? 32 * NQ_ISING_TEAMS : 1024, WARP_T
     }
   }
   if (t_first < t_end)  // first sweep of the pass -> the buffer of its parity
-    build_pair_table(thr_s + (t_first & 1) * 256, io.thr + (size_t)(t_first - 1) * kIsingClasses, tid, tsize);
-  team_sync();
+    build_pair_table(thr_s + (t_first & 1) * 256, io.thr + (size_t)(t_first - 1) * kIsingClasses, btid, bsize);
+  if (WARP_TEAM) __syncthreads(); else team_sync();
 
   // ---- initial spin sum M and bond sum B (each bond joins a colour-0 and a colour-1 site)
   long long M, B;
@@ -467,13 +469,13 @@ __global__ void __launch_bounds__(WARP_TEAM ? 32 * NQ_ISING_TEAMS : 1024, WARP_T
   const KeySchedule ks_rep = key_schedule(io.seeds[2 * rep], io.seeds[2 * rep + 1]);
   const int units = (L / 2) * NW;
   for (int t = t_first; t < t_end; ++t) {
-#if NQ_ISING_SYNC
-    if (WARP_TEAM) __syncthreads();   // keep the teams of a CTA in phase: they then run the same code (i-cache)
-#endif
+    // the teams of a CTA start every sweep together: they then run the same code (instruction cache) and the
+    // shared threshold table of this sweep is complete / the one of the previous sweep is free
+    if (WARP_TEAM) __syncthreads();
     KeySchedule kh[2];
     sweep_keys(ks_rep, t, T, sh.direct_keys != 0, kh[0], kh[1]);
     const uint2* thr_cur = thr_s + (t & 1) * 256;
-    if (t + 1 < t_end) build_pair_table(thr_s + ((t + 1) & 1) * 256, io.thr + (size_t)t * kIsingClasses, tid, tsize);
+    if (t + 1 < t_end) build_pair_table(thr_s + ((t + 1) & 1) * 256, io.thr + (size_t)t * kIsingClasses, btid, bsize);
     // warp teams share ONE copy of the half-sweep code between the colours (their phases differ, so the
     // smaller footprint matters to the instruction cache: +1.6 %); the CTA team runs in lock step and is
     // faster with the two colours unrolled (+2.5 %)
