@@ -127,6 +127,18 @@ int nq_langevin_grad(const NqLangevinDesc* desc /*host*/, const float* r_table,
                      double* grad_sums /*[2][D]*/, double* moments,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same fused pass that ALSO records the trajectories -- the `positions` the reference's estimators
+ * return next to the gradient (barrier_crossing.py:213, 223) -- time-major [S / pos_stride + 1][n], row 0 the
+ * equilibrated start.  Available where the library runs its producer/consumer launch (small ensembles, n <=
+ * 9472 by default); NQ_ERR_UNSUPPORTED otherwise: the caller then records with nq_langevin_forward.   */
+int nq_langevin_grad_record(const NqLangevinDesc* desc /*host*/, const float* r_table,
+                            const float* phi, int32_t D,
+                            const float* x0, const uint32_t* seeds, int64_t n,
+                            float* work, float* logp, float* estimator, float* x_final,
+                            float* positions, int64_t pos_stride,
+                            double* grad_sums /*[2][D]*/, double* moments,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
 /* Checkpointed forward + replay ("adjoint") pair: the forward pass stores (x, rng) every
  * `ckpt_every` steps; the replay pass regenerates each segment from its checkpoint and
  * accumulates the gradient wrt EVERY trap position,

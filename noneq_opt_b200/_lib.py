@@ -14,6 +14,7 @@ NQ_POT_SPRING, NQ_POT_BIOMOLECULE, NQ_POT_BIOMOLECULE_SHIFTED = 0, 1, 2
 NQ_SHIFT_FREE, NQ_SHIFT_PERIODIC = 0, 1
 NQ_MATH_STRICT, NQ_MATH_FAST = 0, 1
 NQ_MOM_COUNT = 8
+NQ_ERR_INVALID_ARGUMENT, NQ_ERR_UNSUPPORTED, NQ_ERR_CUDA, NQ_ERR_WORKSPACE = -1, -2, -3, -4
 NQ_IS_NSUMMARY, NQ_IS_NPARTIAL = 7, 4
 (NQ_IS_WORK, NQ_IS_HEAT, NQ_IS_FWD, NQ_IS_REV, NQ_IS_EP, NQ_IS_MAG, NQ_IS_ENERGY) = range(7)
 (NQ_IS_DFWD_DH, NQ_IS_DFWD_DL, NQ_IS_DREV_DH, NQ_IS_DREV_DL) = range(4)
@@ -58,6 +59,8 @@ SIGNATURES = {
                                       _P, C.c_int64, _P, _P, _P, _P, C.c_size_t, _P]),
     'nq_langevin_grad': (C.c_int, [C.POINTER(NqLangevinDesc), _P, _P, C.c_int32, _P, _P, C.c_int64,
                                    _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    'nq_langevin_grad_record': (C.c_int, [C.POINTER(NqLangevinDesc), _P, _P, C.c_int32, _P, _P, C.c_int64,
+                                          _P, _P, _P, _P, _P, C.c_int64, _P, _P, _P, C.c_size_t, _P]),
     'nq_langevin_ckpt_count': (C.c_size_t, [C.c_int64, C.c_int64]),
     'nq_langevin_forward_ckpt': (C.c_int, [C.POINTER(NqLangevinDesc), _P, _P, _P, C.c_int64, C.c_int64,
                                            _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),

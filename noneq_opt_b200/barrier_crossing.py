@@ -119,11 +119,26 @@ def _simulate(energy_fn, shift, r_table, phi, x0, seeds, S, Neq, dt, kT, mass, g
     # [grad sums (2 D) | moments (8)] in ONE float64 buffer: the multi-GPU combine is a single in-place all-reduce
     flat = torch.zeros(2 * D + _lib.NQ_MOM_COUNT, dtype=torch.float64, device=device)
     out['sums_flat'], out['grad_sums'], out['moments'] = flat, flat[:2 * D].view(2, D), flat[2 * D:]
-    _lib.check(lib.nq_langevin_grad(C.byref(desc), _lib.ptr(r_dev), _lib.ptr(phi_dev), D,
-                                    _lib.ptr(x0), _lib.ptr(seeds), n,
-                                    _lib.ptr(out['work']), _lib.ptr(out['logp']), _lib.ptr(out['estimator']),
-                                    _lib.ptr(out['x_final']), _lib.ptr(out['grad_sums']),
-                                    _lib.ptr(out['moments']), _lib.ptr(ws), ws_bytes, st))
+    out['positions_tm'] = None
+    rc = _lib.NQ_ERR_UNSUPPORTED
+    if positions_stride:
+      # small ensembles: the fused pass records the trajectories too (one pass instead of two)
+      stride = int(positions_stride)
+      pos = torch.empty((S // stride + 1, n), dtype=torch.float32, device=device)
+      rc = lib.nq_langevin_grad_record(C.byref(desc), _lib.ptr(r_dev), _lib.ptr(phi_dev), D, _lib.ptr(x0), _lib.ptr(seeds), n,
+                                       _lib.ptr(out['work']), _lib.ptr(out['logp']), _lib.ptr(out['estimator']),
+                                       _lib.ptr(out['x_final']), _lib.ptr(pos), stride, _lib.ptr(out['grad_sums']),
+                                       _lib.ptr(out['moments']), _lib.ptr(ws), ws_bytes, st)
+      if rc == 0:
+        out['positions_tm'] = pos
+      elif rc != _lib.NQ_ERR_UNSUPPORTED:
+        _lib.check(rc)
+    if rc == _lib.NQ_ERR_UNSUPPORTED:
+      _lib.check(lib.nq_langevin_grad(C.byref(desc), _lib.ptr(r_dev), _lib.ptr(phi_dev), D,
+                                      _lib.ptr(x0), _lib.ptr(seeds), n,
+                                      _lib.ptr(out['work']), _lib.ptr(out['logp']), _lib.ptr(out['estimator']),
+                                      _lib.ptr(out['x_final']), _lib.ptr(out['grad_sums']),
+                                      _lib.ptr(out['moments']), _lib.ptr(ws), ws_bytes, st))
   return out
 
 
@@ -352,7 +367,7 @@ _TERMS = {'reinforce': (1.0, 1.0), 'logP': (1.0, 0.0), 'reparam': (0.0, 1.0)}
 
 
 def gradient_terms(energy_fn, coeffs, init_pos, seeds, r0_init, r0_final, Neq, shift, simulation_steps,
-                   dt, temperature, mass, gamma):
+                   dt, temperature, mass, gamma, positions_stride=None):
   """One fused pass over the trajectories keyed by `seeds [n, 2]`: un-normalised float64 sums of
   the log-prob (score) and reparameterisation gradient terms plus work moments.  This is the
   rank-local piece that `distributed.allreduce_gradient` combines."""
@@ -364,7 +379,8 @@ def gradient_terms(energy_fn, coeffs, init_pos, seeds, r0_init, r0_final, Neq, s
     x0 = x0.expand(seeds.shape[0]).contiguous()
   on_device = _device_schedule_and_jacobian(S, coeffs, r0_init, r0_final, device) if S >= 3 else None
   r, phi = on_device if on_device is not None else _schedule_and_jacobian(np.arange(S + 1), coeffs, r0_init, r0_final)
-  return _simulate(energy_fn, shift, r, phi, x0, seeds, S, Neq, dt, temperature, mass, gamma)
+  return _simulate(energy_fn, shift, r, phi, x0, seeds, S, Neq, dt, temperature, mass, gamma,
+                   positions_stride=positions_stride)
 
 
 def _estimator_factory(term):
@@ -396,11 +412,15 @@ def _estimator_factory(term):
     def _estimate_gradient(coeffs, init_pos, seed):
       """(mean grad [D], (objective [B], (positions [B,S+1,1,1] | None, tot_log_prob [B], total_work [B])))."""
       seeds = nqrandom.split(seed, batch_size)
+      want_pos = _wants_positions(record_positions, batch_size, simulation_steps)
       out = gradient_terms(energy_fn, coeffs, init_pos, seeds, r0_init, r0_final, Neq, shift,
-                           simulation_steps, dt, temperature, mass, gamma)
+                           simulation_steps, dt, temperature, mass, gamma, positions_stride=1 if want_pos else None)
       grad = ((w_logp * out['grad_sums'][0] + w_rep * out['grad_sums'][1]) / batch_size).to(torch.float32)
-      positions = _maybe_positions(energy_fn, coeffs, init_pos, seeds, r0_init, r0_final, Neq, shift,
-                                   simulation_steps, dt, temperature, mass, gamma, record_positions, batch_size)
+      if out.get('positions_tm') is not None:     # recorded by the same pass (small ensembles)
+        positions = out['positions_tm'].t().unsqueeze(-1).unsqueeze(-1)
+      else:
+        positions = _maybe_positions(energy_fn, coeffs, init_pos, seeds, r0_init, r0_final, Neq, shift,
+                                     simulation_steps, dt, temperature, mass, gamma, want_pos, batch_size)
       W, lp = out['work'], out['logp']
       if term == 'reinforce':
         value = out['estimator']
@@ -413,12 +433,16 @@ def _estimator_factory(term):
   return single, batch
 
 
+def _wants_positions(record_positions, n, S):
+  if record_positions is None:
+    return 4 * n * (int(S) + 1) <= MAX_AUTO_POSITION_BYTES
+  return bool(record_positions)
+
+
 def _maybe_positions(energy_fn, coeffs, init_pos, seeds, r0_init, r0_final, Neq, shift, S, dt, kT, mass,
                      gamma, record_positions, n):
   S = int(S)
-  if record_positions is None:
-    record_positions = 4 * n * (S + 1) <= MAX_AUTO_POSITION_BYTES
-  if not record_positions:
+  if not _wants_positions(record_positions, n, S):
     return None
   device = _lib.require_cuda()
   seeds = nqrandom.as_key_tensor(seeds, device).reshape(-1, 2)

@@ -156,8 +156,11 @@ static int run(const NqLangevinDesc* desc, const LangevinIO& io_in, double* mome
   NQ_CHECK_ARG(io.D == 0 || io.phi, "phi is null");
   const bool fast = desc->math_mode == NQ_MATH_FAST;
   const int NV = partial_row(io.D);
-  const bool record = io.positions || io.step_works || io.step_logps || io.ckpt_x;
-  const bool pair = use_pair(io.n, record);
+  // the pair kernel can record positions on the side (also with D > 0); everything else that records runs the
+  // one-warp RECORD kernel, forward only
+  const bool record_other = io.step_works || io.step_logps || io.ckpt_x;
+  const bool pair = use_pair(io.n, record_other);
+  const bool record = record_other || (io.positions && !pair);
   const int blocks = (int)(pair ? (io.n + 31) / 32 : (io.n + kThreads - 1) / kThreads);
   const long long kChunkSteps = chunk_steps(fast);
   const bool persistent = !pair && use_persistent(io.n, c.S, record, fast);
@@ -266,6 +269,26 @@ extern "C" int nq_langevin_grad(const NqLangevinDesc* desc, const float* r_table
   LangevinIO io{};
   io.r_table = r_table; io.phi = phi; io.x0 = x0; io.seeds = seeds;
   io.work = work; io.logp = logp; io.estimator = estimator; io.x_final = x_final;
+  io.n = n; io.D = D;
+  return run(desc, io, moments, grad_sums, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int nq_langevin_grad_record(const NqLangevinDesc* desc, const float* r_table, const float* phi, int32_t D,
+                                       const float* x0, const uint32_t* seeds, int64_t n, float* work, float* logp,
+                                       float* estimator, float* x_final, float* positions, int64_t pos_stride,
+                                       double* grad_sums, double* moments, void* workspace, size_t workspace_bytes,
+                                       void* stream) {
+  NQ_CHECK_ARG(D >= 1, "D must be >= 1 for the gradient entry point");
+  NQ_CHECK_ARG(grad_sums != nullptr && positions != nullptr && pos_stride >= 1, "grad_sums / positions / pos_stride");
+  if (!use_pair(n, false)) {
+    set_error("the fused gradient pass records positions only for small ensembles (n <= %lld); run nq_langevin_forward "
+              "for the record", pair_max());
+    return NQ_ERR_UNSUPPORTED;
+  }
+  LangevinIO io{};
+  io.r_table = r_table; io.phi = phi; io.x0 = x0; io.seeds = seeds;
+  io.work = work; io.logp = logp; io.estimator = estimator; io.x_final = x_final;
+  io.positions = positions; io.pos_stride = pos_stride;
   io.n = n; io.D = D;
   return run(desc, io, moments, grad_sums, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -668,6 +668,10 @@ __global__ void __launch_bounds__(kPairThreads) langevin_pair_kernel(const Lange
       }
     }
   }
+  // optional trajectory record (time-major [S / stride + 1][n], row 0 = the equilibrated start :142): the
+  // consumer is not the slower stage, so the stores are free here
+  float* pos_out = io.positions ? io.positions + gid : nullptr;
+  if (pos_out && live) pos_out[0] = x;
   for (long long t0 = 1; t0 <= c.S; t0 += kTile) {
     const int len = (int)min((long long)kTile, c.S - t0 + 1);
     __syncwarp();
@@ -710,6 +714,10 @@ __global__ void __launch_bounds__(kPairThreads) langevin_pair_kernel(const Lange
         LPt = fmaf(z, z, LPt);
       } else {
         LPt += lp;
+      }
+      if (pos_out && live) {
+        const long long k = t0 + i;
+        if (k % io.pos_stride == 0) pos_out[(k / io.pos_stride) * io.n] = x;
       }
       if (GRAD) {
         const float a = z, b = c.shift_kind == NQ_SHIFT_PERIODIC ? x - x_before : dR;

@@ -538,3 +538,29 @@ def test_small_ensemble_pair_kernel_equals_main_kernel(cuda, monkeypatch, n, D, 
   assert rel(pair_f['work'].cpu().numpy(), main_f['work'].cpu().numpy()) < 1e-4
   if D:
     assert rel(pair_f['grad_sums'].cpu().numpy(), main_f['grad_sums'].cpu().numpy()) < 1e-4
+
+
+def test_small_ensemble_gradient_pass_records_positions(cuda, monkeypatch):
+  """Up to 9472 trajectories the estimators get the `positions` they return (barrier_crossing.py:213, 223)
+  from the same fused pass (nq_langevin_grad_record, written by the integration warp of the pair kernel);
+  they must be the positions of the forward-record kernel bit for bit, and larger ensembles must fall back."""
+  import ctypes as C
+  from noneq_opt_b200 import _lib, barrier_crossing as bc, random as nqr, space
+  _, shift = space.free()
+  pot = bc.V_biomolecule_shifted(KAPPA, KAPPA, XM, 0., 1.5, BETA)
+  coeffs = np.array([20., 19.96, 0.3, -0.2, 0.1], np.float32)
+  B, S, Neq = 333, 290, 4
+  x0 = np.zeros((B, 1, 1), np.float32)
+  est = bc.estimate_gradient_boltzinit(B, pot, 0., 40., Neq, shift, S, 1e-8, KT, 1.0, KT / 1e7)
+  before = _lib.lib().nq_launch_count()
+  grad, (_, (pos, lp, w)) = est(coeffs, x0, J.PRNGKey(9))
+  launches = _lib.lib().nq_launch_count() - before
+  assert pos.shape == (B, S + 1, 1, 1) and launches == 4      # split, schedule, fused pass, finalize: no second simulation
+  seeds = nqr.split(J.PRNGKey(9), B)
+  rec = bc._maybe_positions(pot, coeffs, x0, seeds, 0., 40., Neq, shift, S, 1e-8, KT, 1.0, KT / 1e7, True, B)
+  assert torch.equal(pos, rec)
+  monkeypatch.setenv('NQ_PAIR_MAX', '0')          # as for a large ensemble: the library declines, the host records separately
+  grad2, (_, (pos2, lp2, w2)) = est(coeffs, x0, J.PRNGKey(9))
+  monkeypatch.delenv('NQ_PAIR_MAX')
+  assert torch.equal(pos2, pos) and torch.equal(w2, w) and torch.equal(lp2, lp)
+  np.testing.assert_allclose(grad2.cpu().numpy(), grad.cpu().numpy(), rtol=1e-6)
