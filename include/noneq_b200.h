@@ -308,13 +308,6 @@ int nq_adam_step(const NqAdamDesc* desc /*host*/, int32_t P, const double* grad_
  * nq_ising_run leave their sums on the device; enqueue this on the same stream.               */
 int nq_allreduce_f64(void* nccl_comm, double* buf /*device [n]*/, int64_t n, void* stream);
 
-/* ------------------------------------------------------------------ calibration */
-/* issue-rate microbenchmark: runs `iters` dependent-chain iterations of
- * instruction mix `which` on `blocks` x `threads`; elapsed SM cycles (max over blocks) -> host out.
- * Used only by bench.py --calibrate and profiles/; not part of the hot path.               */
-int nq_microbench(int32_t which, int32_t blocks, int32_t threads, int32_t iters,
-                  uint64_t* out_cycles /*device [blocks]*/, uint32_t* sink /*device*/, void* stream);
-
 #ifdef __cplusplus
 }
 #endif

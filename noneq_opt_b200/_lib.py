@@ -83,7 +83,6 @@ SIGNATURES = {
     'nq_schedule_affine': (C.c_int, [_P, _P, _P, C.c_float, C.c_float, C.c_int64, C.c_int32, _P, _P]),
     'nq_adam_step': (C.c_int, [C.POINTER(NqAdamDesc), C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'nq_allreduce_f64': (C.c_int, [_P, _P, C.c_int64, _P]),
-    'nq_microbench': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
 }
 
 _lib = None

@@ -16,7 +16,9 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libnoneq_b200.so')
 STAMP = os.path.join(HERE, 'csrc', '.build_stamp')
 SOURCES = ['core.cu', 'langevin.cu', 'langevin_pot_spring.cu', 'langevin_pot_biomolecule.cu', 'langevin_pot_shifted.cu',
-           'ising.cu', 'train.cu', 'microbench.cu']
+           'ising.cu', 'train.cu']
+DEV_SOURCES = ['devtools.cu']   # -> libnoneq_b200_dev.so (microbenchmark, math checker; not the product ABI)
+DEV_LIB = os.path.join(HERE, 'libnoneq_b200_dev.so')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr'] + os.environ.get('NQ_EXTRA_NVCC_FLAGS', '').split()
 
@@ -42,14 +44,14 @@ def _digest():
 
 def build(force: bool = False, verbose: bool = False) -> str:
   digest = _digest()
-  if not force and os.path.exists(LIB) and os.path.exists(STAMP):
+  if not force and os.path.exists(LIB) and os.path.exists(DEV_LIB) and os.path.exists(STAMP):
     with open(STAMP) as f:
       if f.read().strip() == digest:
         return LIB
   nvcc = _nvcc()
   objs = []
   procs = []
-  for src in SOURCES:
+  for src in SOURCES + DEV_SOURCES:
     path = os.path.join(CSRC, src)
     if not os.path.exists(path):
       continue
@@ -66,10 +68,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
       print(out)
     if p.returncode:
       raise RuntimeError(f'nvcc failed on {src}:\n{out}')
-  cmd = [nvcc, '-shared', '-o', LIB, *objs, '-gencode', 'arch=compute_100a,code=sm_100a']
-  r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-  if r.returncode:
-    raise RuntimeError(f'link failed:\n{r.stdout}')
+  dev_objs = [o for o in objs if os.path.basename(o) in [d.replace('.cu', '.o') for d in DEV_SOURCES]]
+  objs = [o for o in objs if o not in dev_objs]
+  for lib, members in ((LIB, objs), (DEV_LIB, dev_objs)):
+    cmd = [nvcc, '-shared', '-o', lib, *members, '-gencode', 'arch=compute_100a,code=sm_100a', '-ldl']
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode:
+      raise RuntimeError(f'link failed:\n{r.stdout}')
   with open(STAMP, 'w') as f:
     f.write(digest)
   return LIB

@@ -1,5 +1,9 @@
-// Issue-rate calibration for the instruction mixes the hot path is built from
-// ("first kernel PR must include a microbenchmark").  Not on the hot path.
+// Developer tools, built into libnoneq_b200_dev.so (NOT part of the product ABI, include/noneq_b200_dev.h):
+//   nqdev_microbench  -- issue-rate calibration for the instruction mixes the hot path is built from
+//                        ("first kernel PR must include a microbenchmark");
+//   nqdev_math_check  -- bit-identity of the STRICT main-path math (nq_common.cuh: logf_main, log1pf_main,
+//                        div_main, normal_from_bits) against the CUDA library functions / the literal
+//                        transcription of jax.random.normal, over ranges of input bit patterns.
 //
 // Each thread runs 8 independent dependency chains; one loop iteration issues kOps instructions
 // of the mix per chain-slot.  The host divides (threads * iters * ops_per_iter) by the elapsed SM
@@ -7,6 +11,10 @@
 #include "nq_common.cuh"
 
 namespace nq {
+// self-contained: the dev library does not link core.cu
+void set_error(const char*, ...) {}
+int cuda_fail(cudaError_t, const char*) { return NQ_ERR_CUDA; }
+std::atomic<uint64_t> g_launches{0};
 
 constexpr int kChains = 8;
 
@@ -104,7 +112,7 @@ __global__ void __launch_bounds__(128) placement_kernel(int iters, unsigned long
   if (iters < 0) sink[0] = smid;
 }
 
-extern "C" int nq_microbench(int32_t which, int32_t blocks, int32_t threads, int32_t iters, uint64_t* out_cycles,
+extern "C" int nqdev_microbench(int32_t which, int32_t blocks, int32_t threads, int32_t iters, uint64_t* out_cycles,
                              uint32_t* sink, void* stream) {
   NQ_CHECK_ARG(which >= 0 && which <= 12, "unknown microbenchmark %d", which);
   NQ_CHECK_ARG(blocks >= 1 && threads >= 32 && threads <= 1024 && iters >= 1 && out_cycles && sink, "bad arguments");
@@ -122,4 +130,70 @@ extern "C" int nq_microbench(int32_t which, int32_t blocks, int32_t threads, int
 #undef NQ_MB
   NQ_LAUNCHED();
   return NQ_OK;
+}
+
+// ------------------------------------------------------------------------------ math check
+namespace nq {
+
+// jax.random.normal from a raw word exactly as jax writes it, on the CUDA library
+// functions: the form the STRICT kernels used before the main-path rewrite
+__device__ float normal_literal(uint32_t bits) {
+  const float lo = -0.99999994f;  // nextafter(-1, 0)
+  const float f = __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
+  const float u = fmaxf(lo, __fadd_rn(__fmul_rn(f, 2.0f), lo));
+  float w = -log1pf(-__fmul_rn(u, u));
+  float p;
+#define NQ_H(c) p = __fadd_rn(c, __fmul_rn(p, w));
+  if (w < 5.0f) {
+    w = __fadd_rn(w, -2.5f);
+    p = 2.81022636e-08f;
+    NQ_H(3.43273939e-07f) NQ_H(-3.5233877e-06f) NQ_H(-4.39150654e-06f) NQ_H(0.00021858087f)
+    NQ_H(-0.00125372503f) NQ_H(-0.00417768164f) NQ_H(0.246640727f) NQ_H(1.50140941f)
+  } else {
+    w = __fadd_rn(__fsqrt_rn(w), -3.0f);
+    p = -0.000200214257f;
+    NQ_H(0.000100950558f) NQ_H(0.00134934322f) NQ_H(-0.00367342844f) NQ_H(0.00573950773f)
+    NQ_H(-0.0076224613f) NQ_H(0.00943887047f) NQ_H(1.00167406f) NQ_H(2.83297682f)
+  }
+#undef NQ_H
+  const float r = __fmul_rn(p, u);
+  return __fmul_rn(1.41421356237309504880f, fabsf(u) == 1.0f ? u * __int_as_float(0x7f800000) : r);
+}
+
+// which: 0 logf_main(x) vs logf(x); 1 log1pf_main(-x) vs log1pf(-x); 2 div_main(c, x) vs c / x (IEEE);
+//        3 normal_from_bits<false>(p << 9) vs normal_literal(p << 9), p = the bit pattern itself.
+// x = the float with bit pattern p, p in [first, first + count).  out[0] = mismatches, out[1] = first mismatching p.
+__global__ void math_check_kernel(int which, unsigned long long first, unsigned long long count, float c,
+                                  unsigned long long* out) {
+  unsigned long long bad = 0, where = ~0ull;
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < count;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t p = (uint32_t)(first + i);
+    const float x = __uint_as_float(p);
+    float a, b;
+    if (which == 0) { a = logf_main(x); b = logf(x); }
+    else if (which == 1) { a = log1pf_main(-x); b = log1pf(-x); }
+    else if (which == 2) { a = div_main(c, x); b = __fdiv_rn(c, x); }
+    else { a = normal_from_bits<false>(p << 9); b = normal_literal(p << 9); }
+    if (__float_as_uint(a) != __float_as_uint(b)) {
+      ++bad;
+      if (first + i < where) where = first + i;
+    }
+  }
+  if (bad) {
+    atomicAdd(out, bad);
+    atomicMin(out + 1, where);
+  }
+}
+
+}  // namespace nq
+
+extern "C" int nqdev_math_check(int32_t which, uint64_t first, uint64_t count, float c, uint64_t* out /*device [2]*/,
+                                void* stream) {
+  if (which < 0 || which > 3 || !out) return NQ_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned long long init[2] = {0ull, ~0ull};
+  if (cudaMemcpyAsync(out, init, sizeof(init), cudaMemcpyHostToDevice, st) != cudaSuccess) return NQ_ERR_CUDA;
+  math_check_kernel<<<148 * 8, 256, 0, st>>>(which, first, count, c, (unsigned long long*)out);
+  return cudaGetLastError() == cudaSuccess ? NQ_OK : NQ_ERR_CUDA;
 }

@@ -54,6 +54,9 @@ int make_langevin_consts(const NqLangevinDesc* d, LangevinConsts* c) {
     c->f_crm = (float)(nudt * ib * 2.0 * (double)c->cr);
     c->f_cu = (float)(2.0 * (double)c->hk * nudt);
   }
+  // STRICT main-path window of the division / logarithm of A + B (div_main, logf_main): the numerator
+  // 1 / beta must sit inside [2^-62, 2^62) too, otherwise every step takes the library functions
+  c->guard_span = (c->inv_beta >= 0x1p-62f && c->inv_beta < 0x1p62f) ? 0x3e000000u : 0u;
   c->S = d->steps;
   c->Neq = d->eq_steps;
   return NQ_OK;

@@ -59,6 +59,9 @@ struct LangevinConsts {
   float nudt;   // nu*dt (fast mode only)
   // FAST-math constants (see fast_mean): log2(e)-scaled exponents, (nu dt / beta)-scaled force terms
   float f_cl2, f_ncr2, f_nbde2, f_clm, f_crm, f_cu;
+  // STRICT: width of the operand window [2^-62, 2^62) in which the division / logarithm of A + B take their
+  // main paths (div_main, logf_main); 0 sends every step through the library functions (extreme 1 / beta)
+  uint32_t guard_span;
   long long S, Neq;
 };
 
@@ -75,18 +78,17 @@ template <bool FAST> __device__ __forceinline__ float fexp(float a) { return FAS
 template <bool FAST> __device__ __forceinline__ float flog(float a) { return FAST ? __logf(a) : logf(a); }
 template <bool FAST> __device__ __forceinline__ float fdiv(float a, float b) { return FAST ? __fdividef(a, b) : __fdiv_rn(a, b); }
 
-// a / y for a constant y with r = RN(1/y): one Newton correction in FMA arithmetic returns the
-// correctly rounded quotient (Markstein) -- 3 instructions instead of the IEEE division sequence.
-__device__ __forceinline__ float div_by_const(float a, float y, float r) {
-  const float q = __fmul_rn(a, r);
-  const float e = __fmaf_rn(-q, y, a);
-  return __fmaf_rn(e, r, q);
+// division and logarithm of A + B outside the main-path window (never taken for physical parameters:
+// A + B < 2^-62 needs a particle > 9 well-widths from both wells); kept out of line
+static __device__ __noinline__ float2 div_log_library(float c, float s) {
+  return make_float2(__fdiv_rn(c, s), logf(s));
 }
 
 // energy pieces shared between increment_work (:123-124) and the force (:60,68)
 template <int POT, bool FAST>
 struct Landscape {
   float ul, ur, A, B, sAB;
+  float g, lg;   // STRICT: -(1/beta) / (A + B) and log(A + B)
   __device__ __forceinline__ void eval(const LangevinConsts& c, float x) {
     if (POT == NQ_POT_SPRING) return;
     if (POT == NQ_POT_BIOMOLECULE) {
@@ -101,18 +103,34 @@ struct Landscape {
     A = fexp<FAST>(a);
     B = fexp<FAST>(-v);
     sAB = fadd<FAST>(A, B);
+    if (!FAST) {
+      // one operand check serves both the quotient of the force and the logarithm of the energy (whichever
+      // of the two the caller does not use is dead code)
+      if ((__float_as_uint(sAB) - 0x20800000u) < c.guard_span) {
+        g = div_main(-c.inv_beta, sAB);
+        lg = logf_main(sAB);
+      } else {
+        const float2 t = div_log_library(-c.inv_beta, sAB);
+        g = t.x;
+        lg = t.y;
+      }
+    }
   }
   __device__ __forceinline__ float Em(const LangevinConsts& c) const {
-    return POT == NQ_POT_SPRING ? 0.f : fmul<FAST>(-c.inv_beta, flog<FAST>(sAB));
+    return POT == NQ_POT_SPRING ? 0.f : (FAST ? -c.inv_beta * __logf(sAB) : __fmul_rn(-c.inv_beta, lg));
   }
-  // dEm/dx in the order of jax's VJP rules (log: g/x, exp: g*ans, x**2: g*(2x))
-  __device__ __forceinline__ float dEm(const LangevinConsts& c) const {
+  // HALF of dEm/dx, in the order of jax's VJP rules (log: g/x, exp: g*ans, x**2: g*(2x)).  The factor 2 of
+  // d(x^2)/dx is a power of two: rn(t * (2 u)) = 2 rn(t u) and rn(2 a + 2 b) = 2 rn(a + b) exactly (no
+  // intermediate of this path comes near the subnormal range), so the reference's 2ul, 2ur and 2(x - r)
+  // are carried as ONE factor that the step applies in its final fused add -- same bits, three multiplies
+  // fewer per step.
+  __device__ __forceinline__ float half_dEm(const LangevinConsts& c) const {
     if (POT == NQ_POT_SPRING) return 0.f;
-    const float g = fdiv<FAST>(-c.inv_beta, sAB);
-    const float ga = fmul<FAST>(g, A), gb = fmul<FAST>(g, B);
-    const float dxa = fmul<FAST>(fmul<FAST>(ga, c.cl), fmul<FAST>(2.0f, ul));
-    const float dxb = fmul<FAST>(fmul<FAST>(-gb, c.cr), fmul<FAST>(2.0f, ur));
-    return fadd<FAST>(dxa, dxb);
+    const float gq = FAST ? __fdividef(-c.inv_beta, sAB) : g;
+    const float ga = fmul<FAST>(gq, A), gb = fmul<FAST>(gq, B);
+    const float ta = fmul<FAST>(fmul<FAST>(ga, c.cl), ul);
+    const float tb = fmul<FAST>(fmul<FAST>(-gb, c.cr), ur);
+    return fadd<FAST>(ta, tb);
   }
 };
 
@@ -169,30 +187,39 @@ struct RngPipe {
   }
 };
 
-// One apply_fn (barrier_crossing.py:77-92) given the landscape already evaluated at x and the raw
-// bits of this step's normal draw.  Returns dR; updates x; writes z (standardised noise) and lp.
-template <int POT, bool FAST>
+// One apply_fn (barrier_crossing.py:77-92) given the landscape already evaluated at x and this step's
+// standard-normal draw.  Returns dR; updates x; writes z (standardised noise) and, if WANT_LP, lp.
+template <int POT, bool FAST, bool PERIODIC, bool WANT_LP>
 __device__ __forceinline__ float brownian_apply_xi(const LangevinConsts& c, const Landscape<POT, FAST>& land, float& x,
                                                    float xi, float r, float& z, float& lp) {
-  const float u = fsub<FAST>(x, r);
-  const float dEs = fmul<FAST>(c.hk, fmul<FAST>(2.0f, u));
-  const float F = POT == NQ_POT_SPRING ? -dEs : -fadd<FAST>(land.dEm(c), dEs);
-  const float mean = FAST ? F * c.nudt : __fmul_rn(__fmul_rn(F, c.nu), c.dt);
-  const float dR = fadd<FAST>(fmul<FAST>(xi, c.sigma), mean);  // sampled * scale + loc
+  // -F / 2 = (dEm/dx)/2 + (k_s/2)(x - r); the reference forms dEs = (k_s/2) * (2 (x - r)), see half_dEm
+  const float es = fmul<FAST>(c.hk, fsub<FAST>(x, r));
+  const float q = POT == NQ_POT_SPRING ? es : fadd<FAST>(land.half_dEm(c), es);
+  // mean = F * nu * dt (:67-69) = 2 m2;  dR = sampled * scale + loc (:88) in one rounding of xi sigma + 2 m2
+  const float m2 = FAST ? -q * c.nudt : __fmul_rn(__fmul_rn(-q, c.nu), c.dt);
+  const float dR = FAST ? fmaf(2.0f, m2, xi * c.sigma) : __fmaf_rn(2.0f, m2, __fmul_rn(xi, c.sigma));
   // Normal.log_prob's z = x/scale - loc/scale equals xi up to one rounding of dR: using xi changes
   // each log-prob by < 1e-6 absolute (tolerance 1e-5 relative of ~9) and is 7 instructions cheaper
   // than two correctly rounded quotients; the position and work paths stay in reference order.
   z = xi;
-  lp = fsub<FAST>(fmul<FAST>(-0.5f, fmul<FAST>(z, z)), c.log_norm);
+  if (WANT_LP) lp = fsub<FAST>(fmul<FAST>(-0.5f, fmul<FAST>(z, z)), c.log_norm);
   x = fadd<FAST>(x, dR);
-  if (c.shift_kind == NQ_SHIFT_PERIODIC) x = py_mod(x, c.box);
+  if (PERIODIC) x = py_mod(x, c.box);
   return dR;
 }
 
-template <int POT, bool FAST>
+template <int POT, bool FAST, bool PERIODIC, bool WANT_LP>
 __device__ __forceinline__ float brownian_apply(const LangevinConsts& c, const Landscape<POT, FAST>& land, float& x,
                                                 uint32_t bits, float r, float& z, float& lp) {
-  return brownian_apply_xi<POT, FAST>(c, land, x, normal_from_bits<FAST>(bits), r, z, lp);
+  return brownian_apply_xi<POT, FAST, PERIODIC, WANT_LP>(c, land, x, normal_from_bits<FAST>(bits), r, z, lp);
+}
+
+// run-time shift kind -> the specialised step (equilibration, stationary trap, replay: not the hot loop)
+template <int POT, bool FAST>
+__device__ __forceinline__ float brownian_apply_any(const LangevinConsts& c, const Landscape<POT, FAST>& land, float& x,
+                                                    float xi, float r, float& z, float& lp) {
+  return c.shift_kind == NQ_SHIFT_PERIODIC ? brownian_apply_xi<POT, FAST, true, true>(c, land, x, xi, r, z, lp)
+                                           : brownian_apply_xi<POT, FAST, false, true>(c, land, x, xi, r, z, lp);
 }
 
 // ------------------------------------------------------------------------------ FAST-math step
@@ -289,22 +316,23 @@ __device__ __forceinline__ float fast_normal(uint32_t bits) {
 #endif
 }
 
-template <int POT>
+// PERIODIC: 1 / 0 = the shift kind known at compile time (the hot loops), -1 = read it from the constants
+template <int POT, int PERIODIC = -1>
 __device__ __forceinline__ float fast_step_z(const LangevinConsts& c, float& x, float z, float r) {
   const float mean = fast_mean<POT>(c, x, r);
   const float dR = fmaf(z, c.sigma, mean);
   x += dR;
-  if (c.shift_kind == NQ_SHIFT_PERIODIC) x = py_mod(x, c.box);
+  if (PERIODIC < 0 ? c.shift_kind == NQ_SHIFT_PERIODIC : PERIODIC == 1) x = py_mod(x, c.box);
   return dR;
 }
 
-template <int POT>
+template <int POT, int PERIODIC = -1>
 __device__ __forceinline__ float fast_step(const LangevinConsts& c, float& x, uint32_t bits, float r, float& z) {
   const float mean = fast_mean<POT>(c, x, r);   // (this statement order gives the better ptxas schedule)
   z = fast_normal(bits);
   const float dR = fmaf(z, c.sigma, mean);
   x += dR;
-  if (c.shift_kind == NQ_SHIFT_PERIODIC) x = py_mod(x, c.box);
+  if (PERIODIC < 0 ? c.shift_kind == NQ_SHIFT_PERIODIC : PERIODIC == 1) x = py_mod(x, c.box);
   return dR;
 }
 
@@ -337,6 +365,94 @@ constexpr int pad4(int D) { return (D + 3) / 4 * 4; }
 // (+ equilibration); otherwise restore the carry from `state`.  last: write the outputs and the
 // group's partial sums; otherwise save the carry.  state layout: [word][npad] (coalesced).
 constexpr int state_words(int D) { return 9 + 2 * (D > 0 ? D : 1); }
+
+// The steps of one staged tile (r_s / phi_s / tab_s hold steps t0 .. t0 + len - 1).  Per step: work increment at
+// the position before the kick, the kick, log-prob and gradient moments.  Without RECORD the log-prob sum is
+// carried as sum(z^2) (one FMA per step) and turned into sum(-z^2/2 - log_norm) per tile in binary64 -- at
+// least as accurate as summing the reference's rounded per-step terms; RECORD emits those terms themselves.
+template <int POT, bool FAST, int D>
+struct StepCtx {
+  const LangevinConsts& c;
+  const LangevinIO& io;
+  float& x;
+  RngPipe& rng;
+  Landscape<POT, FAST>& land;
+  float& z;
+  float& lp;
+  float* gA;
+  float* gB;
+  float& Wt;
+  float& LPt;
+  long long gid;
+  bool live;
+};
+
+template <int POT, bool FAST, int D, bool RECORD, bool PERIODIC>
+__device__ __forceinline__ void tile_steps(StepCtx<POT, FAST, D>& s, long long t0, int len, uint32_t r_addr,
+                                           uint32_t phi_addr, uint32_t tab_addr) {
+  constexpr bool GRAD = D > 0;
+  constexpr int DPS = GRAD ? pad4(D) : 4;
+  const LangevinConsts& c = s.c;
+  const LangevinIO& io = s.io;
+  float x = s.x, z = s.z, lp = s.lp, Wt = s.Wt, LPt = s.LPt;
+#pragma unroll kUnroll
+  for (int i = 0; i < len; ++i, r_addr += 4, phi_addr += 4 * DPS, tab_addr += 16) {
+    if (RECORD && io.ckpt_x) {  // checkpoint BEFORE step k = t0+i when (k-1) % ckpt_every == 0
+      const long long k = t0 + i;
+      if ((k - 1) % io.ckpt_every == 0 && s.live) {
+        const long long q = (k - 1) / io.ckpt_every;
+        io.ckpt_x[q * io.n + s.gid] = x;
+        uint32_t* dst = io.ckpt_rng + q * 4 * io.n + s.gid;
+        dst[0] = s.rng.k0; dst[io.n] = s.rng.k1; dst[2 * io.n] = s.rng.s0; dst[3 * io.n] = s.rng.s1;
+      }
+    }
+    float dW, dR;
+    const float x_before = x;
+    if (FAST) {
+      const float4 tab = lds_f32x4(tab_addr);
+      dW = fmaf(tab.y, x, tab.z);
+      dR = fast_step<POT, PERIODIC ? 1 : 0>(c, x, s.rng.next(), tab.x, z);
+      if (RECORD) lp = fmaf(-0.5f * z, z, -c.log_norm);
+    } else {
+      const float r_prev = lds_f32(r_addr), r_cur = lds_f32(r_addr + 4);
+      s.land.eval(c, x);
+      dW = work_increment<POT, FAST>(c, s.land, x, r_prev, r_cur);
+      dR = brownian_apply<POT, FAST, PERIODIC, RECORD>(c, s.land, x, s.rng.next(), r_cur, z, lp);
+    }
+    Wt += dW;
+    if (!RECORD) {
+      LPt = fmaf(z, z, LPt);  // sum of z^2; turned into the log-prob sum at the end of the tile
+    } else {
+      LPt += lp;
+    }
+    if (GRAD) {
+      // d logp_k / d r_k = z * ca and d W / d r_k = k_s * dR: the constant factors are applied
+      // once, after the trajectory
+      // d W / d r_k = -k_s (x_{k-1} - r_k) + k_s (x_k - r_k) = k_s (x_k - x_{k-1}); that is k_s dR unless a
+      // periodic shift wrapped the position
+      const float a = z, b = PERIODIC ? x - x_before : dR;
+#pragma unroll
+      for (int q = 0; q < DPS / 4; ++q) {
+        const float4 p = lds_f32x4(phi_addr + 16 * q);
+        const float pv[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (4 * q + e < D) {
+            s.gA[4 * q + e] = fmaf(a, pv[e], s.gA[4 * q + e]);
+            s.gB[4 * q + e] = fmaf(b, pv[e], s.gB[4 * q + e]);
+          }
+        }
+      }
+    }
+    if (RECORD && s.live) {
+      const long long k = t0 + i;
+      if (io.step_works) io.step_works[k * io.n + s.gid] = dW;
+      if (io.step_logps) io.step_logps[(k - 1) * io.n + s.gid] = lp;
+      if (io.positions && (k % io.pos_stride) == 0) io.positions[(k / io.pos_stride) * io.n + s.gid] = x;
+    }
+  }
+  s.x = x; s.z = z; s.lp = lp; s.Wt = Wt; s.LPt = LPt;
+}
 
 // PIN: hold the per-step constants in registers.  ptxas otherwise re-reads them from the constant bank every
 // iteration (13 LDCU per step in the STRICT loop, 3 % of its issue slots); passing them through an opaque
@@ -394,7 +510,7 @@ __device__ __forceinline__ void langevin_chunk(const LangevinConsts& c_in, const
         fast_step<POT>(c, x, rng.next(), r_eq, z);
       } else {
         land.eval(c, x);
-        brownian_apply<POT, FAST>(c, land, x, rng.next(), r_eq, z, lp);
+        brownian_apply_any<POT, FAST>(c, land, x, normal_from_bits<FAST>(rng.next()), r_eq, z, lp);
       }
     }
     if (RECORD && io.positions && live) io.positions[gid] = x;      // positions[0] = x_eq  :142
@@ -436,67 +552,15 @@ __device__ __forceinline__ void langevin_chunk(const LangevinConsts& c_in, const
     }
     __syncthreads();
     float Wt = 0.f, LPt = 0.f;
-    uint32_t r_addr = (uint32_t)__cvta_generic_to_shared(r_s);
-    uint32_t phi_addr = (uint32_t)__cvta_generic_to_shared(phi_s);
-    uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(tab_s);
-#pragma unroll kUnroll
-    for (int i = 0; i < len; ++i, r_addr += 4, phi_addr += 4 * DPS, tab_addr += 16) {
-      if (RECORD && io.ckpt_x) {  // checkpoint BEFORE step k = t0+i when (k-1) % ckpt_every == 0
-        const long long k = t0 + i;
-        if ((k - 1) % io.ckpt_every == 0 && live) {
-          const long long q = (k - 1) / io.ckpt_every;
-          io.ckpt_x[q * io.n + gid] = x;
-          uint32_t* dst = io.ckpt_rng + q * 4 * io.n + gid;
-          dst[0] = rng.k0; dst[io.n] = rng.k1; dst[2 * io.n] = rng.s0; dst[3 * io.n] = rng.s1;
-        }
-      }
-      float dW, dR;
-      const float x_before = x;
-      if (FAST) {
-        const float4 tab = lds_f32x4(tab_addr);
-        dW = fmaf(tab.y, x, tab.z);
-        dR = fast_step<POT>(c, x, rng.next(), tab.x, z);
-        if (RECORD) lp = fmaf(-0.5f * z, z, -c.log_norm);
-      } else {
-        const float r_prev = lds_f32(r_addr), r_cur = lds_f32(r_addr + 4);
-        land.eval(c, x);
-        dW = work_increment<POT, FAST>(c, land, x, r_prev, r_cur);
-        dR = brownian_apply<POT, FAST>(c, land, x, rng.next(), r_cur, z, lp);
-      }
-      Wt += dW;
-      if (FAST && !RECORD) {
-        LPt = fmaf(z, z, LPt);  // sum of z^2; turned into the log-prob sum at the end of the tile
-      } else {
-        LPt += lp;
-      }
-      if (GRAD) {
-        // d logp_k / d r_k = z * ca and d W / d r_k = k_s * dR: the constant factors are applied
-        // once, after the trajectory
-        // d W / d r_k = -k_s (x_{k-1} - r_k) + k_s (x_k - r_k) = k_s (x_k - x_{k-1}); that is k_s dR unless a
-        // periodic shift wrapped the position
-        const float a = z, b = c.shift_kind == NQ_SHIFT_PERIODIC ? x - x_before : dR;
-#pragma unroll
-        for (int q = 0; q < DPS / 4; ++q) {
-          const float4 p = lds_f32x4(phi_addr + 16 * q);
-          const float pv[4] = {p.x, p.y, p.z, p.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (4 * q + e < D) {
-              gA[4 * q + e] = fmaf(a, pv[e], gA[4 * q + e]);
-              gB[4 * q + e] = fmaf(b, pv[e], gB[4 * q + e]);
-            }
-          }
-        }
-      }
-      if (RECORD && live) {
-        const long long k = t0 + i;
-        if (io.step_works) io.step_works[k * io.n + gid] = dW;
-        if (io.step_logps) io.step_logps[(k - 1) * io.n + gid] = lp;
-        if (io.positions && (k % io.pos_stride) == 0) io.positions[(k / io.pos_stride) * io.n + gid] = x;
-      }
-    }
+    StepCtx<POT, FAST, D> ctx{c, io, x, rng, land, z, lp, gA, gB, Wt, LPt, gid, live};
+    const uint32_t r_addr = (uint32_t)__cvta_generic_to_shared(r_s);
+    const uint32_t phi_addr = (uint32_t)__cvta_generic_to_shared(phi_s);
+    const uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(tab_s);
+    // the shift kind is uniform over the launch: one branch per tile selects the loop specialised for it
+    if (c.shift_kind == NQ_SHIFT_PERIODIC) tile_steps<POT, FAST, D, RECORD, true>(ctx, t0, len, r_addr, phi_addr, tab_addr);
+    else tile_steps<POT, FAST, D, RECORD, false>(ctx, t0, len, r_addr, phi_addr, tab_addr);
     W += (double)Wt;   // two-level accumulation: f32 within a tile, binary64 across tiles
-    if (FAST && !RECORD) {
+    if (!RECORD) {
       LP += -0.5 * (double)LPt - (double)len * (double)c.log_norm;
     } else {
       LP += (double)LPt;
@@ -664,7 +728,7 @@ __global__ void __launch_bounds__(kPairThreads) langevin_pair_kernel(const Lange
         fast_step_z<POT>(c, x, next_z(), r_eq);
       } else {
         land.eval(c, x);
-        brownian_apply_xi<POT, FAST>(c, land, x, next_z(), r_eq, z, lp);
+        brownian_apply_any<POT, FAST>(c, land, x, next_z(), r_eq, z, lp);
       }
     }
   }
@@ -707,14 +771,10 @@ __global__ void __launch_bounds__(kPairThreads) langevin_pair_kernel(const Lange
         const float r_prev = lds_f32(r_addr), r_cur = lds_f32(r_addr + 4);
         land.eval(c, x);
         dW = work_increment<POT, FAST>(c, land, x, r_prev, r_cur);
-        dR = brownian_apply_xi<POT, FAST>(c, land, x, next_z(), r_cur, z, lp);
+        dR = brownian_apply_any<POT, FAST>(c, land, x, next_z(), r_cur, z, lp);
       }
       Wt += dW;
-      if (FAST) {
-        LPt = fmaf(z, z, LPt);
-      } else {
-        LPt += lp;
-      }
+      LPt = fmaf(z, z, LPt);   // as in tile_steps
       if (pos_out && live) {
         const long long k = t0 + i;
         if (k % io.pos_stride == 0) pos_out[(k / io.pos_stride) * io.n] = x;
@@ -736,11 +796,7 @@ __global__ void __launch_bounds__(kPairThreads) langevin_pair_kernel(const Lange
       }
     }
     W += (double)Wt;
-    if (FAST) {
-      LP += -0.5 * (double)LPt - (double)len * (double)c.log_norm;
-    } else {
-      LP += (double)LPt;
-    }
+    LP += -0.5 * (double)LPt - (double)len * (double)c.log_norm;
   }
 #pragma unroll
   for (int j = 0; j < DA; ++j) {
@@ -896,7 +952,7 @@ __global__ void __launch_bounds__(128) replay_kernel(const LangevinConsts c, con
       fast_step<POT>(c, x, rng.next(), r_cur, z);
     } else {
       land.eval(c, x);
-      brownian_apply<POT, FAST>(c, land, x, rng.next(), r_cur, z, lp);
+      brownian_apply_any<POT, FAST>(c, land, x, normal_from_bits<FAST>(rng.next()), r_cur, z, lp);
     }
     // dW_k = E(x_{k-1}; r_k) - E(x_{k-1}; r_{k-1}):  d/dr_k = -k_s (x_{k-1} - r_k), d/dr_{k-1} = +k_s (x_{k-1} - r_{k-1})
     double g_cur = (double)lb * (double)(z * c.ca) - (double)wb * (double)(c.k_s * (x_before - r_cur));
@@ -936,7 +992,7 @@ __global__ void __launch_bounds__(kThreads) stationary_kernel(const LangevinCons
       fast_step<POT>(c, x, rng.next(), r0, z);
     } else {
       land.eval(c, x);
-      brownian_apply<POT, FAST>(c, land, x, rng.next(), r0, z, lp);
+      brownian_apply_any<POT, FAST>(c, land, x, normal_from_bits<FAST>(rng.next()), r0, z, lp);
     }
     if (positions) positions[s * n + gid] = x;
   }
@@ -960,7 +1016,7 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const LangevinConsts c,
     lp = fmaf(-0.5f * z, z, -c.log_norm);
   } else {
     land.eval(c, x);
-    brownian_apply<POT, FAST>(c, land, x, bits, r0, z, lp);
+    brownian_apply_any<POT, FAST>(c, land, x, normal_from_bits<FAST>(bits), r0, z, lp);
   }
   x_io[gid] = x;
   rng_io[2 * gid] = n0;

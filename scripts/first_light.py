@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from noneq_opt_b200 import _lib, barrier_crossing as bc, random as nqr, space  # noqa: E402
+from noneq_opt_b200 import _devlib, _lib, barrier_crossing as bc, random as nqr, space  # noqa: E402
 from oracle import jaxlike as J, langevin_ref as L  # noqa: E402
 
 res = {}
@@ -94,11 +94,11 @@ for threads in (256, 1024):
     cyc = torch.zeros(blocks, dtype=torch.int64, device=dev)
     sink = torch.zeros(4, dtype=torch.int32, device=dev)
     for rep in range(2):
-      _lib.check(lib.nq_microbench(w, blocks, threads, iters, _lib.ptr(cyc), _lib.ptr(sink), None))
+      _lib.check(_devlib.lib().nqdev_microbench(w, blocks, threads, iters, _lib.ptr(cyc), _lib.ptr(sink), None))
       torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    _lib.check(lib.nq_microbench(w, blocks, threads, iters, _lib.ptr(cyc), _lib.ptr(sink), None))
+    _lib.check(_devlib.lib().nqdev_microbench(w, blocks, threads, iters, _lib.ptr(cyc), _lib.ptr(sink), None))
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)

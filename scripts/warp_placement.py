@@ -2,12 +2,12 @@
 import os, sys, collections
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from noneq_opt_b200 import _lib
+from noneq_opt_b200 import _devlib, _lib
 lib = _lib.lib()
 for blocks, threads in ((1563, 64), (1776, 64), (782, 128), (888, 128)):
   out = torch.zeros(blocks, dtype=torch.int64, device='cuda')
   sink = torch.zeros(4, dtype=torch.int32, device='cuda')
-  _lib.check(lib.nq_microbench(12, blocks, threads, 200, _lib.ptr(out), _lib.ptr(sink), None))
+  _lib.check(_devlib.lib().nqdev_microbench(12, blocks, threads, 200, _lib.ptr(out), _lib.ptr(sink), None))
   torch.cuda.synchronize()
   v = out.cpu().numpy()
   per_sm = collections.Counter(); per_smsp = collections.Counter()
