@@ -89,6 +89,8 @@ template <int POT, bool FAST>
 struct Landscape {
   float ul, ur, A, B, sAB;
   float g, lg;   // STRICT: -(1/beta) / (A + B) and log(A + B)
+  // CHECKED = false: the caller tests in_window() itself, after its straight-line code (hot loops)
+  template <bool CHECKED = true>
   __device__ __forceinline__ void eval(const LangevinConsts& c, float x) {
     if (POT == NQ_POT_SPRING) return;
     if (POT == NQ_POT_BIOMOLECULE) {
@@ -104,17 +106,21 @@ struct Landscape {
     B = fexp<FAST>(-v);
     sAB = fadd<FAST>(A, B);
     if (!FAST) {
-      // one operand check serves both the quotient of the force and the logarithm of the energy (whichever
-      // of the two the caller does not use is dead code)
-      if ((__float_as_uint(sAB) - 0x20800000u) < c.guard_span) {
-        g = div_main(-c.inv_beta, sAB);
-        lg = logf_main(sAB);
-      } else {
-        const float2 t = div_log_library(-c.inv_beta, sAB);
-        g = t.x;
-        lg = t.y;
-      }
+      // main paths, no branch (whichever of the two the caller does not use is dead code); callers patch
+      // the result with fix_range() when !in_window()
+      g = div_main(-c.inv_beta, sAB);
+      lg = logf_main(sAB);
+      if (CHECKED && !in_window(c)) fix_range(c);
     }
+  }
+  // STRICT: A + B inside the operand window of div_main / logf_main?  (always true for SPRING)
+  __device__ __forceinline__ bool in_window(const LangevinConsts& c) const {
+    return POT == NQ_POT_SPRING || (__float_as_uint(sAB) - 0x20800000u) < c.guard_span;
+  }
+  __device__ __forceinline__ void fix_range(const LangevinConsts& c) {
+    const float2 t = div_log_library(-c.inv_beta, sAB);
+    g = t.x;
+    lg = t.y;
   }
   __device__ __forceinline__ float Em(const LangevinConsts& c) const {
     return POT == NQ_POT_SPRING ? 0.f : (FAST ? -c.inv_beta * __logf(sAB) : __fmul_rn(-c.inv_beta, lg));
@@ -189,15 +195,24 @@ struct RngPipe {
 
 // One apply_fn (barrier_crossing.py:77-92) given the landscape already evaluated at x and this step's
 // standard-normal draw.  Returns dR; updates x; writes z (standardised noise) and, if WANT_LP, lp.
-template <int POT, bool FAST, bool PERIODIC, bool WANT_LP>
-__device__ __forceinline__ float brownian_apply_xi(const LangevinConsts& c, const Landscape<POT, FAST>& land, float& x,
-                                                   float xi, float r, float& z, float& lp) {
+// HALF of the mean displacement: mean = F * nu * dt (:67-69) = 2 m2
+template <int POT, bool FAST>
+__device__ __forceinline__ float half_mean(const LangevinConsts& c, const Landscape<POT, FAST>& land, float x, float r) {
   // -F / 2 = (dEm/dx)/2 + (k_s/2)(x - r); the reference forms dEs = (k_s/2) * (2 (x - r)), see half_dEm
   const float es = fmul<FAST>(c.hk, fsub<FAST>(x, r));
   const float q = POT == NQ_POT_SPRING ? es : fadd<FAST>(land.half_dEm(c), es);
-  // mean = F * nu * dt (:67-69) = 2 m2;  dR = sampled * scale + loc (:88) in one rounding of xi sigma + 2 m2
-  const float m2 = FAST ? -q * c.nudt : __fmul_rn(__fmul_rn(-q, c.nu), c.dt);
-  const float dR = FAST ? fmaf(2.0f, m2, xi * c.sigma) : __fmaf_rn(2.0f, m2, __fmul_rn(xi, c.sigma));
+  return FAST ? -q * c.nudt : __fmul_rn(__fmul_rn(-q, c.nu), c.dt);
+}
+// dR = sampled * scale + loc (:88) in one rounding of xi sigma + 2 m2
+template <bool FAST>
+__device__ __forceinline__ float kick(const LangevinConsts& c, float m2, float xi) {
+  return FAST ? fmaf(2.0f, m2, xi * c.sigma) : __fmaf_rn(2.0f, m2, __fmul_rn(xi, c.sigma));
+}
+
+template <int POT, bool FAST, bool PERIODIC, bool WANT_LP>
+__device__ __forceinline__ float brownian_apply_xi(const LangevinConsts& c, const Landscape<POT, FAST>& land, float& x,
+                                                   float xi, float r, float& z, float& lp) {
+  const float dR = kick<FAST>(c, half_mean<POT, FAST>(c, land, x, r), xi);
   // Normal.log_prob's z = x/scale - loc/scale equals xi up to one rounding of dR: using xi changes
   // each log-prob by < 1e-6 absolute (tolerance 1e-5 relative of ~9) and is 7 instructions cheaper
   // than two correctly rounded quotients; the position and work paths stay in reference order.
@@ -367,9 +382,9 @@ constexpr int pad4(int D) { return (D + 3) / 4 * 4; }
 constexpr int state_words(int D) { return 9 + 2 * (D > 0 ? D : 1); }
 
 // The steps of one staged tile (r_s / phi_s / tab_s hold steps t0 .. t0 + len - 1).  Per step: work increment at
-// the position before the kick, the kick, log-prob and gradient moments.  Without RECORD the log-prob sum is
-// carried as sum(z^2) (one FMA per step) and turned into sum(-z^2/2 - log_norm) per tile in binary64 -- at
-// least as accurate as summing the reference's rounded per-step terms; RECORD emits those terms themselves.
+// the position before the kick, the kick, log-prob and gradient moments.  The log-prob sum is carried as
+// sum(z^2) (one FMA per step) and turned into sum(-z^2/2 - log_norm) per tile in binary64 -- at least as
+// accurate as summing the reference's rounded per-step terms, which RECORD emits on the side.
 template <int POT, bool FAST, int D>
 struct StepCtx {
   const LangevinConsts& c;
@@ -414,17 +429,33 @@ __device__ __forceinline__ void tile_steps(StepCtx<POT, FAST, D>& s, long long t
       dR = fast_step<POT, PERIODIC ? 1 : 0>(c, x, s.rng.next(), tab.x, z);
       if (RECORD) lp = fmaf(-0.5f * z, z, -c.log_norm);
     } else {
+      // One straight-line block: key chain, central-range normal draw, landscape on the main paths, work
+      // increment, mean -- no branch, so ptxas interleaves the three threefry blocks with the dependent
+      // floating-point chains.  The two rare cases -- a draw in erf_inv's tail range (0.3 % of the lanes) and
+      // A + B outside the main-path window (never, for physical parameters) -- are patched afterwards.
       const float r_prev = lds_f32(r_addr), r_cur = lds_f32(r_addr + 4);
-      s.land.eval(c, x);
+      const float u = uniform_pm1_from_bits(s.rng.next());
+      const float w = erfinv_w<false>(u);
+      z = __fmul_rn(1.41421356237309504880f, __fmul_rn(erfinv_poly_central<false>(w), u));
+      asm volatile("" : "+f"(z));   // keep the central polynomial in the straight-line block (the compiler would sink it into the w < 5 arm)
+      s.land.template eval<false>(c, x);
       dW = work_increment<POT, FAST>(c, s.land, x, r_prev, r_cur);
-      dR = brownian_apply<POT, FAST, PERIODIC, RECORD>(c, s.land, x, s.rng.next(), r_cur, z, lp);
+      float m2 = half_mean<POT, FAST>(c, s.land, x, r_cur);
+      if (!(w < 5.0f) || !s.land.in_window(c)) {
+        if (!(w < 5.0f)) z = __fmul_rn(1.41421356237309504880f, __fmul_rn(erfinv_poly_tail<false>(w), u));
+        if (!s.land.in_window(c)) {
+          s.land.fix_range(c);
+          dW = work_increment<POT, FAST>(c, s.land, x, r_prev, r_cur);
+          m2 = half_mean<POT, FAST>(c, s.land, x, r_cur);
+        }
+      }
+      dR = kick<FAST>(c, m2, z);
+      if (RECORD) lp = __fsub_rn(__fmul_rn(-0.5f, __fmul_rn(z, z)), c.log_norm);
+      x = __fadd_rn(x, dR);
+      if (PERIODIC) x = py_mod(x, c.box);
     }
     Wt += dW;
-    if (!RECORD) {
-      LPt = fmaf(z, z, LPt);  // sum of z^2; turned into the log-prob sum at the end of the tile
-    } else {
-      LPt += lp;
-    }
+    LPt = fmaf(z, z, LPt);  // sum of z^2; turned into the log-prob sum at the end of the tile
     if (GRAD) {
       // d logp_k / d r_k = z * ca and d W / d r_k = k_s * dR: the constant factors are applied
       // once, after the trajectory
@@ -560,11 +591,7 @@ __device__ __forceinline__ void langevin_chunk(const LangevinConsts& c_in, const
     if (c.shift_kind == NQ_SHIFT_PERIODIC) tile_steps<POT, FAST, D, RECORD, true>(ctx, t0, len, r_addr, phi_addr, tab_addr);
     else tile_steps<POT, FAST, D, RECORD, false>(ctx, t0, len, r_addr, phi_addr, tab_addr);
     W += (double)Wt;   // two-level accumulation: f32 within a tile, binary64 across tiles
-    if (!RECORD) {
-      LP += -0.5 * (double)LPt - (double)len * (double)c.log_norm;
-    } else {
-      LP += (double)LPt;
-    }
+    LP += -0.5 * (double)LPt - (double)len * (double)c.log_norm;
   }
   if (!last) {
     if (live) {

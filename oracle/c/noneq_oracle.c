@@ -309,8 +309,10 @@ static void masked_update(int8_t* s, int L, float log_temp, float field, int par
 }
 
 /* simulate_ising for R replicas; summary [R][7][T-1]; spins int8 +-1 */
+// snaps (nullable): [R][n_snap][L*L] lattices after sweeps snap_t[0..n_snap) (1-based sweep index t, ascending)
 void oracle_ising(int L, int T, long R, const float* log_temp, const float* field, const int8_t* spins0,
-                  int broadcast0, const uint32_t* seeds, int8_t* final_spins, float* summary) {
+                  int broadcast0, const uint32_t* seeds, int8_t* final_spins, float* summary, int n_snap,
+                  const int* snap_t, int8_t* snaps) {
   const int N = L * L;
 #pragma omp parallel
   {
@@ -343,6 +345,9 @@ void oracle_ising(int L, int T, long R, const float* log_temp, const float* fiel
         out[4 * (T - 1) + t - 1] = F(fwd - rev);
         out[5 * (T - 1) + t - 1] = (float)(m / N);
         out[6 * (T - 1) + t - 1] = e_fin;
+        if (snaps)
+          for (int q = 0; q < n_snap; ++q)
+            if (snap_t[q] == t) memcpy(snaps + ((size_t)rep * n_snap + q) * N, s, N);
       }
       if (final_spins) memcpy(final_spins + rep * N, s, N);
     }

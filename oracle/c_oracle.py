@@ -59,8 +59,9 @@ def langevin(pot, r, phi, x0, seeds, S, Neq, dt, kT, gamma, mass, shift='free', 
   return dict(work=work, logp=logp, grad_sums=grad[:, :D], positions=pos)
 
 
-def ising(log_temp, field, spins0, seeds):
-  """spins0 [L, L] (shared) or [R, L, L]; seeds [R, 2].  Returns (final int8 [R, L, L], summary [R, 7, T-1])."""
+def ising(log_temp, field, spins0, seeds, snapshots=None):
+  """spins0 [L, L] (shared) or [R, L, L]; seeds [R, 2].  Returns (final int8 [R, L, L], summary [R, 7, T-1]);
+  with snapshots = ascending sweep indices t (1 .. T-1) also the lattices after those sweeps, int8 [R, len, L, L]."""
   log_temp = np.ascontiguousarray(log_temp, np.float32)
   field = np.ascontiguousarray(field, np.float32)
   seeds = np.ascontiguousarray(seeds, np.uint32).reshape(-1, 2)
@@ -69,7 +70,10 @@ def ising(log_temp, field, spins0, seeds):
   L = s0.shape[-1]
   final = np.zeros((R, L, L), np.int8)
   summary = np.zeros((R, 7, T - 1), np.float32)
+  snap_t = None if snapshots is None else np.ascontiguousarray(snapshots, np.int32)
+  snaps = None if snapshots is None else np.zeros((R, len(snap_t), L, L), np.int8)
   lib().oracle_ising(C.c_int(L), C.c_int(T), C.c_long(R), _p(log_temp, C.c_float), _p(field, C.c_float),
                      _p(s0, C.c_int8), C.c_int(int(s0.ndim == 2)), _p(seeds, C.c_uint32), _p(final, C.c_int8),
-                     _p(summary, C.c_float))
-  return final, summary
+                     _p(summary, C.c_float), C.c_int(0 if snap_t is None else len(snap_t)), _p(snap_t, C.c_int),
+                     _p(snaps, C.c_int8))
+  return (final, summary) if snapshots is None else (final, summary, snaps)
