@@ -42,6 +42,7 @@ C2_COEFFS = np.array([2.00000000e+01, 1.99599600e+01, -2.63245988e-15, 8.4148423
                       -7.47209997e-15, -1.69086360e-14, 1.27892999e-14, 3.02606960e-15, -6.05805446e-15,
                       -6.36600761e-16, -5.53701086e-15, -1.14938537e-14], np.float32)
 C2_B, C2_S = 100_000, 10_000
+C5_B = 10_000_000                # configs[4]: the same path, 10^7 trajectories sharded over the GPUs
 INSTR_PER_TRAJ_STEP = 326.0      # 3 threefry blocks (219 INT) + ~75 FP32 + ~6 SFU + 2*13 FFMA
 INSTR_PER_SPIN_UPDATE = 47.0     # half a threefry block (36.5) + ~10 logic/compare/popc
 ISSUE_PEAK = 148 * 128 * 1.965e9  # thread-instructions/s at max SM clock
@@ -183,9 +184,12 @@ def run_reference(args):
   if rank != 0:
     return
   from oracle import c_oracle, jaxlike as J, langevin_ref as L
+  # every core of the host, at every --gpus N: torchrun exports OMP_NUM_THREADS=1 to its workers, which made the
+  # N > 1 reference arms of round 1 run on ONE core.  The OpenMP team is set explicitly instead.
+  cores = c_oracle.use_all_cores()
   pot = L.V_biomolecule_shifted(KAPPA, KAPPA, X_M, 0., K_TRAP, BETA)
   r, phi = L.make_schedule_chebyshev(C2_S, C2_COEFFS, 0., 40.)
-  n = 1024 * c_oracle.max_threads()
+  n = 1024 * cores
   seeds = J.split(J.PRNGKey(0), C2_B)[:n]
   x0 = np.zeros(n, np.float32)
   times = []
@@ -196,14 +200,16 @@ def run_reference(args):
       times.append(time.perf_counter() - t0)
   ms = 1e3 * float(np.mean(times))
   value = n * C2_S / (ms * 1e-3)
-  cores = c_oracle.max_threads()
+  assert c_oracle.max_threads() == cores
   line = dict(impl='reference', metric='langevin_traj_steps_per_s', value=value, unit='traj-steps/s',
               n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True,
               scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
               config=workload_config(args.gpus),
               cpu_baseline=dict(value=value, unit='traj-steps/s', cores=cores, kind='port',
                                 sample=f'{n} of {C2_B} trajectories x {C2_S} steps per step, C/OpenMP oracle port '
-                                       '(JAX itself is not installable here)'),
+                                       '(JAX itself is not installable here)',
+                                normalisation='whole host: the same all-core CPU rate at every --gpus N (the host does '
+                                              'not grow with N); divide the native value by n_gpus for a per-GPU ratio'),
               e2e=dict(value=value, unit='traj-steps/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
   print(json.dumps(line), flush=True)
 
@@ -305,12 +311,43 @@ def run_native(args):
   ms, launches, clocks, (grad, mom) = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
   units = float(B_global) * C2_S
   value = units / (ms * 1e-3)
+  if args.no_extras:     # kernel variants (scripts/variant_strict.sh): the device-resident leg only
+    if rank == 0:
+      print(json.dumps(dict(metric='langevin_traj_steps_per_s', value=value, ms_per_step=ms, math_mode=args.math,
+                            n_gpus=ws, mean_work=float(mom[1] / mom[0]))), flush=True)
+    if ws > 1:
+      dist.barrier()
+      dist.destroy_process_group()
+    return
   ms_e2e, _, _, grad_e2e = timed(step_e2e, max(3, args.steps // 2), 2)
   e2e_value = units / (ms_e2e * 1e-3)
   other = 'fast' if args.math == 'strict' else 'strict'
   bc.set_math_mode(other)
   ms_other, _, _, (grad_other, mom_other) = timed(step_resident, max(3, args.steps // 2), 2)
   bc.set_math_mode(args.math)
+
+  # ---- configs[4]: 10^7 trajectories x 10^4 steps SHARDED over the ranks (strong scaling), one all-reduce
+  c5 = None
+  if not args.no_config5:
+    B5 = C5_B
+    f5, n5 = nqd.shard_range(B5, rank, ws)
+    seeds5 = nqr.split(seed, B5, first=f5, count=n5)
+    x5 = bc._stationary_final(pot, np.zeros((1, 1), np.float32), 0.0, shift, nqr.split(eq_key, B5, f5, n5), 1000, DT, KT,
+                              GAMMA).reshape(-1).contiguous()
+
+    def step_c5():
+      out = bc._simulate(pot, shift, r_dev, phi_dev, x5, seeds5, C2_S, 0, DT, KT, 1.0, GAMMA)
+      if ws > 1:
+        dist.all_reduce(out['sums_flat'], op=dist.ReduceOp.SUM)
+      gs, mom5 = out['grad_sums'], out['moments']
+      return (gs[0] + gs[1]) / B5, mom5
+    ms5, _, _, (grad5, mom5) = timed(step_c5, 2, 1)
+    c5 = dict(workload=f'configs[4]: {B5} trajectories x {C2_S} steps sharded contiguously over {ws} GPU(s) '
+                       f'({n5} per rank), positions not recorded, one all-reduce of [2 x 13 gradient sums | 8 moments]',
+              scaling='strong', value=float(B5) * C2_S / (ms5 * 1e-3), unit='traj-steps/s', ms_per_step=ms5,
+              per_gpu=float(B5) * C2_S / (ms5 * 1e-3) / ws, steps=2, warmup=1,
+              check=dict(n=float(mom5[0]), mean_work=float(mom5[1] / mom5[0]), grad0=float(grad5[0])))
+    del seeds5, x5
 
   line = None
   if rank == 0:
@@ -339,6 +376,7 @@ def run_native(args):
                          '(= barrier_crossing.estimate_gradient_boltzinit per rank)'),
                 roofline=roofline,
                 check=dict(mean_work=float(mom[1] / mom[0]), grad0=float(grad[0]), grad0_e2e=float(grad_e2e[0])),
+                config5=c5,
                 other_math_mode={'math_mode': other, 'value': units / (ms_other * 1e-3), 'ms_per_step': ms_other,
                                  'mean_work': float(mom_other[1] / mom_other[0]), 'grad0': float(grad_other[0]),
                                  'note': 'strict = reference operation order (parity-certified, default); fast = MUFU/FMA '
@@ -352,6 +390,10 @@ def run_native(args):
       line['config1_training'] = bench_config1_training(dev)
     if ws == 1 and not args.no_cpu:
       line['cpu_baseline'] = cpu_baseline()
+      if not args.no_ising:
+        cpu_i = cpu_baseline_ising()
+        line['ising']['c3_64x64_4096rep_1000sweeps_grad']['cpu_baseline'] = cpu_i['c3']
+        line['ising']['c4_1024x1024_256rep']['cpu_baseline'] = cpu_i['c4']
     print(json.dumps(line), flush=True)
   if ws > 1:
     dist.barrier()
@@ -403,11 +445,23 @@ def bench_config1_training(dev):
               note='latency-bound: 32 CTAs of one producer + one consumer warp (DESIGN.md 4.1, 4.5)')
 
 
+def ising_instr_per_update():
+  """Executed thread-instructions per spin-update of the two Ising kernels, from the committed `ncu --set full`
+  summaries (profiles/ising_instr_per_update.json is written next to them by scripts/summarize_ncu.py)."""
+  try:
+    return json.load(open(os.path.join(ROOT, 'profiles', 'ising_instr_per_update.json')))
+  except Exception:
+    return {}
+
+
 def bench_ising(args, dev, rank, ws):
+  """Spin-updates/s at configs[2] (with the REINFORCE gradient) and configs[3]; per config: the device-resident
+  rate, the end-to-end rate through the public API with HOST buffers, and the issue roofline."""
   import torch
   import torch.distributed as dist
   from noneq_opt_b200 import ising, parameterization as p10n, random as nqr
   out = {}
+  measured = ising_instr_per_update()
 
   def schedule(D, weights):
     return ising.IsingSchedule(
@@ -433,47 +487,119 @@ def bench_ising(args, dev, rank, ws):
       dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item()) / steps
 
+  def roofline(per_gpu, key):
+    m = measured.get(key, {})
+    return dict(bound='issue', kernel=m.get('kernel', 'ising_fast_kernel'), achieved=per_gpu * INSTR_PER_SPIN_UPDATE / 1e12,
+                peak=ISSUE_PEAK / 1e12, unit='Tinstr/s (thread-instructions)', frac=per_gpu * INSTR_PER_SPIN_UPDATE / ISSUE_PEAK,
+                algorithmic_instr_per_update=INSTR_PER_SPIN_UPDATE, executed_instr_per_update=m.get('instr_per_update'),
+                executed_alu_instr_per_update=m.get('alu_instr_per_update'), source=m.get('source'),
+                note='issue-bound (half a threefry2x32-20 block per spin-update); lattice resident in shared memory, '
+                     'HBM touched at start / end and for 44 B of summaries per replica-sweep')
+
   # config 3: 64x64, 4096 replicas/GPU, T = 1001, REINFORCE gradient of total entropy production
   L, R, T = 64, 4096, 1001
   w = (0.1 * np.random.RandomState(0).normal(size=(2, 16))).astype(np.float32)
   sched = schedule(16, w)
   times = np.linspace(0, 1, T, dtype=np.float32)
   spins0 = -torch.ones((L, L), dtype=torch.float32, device=dev)
-  first, count = rank * R, R
-  seeds = nqr.split(nqr.PRNGKey(0), R * ws, first=first, count=count)
+  seeds = nqr.split(nqr.PRNGKey(0), R * ws, first=rank * R, count=R)
   est = ising.estimate_gradient_rev(ising.total_entropy_production)
-  ms = timed(lambda: est(sched, times, spins0, seeds), 3, 1)
+  ms = timed(lambda: est(sched, times, spins0, seeds), 5, 2)
   upd = float(R * ws) * (T - 1) * L * L
-  out['c3_64x64_4096rep_1000sweeps_grad'] = dict(spin_updates_per_s=upd / (ms * 1e-3), ms_per_step=ms,
-                                                 per_gpu=upd / ws / (ms * 1e-3),
-                                                 roofline_frac_issue=upd / ws / (ms * 1e-3) * INSTR_PER_SPIN_UPDATE / ISSUE_PEAK)
-  # config 4: 1024x1024 bit-packed, 256 replicas/GPU; 100 sweeps per step (throughput is per sweep)
-  L, R, T = 1024, 256, 101
+  # end to end: host lattice + host keys in, host gradient + per-replica loss terms out
+  spins0_h = -np.ones((L, L), np.float32)
+  seeds_h = seeds.cpu().numpy()
+  h2d = spins0_h.nbytes + seeds_h.nbytes + 2 * 16 * 4
+
+  def c3_e2e():
+    grad, summ = est(sched, times, spins0_h, seeds_h)
+    g = np.concatenate([grad.log_temp.wrapped.wrapped.weights.cpu().numpy().reshape(-1),
+                        grad.field.wrapped.wrapped.weights.cpu().numpy().reshape(-1)])
+    return g, summ.entropy_production.sum(-1).cpu().numpy()
+  g3, ep3 = c3_e2e()
+  d2h = g3.nbytes + ep3.nbytes
+  ms_e = timed(c3_e2e, 5, 1)
+  out['c3_64x64_4096rep_1000sweeps_grad'] = dict(
+      spin_updates_per_s=upd / (ms * 1e-3), ms_per_step=ms, per_gpu=upd / ws / (ms * 1e-3), steps=5, warmup=2,
+      e2e=dict(value=upd / (ms_e * 1e-3), unit='spin-updates/s', ms_per_step=ms_e, h2d_bytes_per_step=h2d,
+               d2h_bytes_per_step=d2h, api='noneq_opt_b200.ising.estimate_gradient_rev(total_entropy_production) with numpy '
+               'lattice and keys in, per-replica gradients and entropy production back on the host'),
+      roofline=roofline(upd / ws / (ms * 1e-3), 'c3'), roofline_frac_issue=upd / ws / (ms * 1e-3) * INSTR_PER_SPIN_UPDATE / ISSUE_PEAK)
+
+  # config 4: 1024x1024 bit-packed, 256 replicas/GPU, 1000 of the 10 000 sweeps per step (throughput is per sweep)
+  L, R, T = 1024, 256, 1001
   sched0 = schedule(16, np.zeros((2, 16), np.float32))
-  times = np.linspace(0, 1, T, dtype=np.float32)
+  times = np.linspace(0, 1, 10001, dtype=np.float32)[:T]
   params = sched0(times)
   spins0 = ising.random_spins([L, L], 0.5, nqr.PRNGKey(1))
   seeds = nqr.split(nqr.PRNGKey(0), R * ws, first=rank * R, count=R)
   log_temp, field, spins, L_, batched, seeds_t, broadcast, bits = ising._prepare(params, spins0, seeds)
-  ms = timed(lambda: ising._run_kernel(log_temp, field, bits, broadcast, seeds_t, L), 2, 1)
+  ms = timed(lambda: ising._run_kernel(log_temp, field, bits, broadcast, seeds_t, L), 5, 1)
   upd = float(R * ws) * (T - 1) * L * L
+  spins0_h = spins0.cpu().numpy()
+  seeds_h = seeds.cpu().numpy()
+
+  def c4_e2e():
+    final, summ = ising.simulate_ising(params, spins0_h, seeds_h)
+    return summ.energy[:, -1].cpu().numpy(), summ.magnetization[:, -1].cpu().numpy()
+  e4, m4 = c4_e2e()
+  ms_e = timed(c4_e2e, 3, 0)
   peaks = measured_peaks()
   hbm_peak = peaks['hbm_gbs'] if peaks else 6650.0
-  out['c4_1024x1024_256rep'] = dict(spin_updates_per_s=upd / (ms * 1e-3), ms_per_step=ms, sweeps_per_step=T - 1,
-                                    per_gpu=upd / ws / (ms * 1e-3),
-                                    roofline_frac_issue=upd / ws / (ms * 1e-3) * INSTR_PER_SPIN_UPDATE / ISSUE_PEAK,
-                                    hbm_gbs_if_streamed=upd / ws / (ms * 1e-3) * 0.375 / 1e9,
-                                    hbm_frac_if_streamed=upd / ws / (ms * 1e-3) * 0.375 / 1e9 / hbm_peak,
-                                    note='lattice is shared-memory resident for the whole trajectory: HBM is touched '
-                                         'only at start/end (0.375 B/update is the streamed-design figure of SURVEY 8d)')
+  out['c4_1024x1024_256rep'] = dict(
+      spin_updates_per_s=upd / (ms * 1e-3), ms_per_step=ms, sweeps_per_step=T - 1, per_gpu=upd / ws / (ms * 1e-3),
+      steps=5, warmup=1,
+      e2e=dict(value=upd / (ms_e * 1e-3), unit='spin-updates/s', ms_per_step=ms_e,
+               h2d_bytes_per_step=spins0_h.nbytes + seeds_h.nbytes + 2 * T * 4, d2h_bytes_per_step=e4.nbytes + m4.nbytes,
+               api='noneq_opt_b200.ising.simulate_ising with a numpy lattice and keys in (unpacked [R, L, L] final '
+                   'lattices stay on the device), final energy and magnetisation back on the host'),
+      roofline=roofline(upd / ws / (ms * 1e-3), 'c4'),
+      roofline_frac_issue=upd / ws / (ms * 1e-3) * INSTR_PER_SPIN_UPDATE / ISSUE_PEAK,
+      hbm_gbs_if_streamed=upd / ws / (ms * 1e-3) * 0.375 / 1e9,
+      hbm_frac_if_streamed=upd / ws / (ms * 1e-3) * 0.375 / 1e9 / hbm_peak,
+      note='lattice is shared-memory resident for the whole trajectory: HBM is touched '
+           'only at start/end (0.375 B/update is the streamed-design figure of SURVEY 8d)')
   out['unit'] = 'spin-updates/s'
   out['target_per_gpu'] = 1e11
+  return out
+
+
+def cpu_baseline_ising():
+  """Oracle port (C/OpenMP over replicas) on bounded samples of configs 3 and 4, all host cores."""
+  from oracle import c_oracle, ising_ref as I, jaxlike as J, parameterization_ref as P
+  cores = c_oracle.use_all_cores()
+  out = {}
+  # config 3: 64^2, T = 1001, 4 replicas per core
+  L, T, R = 64, 1001, 4 * cores
+  w = (0.1 * np.random.RandomState(0).normal(size=(2, 16))).astype(np.float32)
+  times = np.linspace(0, 1, T, dtype=np.float32)
+  lt = P.AddBaseline(P.ConstrainEndpoints(P.Chebyshev(w[0]), 0., 0.), P.log_temp_baseline(0.69, 10, 1))(times)
+  h = P.AddBaseline(P.ConstrainEndpoints(P.Chebyshev(w[1]), 0., 0.), P.field_baseline(-1, 1))(times)
+  seeds = J.split(J.PRNGKey(0), 4096)[:R]
+  s0 = -np.ones((L, L), np.int8)
+  t0 = time.perf_counter()
+  c_oracle.ising(lt, h, s0, seeds)
+  dt = time.perf_counter() - t0
+  out['c3'] = dict(value=R * (T - 1) * L * L / dt, unit='spin-updates/s', cores=cores, kind='port',
+                   sample=f'{R} of 4096 replicas x {T - 1} sweeps of 64^2 (forward + summaries), {dt:.1f} s')
+  # config 4: 1024^2, one replica per core, 6 sweeps
+  L, T, R = 1024, 7, cores
+  times = np.linspace(0, 1, 10001, dtype=np.float32)[:T]
+  lt, h = P.log_temp_baseline(0.69, 10, 1)(times), P.field_baseline(-1, 1)(times)
+  s0 = I.random_spins((L, L), .5, J.PRNGKey(1)).astype(np.int8)
+  seeds = J.split(J.PRNGKey(0), 256)[:R]
+  t0 = time.perf_counter()
+  c_oracle.ising(lt, h, s0, seeds)
+  dt = time.perf_counter() - t0
+  out['c4'] = dict(value=R * (T - 1) * L * L / dt, unit='spin-updates/s', cores=cores, kind='port',
+                   sample=f'{R} of 256 replicas x {T - 1} of 10000 sweeps of 1024^2, {dt:.1f} s')
   return out
 
 
 def cpu_baseline():
   """Oracle port (C/OpenMP) on a bounded sample of config 2, timed on this box's host cores."""
   from oracle import c_oracle, jaxlike as J, langevin_ref as L
+  c_oracle.use_all_cores()
   pot = L.V_biomolecule_shifted(KAPPA, KAPPA, X_M, 0., K_TRAP, BETA)
   r, phi = L.make_schedule_chebyshev(C2_S, C2_COEFFS, 0., 40.)
   n = min(C2_B, 4096 * c_oracle.max_threads())     # ~10 s of CPU work
@@ -496,6 +622,8 @@ def main():
   ap.add_argument('--math', default=os.environ.get('NQ_MATH_MODE', 'strict'), choices=['strict', 'fast'])
   ap.add_argument('--no-ising', action='store_true')
   ap.add_argument('--no-cpu', action='store_true')
+  ap.add_argument('--no-config5', action='store_true')
+  ap.add_argument('--no-extras', action='store_true', help='device-resident Langevin leg only (kernel variant scans)')
   args = ap.parse_args()
   if args.impl == 'reference':
     run_reference(args)

@@ -84,6 +84,7 @@ static NcclAllReduceFn find_nccl_allreduce() {
 }
 
 extern "C" int nq_allreduce_f64(void* nccl_comm, double* buf, int64_t n, void* stream) {
+  NQ_RANGE();
   NQ_CHECK_ARG(nccl_comm != nullptr && buf != nullptr && n >= 1, "need a communicator, a buffer and n >= 1");
   NcclAllReduceFn fn = find_nccl_allreduce();
   if (!fn) {
@@ -100,26 +101,31 @@ extern "C" int nq_allreduce_f64(void* nccl_comm, double* buf, int64_t n, void* s
 
 extern "C" int nq_random_split(const uint32_t key[2], int64_t num, int64_t first, int64_t count, uint32_t* out,
                                void* stream) {
+  NQ_RANGE();
   // split(key, num) = threefry_2x32(key, iota(2*num)).reshape(num, 2)
   return launch_bits<kRawBits>(key, 2 * num, 2 * first, 2 * count, 0.f, 1.f, out, stream);
 }
 
 extern "C" int nq_langevin_keys(const uint32_t seed[2], int64_t B_total, int64_t n0, int64_t n, uint32_t* keys,
                                 void* stream) {
+  NQ_RANGE();
   return nq_random_split(seed, B_total, n0, n, keys, stream);
 }
 
 extern "C" int nq_random_bits(const uint32_t key[2], int64_t size, int64_t first, int64_t count, uint32_t* out,
                               void* stream) {
+  NQ_RANGE();
   return launch_bits<kRawBits>(key, size, first, count, 0.f, 1.f, out, stream);
 }
 
 extern "C" int nq_random_uniform(const uint32_t key[2], int64_t size, int64_t first, int64_t count, float lo,
                                  float hi, float* out, void* stream) {
+  NQ_RANGE();
   return launch_bits<kUniform>(key, size, first, count, lo, hi, out, stream);
 }
 
 extern "C" int nq_random_normal(const uint32_t key[2], int64_t size, int64_t first, int64_t count, float* out,
                                 void* stream) {
+  NQ_RANGE();
   return launch_bits<kNormal>(key, size, first, count, 0.f, 1.f, out, stream);
 }

@@ -107,9 +107,10 @@ struct IsingShape {
   // replica are cut into n_seg segments handed out through a ticket counter, so the last wave is
   // 1/n_seg as long.  Between segments a replica lives in seg_lat / seg_mb.
   int n_seg;
-  unsigned* seg_ctl;     // [0] ticket counter, [1 + r] segments of replica r completed (zeroed per launch)
+  unsigned* seg_ctl;     // [0] ticket counter, [1 + r] segments of replica r completed, [1 + R] status (zeroed per launch)
   long long* seg_mb;     // [R][2] spin sum, bond sum carried between segments
   uint32_t* seg_lat;     // [R][2][L][NW] colour planes carried between segments
+  unsigned seg_max_polls;  // bound of a wait for the previous segment, in polls of 256 ns; 0 = unbounded
 };
 
 struct IsingIO {
@@ -392,14 +393,20 @@ __global__ void __launch_bounds__(WARP_TEAM ? 32 * NQ_ISING_TEAMS : 1024, WARP_T
         // the previous segment of this replica was handed out R tickets ago: it is running or done
         const volatile unsigned* done = sh.seg_ctl + 1 + it % (unsigned)sh.R;
         const unsigned want = it / (unsigned)sh.R;
+        // bounded wait (NQ_WAIT_POLLS; 0 = unbounded): when it runs out the launch is abandoned cleanly --
+        // status word set, every CTA leaves at its next ticket, ising_status_kernel turns the summaries into
+        // NaN -- instead of a __trap() that would poison the caller's CUDA context
+        volatile unsigned* dead = sh.seg_ctl + 1 + sh.R;
         unsigned polls = 0;
+        bool lost = false;
         while (*done < want) {
           __nanosleep(256);
-          if (++polls > (1u << 24)) __trap();  // bounded wait: a lost segment must not hang the device
+          if ((sh.seg_max_polls && ++polls > sh.seg_max_polls) || *dead) { lost = true; break; }
         }
         __threadfence();
+        if (lost) atomicExch(sh.seg_ctl + 1 + sh.R, 1u);
       }
-      ticket_s = it;
+      ticket_s = (it < total && *(volatile unsigned*)(sh.seg_ctl + 1 + sh.R) == 0u) ? it : 0xffffffffu;
     }
     __syncthreads();
     const unsigned it = ticket_s;
@@ -566,6 +573,13 @@ __global__ void __launch_bounds__(WARP_TEAM ? 32 * NQ_ISING_TEAMS : 1024, WARP_T
     atomicExch(&sh.seg_ctl[1 + rep], (unsigned)(seg + 1));
   }
   }
+}
+
+// an abandoned segment-scheduled launch (bounded wait ran out) must not look like a result: NaN summaries
+__global__ void ising_status_kernel(const unsigned* status, float* summary, size_t n) {
+  if (*status == 0u) return;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    summary[i] = __int_as_float(0x7fc00000);
 }
 
 // ------------------------------------------------------------------------------ generic kernel
@@ -947,7 +961,7 @@ static SegPlan plan_segments(int L, long long R, int T) {
   // n never lengthens the schedule (ceil(2Rn/s)/(2n) <= ceil(Rn/s)/n).
   while ((T - 1) / p.n_seg > 512 && 2 * p.n_seg <= T - 1 && R * 2 * p.n_seg < 0x7fffffffll) p.n_seg *= 2;
   p.grid = (int)slots;
-  p.ctl_bytes = (((size_t)R + 1) * 4 + 15) / 16 * 16;
+  p.ctl_bytes = (((size_t)R + 2) * 4 + 15) / 16 * 16;
   p.mb_bytes = (size_t)R * 2 * 8;
   p.lat_bytes = (size_t)R * 2 * L * (L / 64) * 4;
   return p;
@@ -996,6 +1010,7 @@ extern "C" int nq_ising_run(const NqIsingDesc* desc, const uint32_t* thr, const 
                             const float* log_temp, const uint32_t* spins0, const uint32_t* seeds,
                             uint32_t* spins_out, float* summary, float* partials, int32_t* counts, uint32_t* states,
                             void* workspace, size_t workspace_bytes, void* stream) {
+  NQ_RANGE();
   NQ_CHECK_ARG(desc != nullptr, "desc is null");
   int dims[3];
   const int ndim = lattice_dims(desc, dims);
@@ -1016,7 +1031,7 @@ extern "C" int nq_ising_run(const NqIsingDesc* desc, const uint32_t* thr, const 
   NQ_CHECK_ARG(desc->sweep_key_mode == 0 || (desc->sweep_key_mode == 1 && T == 2), "sweep_key_mode 1 needs T == 2");
   const int L = dims[0];
   IsingShape sh{L, L / 64, T, desc->R, desc->spins0_broadcast, desc->sweep_key_mode, ndim, dims[0], dims[1], dims[2],
-                (int)N, nullptr, nullptr, 1u, 1, nullptr, nullptr, nullptr};
+                (int)N, nullptr, nullptr, 1u, 1, nullptr, nullptr, nullptr, 0u};
   IsingIO io{thr, lut, field, log_temp, spins0, seeds, spins_out, summary, partials, counts, states};
   cudaStream_t st = (cudaStream_t)stream;
   const bool square2d = ndim == 2 && dims[0] == dims[1];
@@ -1048,8 +1063,14 @@ extern "C" int nq_ising_run(const NqIsingDesc* desc, const uint32_t* thr, const 
         sh.seg_ctl = (unsigned*)ws;
         sh.seg_mb = (long long*)(ws + plan.ctl_bytes);
         sh.seg_lat = (uint32_t*)(ws + plan.ctl_bytes + plan.mb_bytes);
+        {
+          const char* env = getenv("NQ_WAIT_POLLS");
+          sh.seg_max_polls = env ? (unsigned)strtoul(env, nullptr, 10) : (1u << 24);
+        }
         NQ_CUDA(cudaMemsetAsync(sh.seg_ctl, 0, plan.ctl_bytes, st));
         ising_fast_kernel<false, false, true><<<plan.grid, threads, smem, st>>>(sh, io);
+        ising_status_kernel<<<64, 256, 0, st>>>(sh.seg_ctl + 1 + desc->R, io.summary,
+                                                (size_t)NQ_IS_NSUMMARY * desc->R * (T - 1));
       } else {
         NQ_CUDA(cudaFuncSetAttribute(ising_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ising_fast_kernel<false><<<blocks, threads, smem, st>>>(sh, io);
@@ -1075,6 +1096,7 @@ extern "C" int nq_ising_run(const NqIsingDesc* desc, const uint32_t* thr, const 
 
 extern "C" int nq_ising_random_spins(const uint32_t key[2], int64_t n_sites, float p, uint32_t* out_bits,
                                      void* stream) {
+  NQ_RANGE();
   NQ_CHECK_ARG(key && out_bits && n_sites > 0 && n_sites <= 0x7fffffffll, "bad arguments");
   const long long n = n_sites;
   // u < p  with u = m * 2^-23  <=>  m < ceil(p * 2^23)
@@ -1089,6 +1111,7 @@ extern "C" int nq_ising_random_spins(const uint32_t key[2], int64_t n_sites, flo
 }
 
 extern "C" int nq_ising_pack(const void* spins, int32_t is_float, int64_t n_sites, uint32_t* bits, void* stream) {
+  NQ_RANGE();
   NQ_CHECK_ARG(spins && bits && n_sites > 0, "bad arguments");
   const long long words = (n_sites + 31) / 32;
   const unsigned blocks = (unsigned)((words + 127) / 128);
@@ -1099,6 +1122,7 @@ extern "C" int nq_ising_pack(const void* spins, int32_t is_float, int64_t n_site
 }
 
 extern "C" int nq_ising_unpack(const uint32_t* bits, int64_t n_sites, int32_t is_float, void* spins, void* stream) {
+  NQ_RANGE();
   NQ_CHECK_ARG(spins && bits && n_sites > 0, "bad arguments");
   const unsigned blocks = (unsigned)((n_sites + 255) / 256);
   if (is_float) unpack_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(bits, n_sites, (float*)spins);
@@ -1109,6 +1133,7 @@ extern "C" int nq_ising_unpack(const uint32_t* bits, int64_t n_sites, int32_t is
 
 extern "C" int nq_ising_measure(const uint32_t* bits, int32_t ndim, const int32_t dims[3], int64_t R,
                                 int64_t* out_MB, void* stream) {
+  NQ_RANGE();
   NQ_CHECK_ARG(bits && out_MB && dims && ndim >= 1 && ndim <= 3 && R > 0, "bad arguments");
   const int d0 = dims[0], d1 = ndim >= 2 ? dims[1] : 1, d2 = ndim >= 3 ? dims[2] : 1;
   NQ_CHECK_ARG(d0 > 0 && d1 > 0 && d2 > 0, "bad lattice shape");
@@ -1145,6 +1170,7 @@ extern "C" int nq_ising_grad_assemble(int32_t kind, int32_t T, int64_t R, int64_
                                       const double* dL_dh_ext, const double* dL_dl_ext, const float* loss_ext,
                                       float* loss, double* logP_lt, double* logP_h, double* rep_lt, double* rep_h,
                                       void* stream) {
+  NQ_RANGE();
   NQ_CHECK_ARG(kind >= 0 && kind <= 2, "kind must be 0 (work), 1 (entropy production) or 2 (external)");
   NQ_CHECK_ARG(T >= 2 && R >= 1 && n_sites >= 1, "need T >= 2, R >= 1, n_sites >= 1");
   NQ_CHECK_ARG(Dl >= 1 && Dl <= 32 && Dh >= 1 && Dh <= 32, "1 <= variables per schedule component <= 32 (got %d, %d)", Dl, Dh);

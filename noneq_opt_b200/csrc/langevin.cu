@@ -57,6 +57,7 @@ int make_langevin_consts(const NqLangevinDesc* d, LangevinConsts* c) {
   // STRICT main-path window of the division / logarithm of A + B (div_main, logf_main): the numerator
   // 1 / beta must sit inside [2^-62, 2^62) too, otherwise every step takes the library functions
   c->guard_span = (c->inv_beta >= 0x1p-62f && c->inv_beta < 0x1p62f) ? 0x3e000000u : 0u;
+  c->one = 1u;
   c->S = d->steps;
   c->Neq = d->eq_steps;
   return NQ_OK;
@@ -66,12 +67,14 @@ int make_langevin_consts(const NqLangevinDesc* d, LangevinConsts* c) {
 // l, l+32, ... in order and the lanes are combined by a fixed shuffle tree, so the result does not
 // depend on scheduling (bit-deterministic gradients).
 __global__ void __launch_bounds__(256) langevin_finalize_kernel(const double* partials, int nblocks, int NV, int DPS,
-                                                                 int D, double* out_mom, double* out_grad) {
+                                                                 int D, double* out_mom, double* out_grad,
+                                                                 const unsigned int* status) {
   const int q = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (q >= NV) return;
   double s = 0.0;
   for (int b = lane; b < nblocks; b += 32) s += partials[(long long)b * NV + q];
   s = warp_sum(s);
+  if (status && *status) s = __longlong_as_double(0x7ff8000000000000ll);   // abandoned persistent launch: NaN, loudly
   if (lane != 0) return;
   if (q < 8) {
     if (out_mom) out_mom[q] = s;
@@ -118,7 +121,7 @@ static long long chunk_steps(bool fast) {
 }
 static long long persistent_ctas_per_sm(bool fast, long long n) {
   const char* env = getenv("NQ_PERSISTENT_PER_SM");
-  return env ? atoll(env) : (fast ? 6 : (n <= 130000 ? 8 : 10));
+  return env ? atoll(env) : kCtaScale * (fast ? 6 : (n <= 130000 ? 8 : 10));
 }
 static bool use_persistent(long long n, long long S, bool record, bool fast) {
   if (record || S < 2 * chunk_steps(fast)) return false;
@@ -144,7 +147,7 @@ static size_t persistent_bytes(long long n, int D) {
   const long long groups = (n + kThreads - 1) / kThreads;
   const long long n_chunks_max = 1 << 16;  // callers size the workspace without knowing S: bound the ring by n
   (void)n_chunks_max;
-  return align256((size_t)state_words(kernel_D(D)) * groups * kThreads * 4) + align256((size_t)(groups + 2) * 4);
+  return align256((size_t)state_words(kernel_D(D)) * groups * kThreads * 4) + align256((size_t)(groups + 4) * 4);
 }
 
 static int run(const NqLangevinDesc* desc, const LangevinIO& io_in, double* moments, double* grad_sums,
@@ -187,6 +190,7 @@ static int run(const NqLangevinDesc* desc, const LangevinIO& io_in, double* mome
     return NQ_ERR_WORKSPACE;
   }
   io.partials = (double*)workspace;
+  const unsigned int* status = nullptr;
   if (record) NQ_CHECK_ARG(io.D == 0, "per-step recording is only available on the forward entry points");
   if (io.positions) NQ_CHECK_ARG(io.pos_stride >= 1, "pos_stride must be >= 1");
   if (io.ckpt_x) NQ_CHECK_ARG(io.ckpt_rng && io.ckpt_every >= 1, "checkpointing needs ckpt_rng and ckpt_every >= 1");
@@ -201,7 +205,13 @@ static int run(const NqLangevinDesc* desc, const LangevinIO& io_in, double* mome
     const size_t state_bytes = align256((size_t)state_words(kernel_D(io.D)) * ctl.npad * 4);
     ctl.head = (unsigned int*)(base + state_bytes);
     ctl.tail = ctl.head + 1;
-    ctl.progress = (int*)(ctl.head + 2);
+    ctl.status = ctl.head + 2;
+    ctl.progress = (int*)(ctl.head + 4);
+    {
+      const char* env = getenv("NQ_WAIT_POLLS");   // bound of a scheduler wait in 100 ns polls; 0 = unbounded (sanitizers)
+      ctl.max_polls = env ? (unsigned int)strtoul(env, nullptr, 10) : (1u << 25);
+    }
+    status = ctl.status;
     ctl.ring = ring;
     persistent_init_kernel<<<64, 256, 0, st>>>(ctl);
     NQ_LAUNCHED();
@@ -225,7 +235,8 @@ static int run(const NqLangevinDesc* desc, const LangevinIO& io_in, double* mome
   }
   NQ_LAUNCHED();
   if (moments || grad_sums) {
-    langevin_finalize_kernel<<<(NV + 7) / 8, 256, 0, st>>>(io.partials, blocks, NV, (NV - 8) / 2, io.D, moments, grad_sums);
+    langevin_finalize_kernel<<<(NV + 7) / 8, 256, 0, st>>>(io.partials, blocks, NV, (NV - 8) / 2, io.D, moments, grad_sums,
+                                                        status);
     NQ_LAUNCHED();
   }
   return NQ_OK;
@@ -255,6 +266,7 @@ extern "C" int nq_langevin_forward(const NqLangevinDesc* desc, const float* r_ta
                                    const uint32_t* seeds, int64_t n, float* work, float* logp, float* x_final,
                                    float* positions, int64_t pos_stride, float* step_works, float* step_logps,
                                    double* moments, void* workspace, size_t workspace_bytes, void* stream) {
+  NQ_RANGE();
   LangevinIO io{};
   io.r_table = r_table; io.x0 = x0; io.seeds = seeds;
   io.work = work; io.logp = logp; io.x_final = x_final;
@@ -267,6 +279,7 @@ extern "C" int nq_langevin_grad(const NqLangevinDesc* desc, const float* r_table
                                 const float* x0, const uint32_t* seeds, int64_t n, float* work, float* logp,
                                 float* estimator, float* x_final, double* grad_sums, double* moments,
                                 void* workspace, size_t workspace_bytes, void* stream) {
+  NQ_RANGE();
   NQ_CHECK_ARG(D >= 1, "D must be >= 1 for the gradient entry point");
   NQ_CHECK_ARG(grad_sums != nullptr, "grad_sums is null");
   LangevinIO io{};
@@ -281,6 +294,7 @@ extern "C" int nq_langevin_grad_record(const NqLangevinDesc* desc, const float* 
                                        float* estimator, float* x_final, float* positions, int64_t pos_stride,
                                        double* grad_sums, double* moments, void* workspace, size_t workspace_bytes,
                                        void* stream) {
+  NQ_RANGE();
   NQ_CHECK_ARG(D >= 1, "D must be >= 1 for the gradient entry point");
   NQ_CHECK_ARG(grad_sums != nullptr && positions != nullptr && pos_stride >= 1, "grad_sums / positions / pos_stride");
   if (!use_pair(n, false)) {
@@ -304,6 +318,7 @@ extern "C" int nq_langevin_forward_ckpt(const NqLangevinDesc* desc, const float*
                                         const uint32_t* seeds, int64_t n, int64_t ckpt_every, float* work,
                                         float* logp, float* x_final, float* ckpt_x, uint32_t* ckpt_rng,
                                         double* moments, void* workspace, size_t workspace_bytes, void* stream) {
+  NQ_RANGE();
   NQ_CHECK_ARG(ckpt_x && ckpt_rng && ckpt_every >= 1, "checkpoint buffers / interval missing");
   LangevinIO io{};
   io.r_table = r_table; io.x0 = x0; io.seeds = seeds;
@@ -317,6 +332,7 @@ extern "C" int nq_langevin_replay(const NqLangevinDesc* desc, const float* r_tab
                                   const float* ckpt_x, const uint32_t* ckpt_rng, const float* lbar,
                                   const float* wbar, double* gbar, void* workspace, size_t workspace_bytes,
                                   void* stream) {
+  NQ_RANGE();
   (void)workspace;
   (void)workspace_bytes;
   LangevinConsts c;
@@ -339,6 +355,7 @@ extern "C" int nq_langevin_replay(const NqLangevinDesc* desc, const float* r_tab
 
 extern "C" int nq_langevin_stationary(const NqLangevinDesc* desc, float r0, const float* x0, const uint32_t* seeds,
                                       int64_t n, float* x_final, float* positions, void* stream) {
+  NQ_RANGE();
   LangevinConsts c;
   int rc = make_langevin_consts(desc, &c);
   if (rc) return rc;
@@ -352,6 +369,7 @@ extern "C" int nq_langevin_stationary(const NqLangevinDesc* desc, float r0, cons
 
 extern "C" int nq_langevin_apply(const NqLangevinDesc* desc, float r0, float* x, uint32_t* rng, float* log_prob,
                                  int64_t n, void* stream) {
+  NQ_RANGE();
   NQ_CHECK_ARG(desc != nullptr, "desc is null");
   NqLangevinDesc d1 = *desc;
   if (d1.steps < 1) d1.steps = 1;

@@ -44,12 +44,17 @@ namespace nq {
 #endif
 constexpr int kUnroll = NQ_LANGEVIN_UNROLL;
 constexpr int kTile = 128;    // steps staged per shared-memory tile
-constexpr int kThreads = 64;  // trajectories per CTA (small CTAs balance 1e5 trajectories over 148 SMs)
-// resident CTAs per SM the register budget is held to, so that config 2 (1563 CTAs) is one wave
-constexpr int min_blocks(int D) { return D <= 8 ? 16 : (D <= 16 ? 11 : (D <= 24 ? 8 : 6)); }
+#ifndef NQ_LANGEVIN_THREADS
+#define NQ_LANGEVIN_THREADS 64
+#endif
+constexpr int kThreads = NQ_LANGEVIN_THREADS;  // trajectories per CTA (small CTAs balance 1e5 trajectories over 148 SMs)
+constexpr int kCtaScale = 64 / kThreads;       // CTAs per 64 trajectories
+static_assert(kThreads == 32 || kThreads == 64, "32 or 64 trajectories per CTA");
+// resident CTAs per SM the register budget is held to, so that config 2 (1563 CTAs of 64) is one wave
+constexpr int min_blocks(int D) { return kCtaScale * (D <= 8 ? 16 : (D <= 16 ? 11 : (D <= 24 ? 8 : 6))); }
 // The persistent kernel keeps at most 10 CTAs per SM resident, so STRICT may use up to 96 registers
 // (fewer constant reloads: +2.7 % at config 2); FAST is faster with the 80-register schedule (measured).
-constexpr int persistent_min_blocks(int D, bool fast) { return (fast || D > 16) ? min_blocks(D) : 10; }
+constexpr int persistent_min_blocks(int D, bool fast) { return (fast || D > 16) ? min_blocks(D) : 10 * kCtaScale; }
 
 struct LangevinConsts {
   int potential, shift_kind;
@@ -62,6 +67,7 @@ struct LangevinConsts {
   // STRICT: width of the operand window [2^-62, 2^62) in which the division / logarithm of A + B take their
   // main paths (div_main, logf_main); 0 sends every step through the library functions (extreme 1 / beta)
   uint32_t guard_span;
+  uint32_t one;   // = 1: multiplicand of the IMAD-form additions of the key chain (threefry2x32_inj)
   long long S, Neq;
 };
 
@@ -179,19 +185,39 @@ __device__ __forceinline__ float py_mod(float x, float box) {
 
 // The software-pipelined key chain of one trajectory.  Invariant at the top of step k:
 // (k0, k1) is the chain key AFTER the split of step k, (s0, s1) the sub-key step k samples with.
-struct RngPipe {
+// INJ: 0 plain threefry; 1 key-injection adds as IMADs (threefry2x32_inj); 2 every add as IMAD.  Measured at
+// config 2 (gpurun_out/variants_r02b.log, 1e10 traj-steps/s, STRICT / FAST): 0: 8.15 / 9.54, 1: 7.96 / 9.89,
+// 2: 7.67 / 9.49 -- the FAST loop (fewer FMA-pipe instructions) gains from moving the injections off the ALU
+// pipe, the STRICT loop loses, and true IMADs (half rate, one pipe) for every add lose in both.
+#ifndef NQ_RNG_INJ_STRICT
+#define NQ_RNG_INJ_STRICT 0
+#endif
+#ifndef NQ_RNG_INJ_FAST
+#define NQ_RNG_INJ_FAST 1
+#endif
+template <int INJ>
+struct RngPipeT {
   uint32_t k0, k1, s0, s1;
+  uint32_t one = 1u;   // set from LangevinConsts::one by the hot loops (a value the compiler cannot fold)
   // state.rng -> pipeline (performs the split of the first step)
   __device__ __forceinline__ void prime(uint32_t r0, uint32_t r1) { split2(r0, r1, k0, k1, s0, s1); }
   // bits for this step's normal draw; advances the chain by one step
   __device__ __forceinline__ uint32_t next() {
     uint32_t bits, unused, n0, n1, t0, t1;
-    threefry2x32(key_schedule(s0, s1), 0u, 0u, bits, unused);  // normal(split, [1,1,1]) :88
-    split2(k0, k1, n0, n1, t0, t1);                            // key, split = split(state.rng) of the NEXT step :79
+    if (INJ) {
+      const KeyInject ks = key_inject(s0, s1, one);
+      threefry2x32_inj<INJ == 2>(ks, ks.ks0, ks.ks1, one, bits, unused);   // normal(split, [1,1,1]) :88
+      split2_inj<INJ == 2>(k0, k1, one, n0, n1, t0, t1);       // key, split = split(state.rng) of the NEXT step :79
+    } else {
+      threefry2x32(key_schedule(s0, s1), 0u, 0u, bits, unused);  // normal(split, [1,1,1]) :88
+      split2(k0, k1, n0, n1, t0, t1);                            // key, split = split(state.rng) of the NEXT step :79
+    }
     k0 = n0; k1 = n1; s0 = t0; s1 = t1;
     return bits;
   }
 };
+template <bool FAST> using RngPipeFor = RngPipeT<FAST ? NQ_RNG_INJ_FAST : NQ_RNG_INJ_STRICT>;
+using RngPipe = RngPipeT<0>;   // kernels off the hot path
 
 // One apply_fn (barrier_crossing.py:77-92) given the landscape already evaluated at x and this step's
 // standard-normal draw.  Returns dR; updates x; writes z (standardised noise) and, if WANT_LP, lp.
@@ -390,7 +416,7 @@ struct StepCtx {
   const LangevinConsts& c;
   const LangevinIO& io;
   float& x;
-  RngPipe& rng;
+  RngPipeFor<FAST>& rng;
   Landscape<POT, FAST>& land;
   float& z;
   float& lp;
@@ -522,7 +548,8 @@ __device__ __forceinline__ void langevin_chunk(const LangevinConsts& c_in, const
   const long long idx = live ? gid : io.n - 1;
 
   float x;
-  RngPipe rng;
+  RngPipeFor<FAST> rng;
+  rng.one = c.one;
   double W = 0.0, LP = 0.0;
   float gA[DA], gB[DA];
   Landscape<POT, FAST> land;
@@ -703,7 +730,8 @@ __global__ void __launch_bounds__(kPairThreads) langevin_pair_kernel(const Lange
   const long long n_chunks = (total + kRingHalf - 1) / kRingHalf;
 
   if (producer) {
-    RngPipe rng;
+    RngPipeFor<FAST> rng;
+    rng.one = c.one;
     {
       uint32_t n0, n1, r0, r1;
       split2(io.seeds[2 * idx], io.seeds[2 * idx + 1], n0, n1, r0, r1);   // barrier_crossing.py:133,138
@@ -874,6 +902,8 @@ struct PersistentCtl {
   unsigned int* tail;        // push tickets handed out (starts at groups)
   int* ring;                 // [groups * n_chunks]
   int* progress;             // [groups] chunks completed
+  unsigned int* status;      // 0 = ok; set to 1 when a bounded wait ran out (the launch is then abandoned)
+  unsigned int max_polls;    // bound of a wait on the ring, in polls of 100 ns; 0 = unbounded
   uint32_t* state;           // [state_words][npad]
   long long groups, npad, chunk, n_chunks;
 };
@@ -887,6 +917,7 @@ static __global__ void persistent_init_kernel(PersistentCtl ctl) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     *ctl.head = 0u;
     *ctl.tail = (unsigned int)ctl.groups;
+    *ctl.status = 0u;
   }
 }
 
@@ -902,14 +933,28 @@ __global__ void __launch_bounds__(kThreads, persistent_min_blocks(D, FAST)) lang
       const unsigned int t = atomicAdd(ctl.head, 1u);
       int g = -2;
       if (t < n_items) {
+        // A popped ticket whose entry is not published yet always has a running chunk that will publish it
+        // (n_items tickets in total), provided the resident CTAs make progress together -- true for one
+        // kernel owning the GPU, not guaranteed under a debugger, MPS time-slicing or pre-emption.  The wait
+        // is therefore bounded (~3 s by default, NQ_WAIT_POLLS; 0 = unbounded): when it runs out the launch
+        // is abandoned CLEANLY -- status word set, this CTA leaves, the others follow as their own waits run
+        // out or the queue drains -- and the finalize kernel turns the status into NaN sums.  No __trap():
+        // a trap would poison the whole CUDA context of the caller.
         volatile int* slot = ctl.ring + t;
+        volatile unsigned int* dead = ctl.status;
         unsigned int spins = 0;
         while ((g = *slot) < 0) {
           __nanosleep(100);
-          if (++spins > (1u << 25)) __trap();  // > 3 s: a scheduling bug must fail loudly, never hang the GPU
+          if ((ctl.max_polls && ++spins > ctl.max_polls) || *dead) {
+            atomicExch(ctl.status, 1u);
+            g = -2;
+            break;
+          }
         }
-        __threadfence();
-        chunk_s = ctl.progress[g];
+        if (g >= 0) {
+          __threadfence();
+          chunk_s = ctl.progress[g];
+        }
       }
       chain_s = g;
     }

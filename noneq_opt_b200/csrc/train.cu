@@ -107,6 +107,7 @@ using namespace nq;
 
 extern "C" int nq_random_split_dev(const uint32_t* key_dev, int64_t num, int64_t first, int64_t count,
                                    uint32_t* out, void* stream) {
+  NQ_RANGE();
   NQ_CHECK_ARG(key_dev && out, "null pointer");
   NQ_CHECK_ARG(num >= 0 && first >= 0 && count >= 0 && first + count <= num, "bad slice [%lld,+%lld) of %lld",
                (long long)first, (long long)count, (long long)num);
@@ -122,6 +123,7 @@ extern "C" int nq_random_split_dev(const uint32_t* key_dev, int64_t num, int64_t
 
 extern "C" int nq_schedule_affine(const float* basis, const float* variables, const float* offset, float first,
                                   float last, int64_t K, int32_t D, float* table, void* stream) {
+  NQ_RANGE();
   NQ_CHECK_ARG(basis && variables && table, "null pointer");
   NQ_CHECK_ARG(K >= 0 && D >= 1 && D <= 4096, "need K >= 0 and 1 <= D <= 4096 (got K=%lld D=%d)", (long long)K, D);
   const long long blocks = (K + 2 + 255) / 256;
@@ -134,6 +136,7 @@ extern "C" int nq_schedule_affine(const float* basis, const float* variables, co
 extern "C" int nq_adam_step(const NqAdamDesc* d, int32_t P, const double* grad_sums0, const double* grad_sums1,
                             const float* grad_f32, float* x, float* m, float* v, int64_t* step_dev,
                             float* grad_out, void* stream) {
+  NQ_RANGE();
   NQ_CHECK_ARG(d && x && m && v && step_dev && P >= 1, "null pointer or P < 1");
   NQ_CHECK_ARG((grad_sums0 != nullptr) != (grad_f32 != nullptr), "pass either grad_sums0 (f64 sums) or grad_f32");
   NQ_CHECK_ARG(grad_f32 || d->denom != 0.0, "denom must be non-zero");

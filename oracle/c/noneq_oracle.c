@@ -357,6 +357,20 @@ void oracle_ising(int L, int T, long R, const float* log_temp, const float* fiel
   }
 }
 
+// n <= 0: every core this process may run on.  torchrun exports OMP_NUM_THREADS=1 to its workers; the timed
+// CPU arms of bench.py call this so that "all host cores" means the same thing at every --gpus N.
+int oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n <= 0) n = omp_get_num_procs();
+  omp_set_dynamic(0);
+  omp_set_num_threads(n);
+  return n;
+#else
+  (void)n;
+  return 1;
+#endif
+}
+
 int oracle_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

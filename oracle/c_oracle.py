@@ -32,6 +32,13 @@ def max_threads() -> int:
   return int(lib().oracle_max_threads())
 
 
+def use_all_cores() -> int:
+  """OpenMP team = every core this process may run on, whatever OMP_NUM_THREADS says (torchrun sets it to 1)."""
+  fn = lib().oracle_set_threads
+  fn.restype = C.c_int
+  return int(fn(C.c_int(len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else 0)))
+
+
 def _p(a, t):
   return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
 
