@@ -264,6 +264,15 @@ int nq_ising_grad_assemble(int32_t kind, int32_t T, int64_t R, int64_t n_sites, 
                            float* loss /*[R]*/, double* logP_lt /*[R][Dl]*/, double* logP_h /*[R][Dh]*/,
                            double* rep_lt, double* rep_h, void* stream);
 
+/* The same assembly (kinds 0 and 1) with the schedule end points read from the DEVICE tables log_temp[T],
+ * field[T] the sweep ran on -- no host copy of the schedule (device-resident training step, ising.py:263-290). */
+int nq_ising_grad_assemble_dev(int32_t kind, int32_t T, int64_t R, int64_t n_sites, int32_t broadcast0,
+                               const float* log_temp /*device [T]*/, const float* field /*device [T]*/,
+                               const float* summary, const float* partials, const int64_t* MB0,
+                               const double* J_lt, int32_t Dl, const double* J_h, int32_t Dh,
+                               float* loss, double* logP_lt, double* logP_h, double* rep_lt, double* rep_h,
+                               void* stream);
+
 /* ------------------------------------------------------------------ device-resident training step */
 /* The pieces that let one optimisation step of the reference's drivers
  * (run_barrier_crossing_opt.py:113-137; ising.py:263-290) run as a fixed launch sequence with
@@ -282,6 +291,29 @@ int nq_random_split_dev(const uint32_t* key_dev /*device [2]*/, int64_t num, int
  * same [K][D] array nq_langevin_grad takes as phi.                                              */
 int nq_schedule_affine(const float* basis, const float* variables, const float* offset, float first, float last,
                        int64_t K, int32_t D, float* table /*[K+2]*/, void* stream);
+
+/* Schedule table of the Ising drivers' composition (run_ising_opt.py:45-66)
+ *   AddBaseline(ConstrainEndpoints(Chebyshev(variables), y0, y1), baseline)   (parameterization.py:144-179, 295-344):
+ *   table[i] = ((scale[i] * sum_j variables[j] * basis[i][j]) + offset1[i]) + offset2[i]
+ * with one binary32 rounding per operation in that order (scale = the end-point envelope, offset1 = its linear
+ * part, offset2 = the baseline; each nullable), all operands in device memory.                                  */
+int nq_schedule_compose(const float* basis /*[K][D]*/, const float* variables /*[D]*/, const float* scale /*[K]*/,
+                        const float* offset1 /*[K]*/, const float* offset2 /*[K]*/, int64_t K, int32_t D,
+                        float* table /*[K]*/, void* stream);
+
+/* Per-sweep class tables nq_ising_run consumes, computed ON THE DEVICE from device schedule tables: the
+ * arithmetic of flip_logits (ising.py:93-96) and distrax.Bernoulli's sigmoid / log_sigmoid in float32 with
+ * binary64-evaluated transcendentals rounded once (bit-equal to the host tables of noneq_opt_b200.ising).
+ * thr [T-1][16] uint32, lut [T-1][4][16] float64; ndim = lattice rank.                                         */
+int nq_ising_class_tables(const float* log_temp /*device [T]*/, const float* field /*device [T]*/, int32_t T,
+                          int32_t ndim, uint32_t* thr, double* lut, void* stream);
+
+/* Batch mean of the per-replica schedule gradients nq_ising_grad_assemble leaves on the device
+ * (tree_map(mean) of ising.py:286): mean_out[Dl + Dh] = mean_r float32(w_logp * logP[r] + w_rep * rep[r]),
+ * log-temperature variables first.  Feed mean_out to nq_adam_step(grad_f32 = ...).                           */
+int nq_ising_grad_mean(const double* logP_lt, const double* logP_h, const double* rep_lt, const double* rep_h,
+                       int64_t R, int32_t Dl, int32_t Dh, double w_logp, double w_rep, float* mean_out /*[Dl+Dh]*/,
+                       void* stream);
 
 typedef struct NqAdamDesc {
   double step_size, decay_steps, decay_rate; /* lr(i) = step_size * decay_rate^(i/decay_steps);

@@ -79,6 +79,11 @@ SIGNATURES = {
     'nq_ising_grad_assemble': (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_float),
                                          C.c_float, _P, _P, _P, _P, C.c_int32, _P, C.c_int32, _P, _P, _P, _P, _P, _P,
                                          _P, _P, _P]),
+    'nq_ising_grad_assemble_dev': (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _P, _P, _P, _P, _P,
+                                             _P, C.c_int32, _P, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    'nq_schedule_compose': (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int32, _P, _P]),
+    'nq_ising_class_tables': (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
+    'nq_ising_grad_mean': (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_double, _P, _P]),
     'nq_random_split_dev': (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, _P, _P]),
     'nq_schedule_affine': (C.c_int, [_P, _P, _P, C.c_float, C.c_float, C.c_int64, C.c_int32, _P, _P]),
     'nq_adam_step': (C.c_int, [C.POINTER(NqAdamDesc), C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -783,6 +783,8 @@ struct IsingGradArgs {
   long long R;
   double n_sites, lt0, ltf, h0;      // schedule end points as float64 of the float32 values
   float exp_lt0, exp_ltf;            // float32(exp(log_temp)) at both ends, for the loss in reference arithmetic
+  const float* lt_tab;               // device schedule tables [T] (nullable): when given, the four end-point values
+  const float* h_tab;                //   above are read from them instead (device-resident training step)
   const float* summary;              // [7][R][T-1]
   const float* partials;             // [4][R][T-1]
   const long long* MB0;              // [R or 1][2]
@@ -808,7 +810,12 @@ __device__ __forceinline__ double block_sum_128(double v, double* scratch) {
   return (scratch[0] + scratch[1]) + (scratch[2] + scratch[3]);
 }
 
-__global__ void __launch_bounds__(128) ising_grad_kernel(const IsingGradArgs a) {
+__global__ void __launch_bounds__(128) ising_grad_kernel(const IsingGradArgs a_in) {
+  IsingGradArgs a = a_in;
+  if (a.lt_tab) {
+    a.lt0 = (double)a.lt_tab[0]; a.ltf = (double)a.lt_tab[a.T - 1]; a.h0 = (double)a.h_tab[0];
+    a.exp_lt0 = (float)exp(a.lt0); a.exp_ltf = (float)exp(a.ltf);
+  }
   __shared__ double sens_s[4][kGradTile];   // dF/dl, dF/dh, dL/dl, dL/dh of the current tile of sweeps
   __shared__ double red_s[4];
   __shared__ double acc_s[4][32];
@@ -1163,6 +1170,40 @@ extern "C" int nq_ising_measure(const uint32_t* bits, int32_t ndim, const int32_
   return NQ_OK;
 }
 
+static int grad_assemble(int32_t kind, int32_t T, int64_t R, int64_t n_sites, int32_t broadcast0,
+                         const float* log_temp_ends /*host [2]*/, float field0, const float* lt_tab, const float* h_tab,
+                         const float* summary, const float* partials, const int64_t* MB0,
+                         const double* J_lt, int32_t Dl, const double* J_h, int32_t Dh,
+                         const double* dL_dh_ext, const double* dL_dl_ext, const float* loss_ext,
+                         float* loss, double* logP_lt, double* logP_h, double* rep_lt, double* rep_h, void* stream) {
+  NQ_CHECK_ARG(kind >= 0 && kind <= 2, "kind must be 0 (work), 1 (entropy production) or 2 (external)");
+  NQ_CHECK_ARG(T >= 2 && R >= 1 && n_sites >= 1, "need T >= 2, R >= 1, n_sites >= 1");
+  // the spin sum of a sweep is recovered as rint(float32(M / N) * N): exact while N <= 2^23 or N is a power of two
+  NQ_CHECK_ARG(n_sites <= (1ll << 23) || (n_sites & (n_sites - 1)) == 0,
+               "lattices of more than 2^23 sites must have a power-of-two site count (got %lld)", (long long)n_sites);
+  NQ_CHECK_ARG(Dl >= 1 && Dl <= 32 && Dh >= 1 && Dh <= 32, "1 <= variables per schedule component <= 32 (got %d, %d)", Dl, Dh);
+  NQ_CHECK_ARG((log_temp_ends || (lt_tab && h_tab)) && summary && MB0 && J_lt && J_h && loss && logP_lt && logP_h && rep_lt && rep_h,
+               "null pointer");
+  NQ_CHECK_ARG(kind == 2 || partials || kind == 0, "partials are required for the entropy-production loss");
+  NQ_CHECK_ARG(kind != 1 || partials, "partials are required for the entropy-production loss");
+  NQ_CHECK_ARG(kind != 2 || (dL_dh_ext && dL_dl_ext && loss_ext), "kind 2 needs loss_ext, dL_dh_ext, dL_dl_ext");
+  IsingGradArgs a{};
+  a.kind = kind; a.T = T; a.Dl = Dl; a.Dh = Dh; a.broadcast0 = broadcast0; a.R = R;
+  a.n_sites = (double)n_sites;
+  if (lt_tab) {
+    a.lt_tab = lt_tab; a.h_tab = h_tab;
+  } else {
+    a.lt0 = (double)log_temp_ends[0]; a.ltf = (double)log_temp_ends[1]; a.h0 = (double)field0;
+    a.exp_lt0 = (float)exp((double)log_temp_ends[0]); a.exp_ltf = (float)exp((double)log_temp_ends[1]);
+  }
+  a.summary = summary; a.partials = partials; a.MB0 = (const long long*)MB0;
+  a.J_lt = J_lt; a.J_h = J_h; a.dL_dh_ext = dL_dh_ext; a.dL_dl_ext = dL_dl_ext; a.loss_ext = loss_ext;
+  a.loss = loss; a.logP_lt = logP_lt; a.logP_h = logP_h; a.rep_lt = rep_lt; a.rep_h = rep_h;
+  ising_grad_kernel<<<(unsigned)R, 128, 0, (cudaStream_t)stream>>>(a);
+  NQ_LAUNCHED();
+  return NQ_OK;
+}
+
 extern "C" int nq_ising_grad_assemble(int32_t kind, int32_t T, int64_t R, int64_t n_sites, int32_t broadcast0,
                                       const float* log_temp_ends /*host [2]*/, float field0,
                                       const float* summary, const float* partials, const int64_t* MB0,
@@ -1171,22 +1212,20 @@ extern "C" int nq_ising_grad_assemble(int32_t kind, int32_t T, int64_t R, int64_
                                       float* loss, double* logP_lt, double* logP_h, double* rep_lt, double* rep_h,
                                       void* stream) {
   NQ_RANGE();
-  NQ_CHECK_ARG(kind >= 0 && kind <= 2, "kind must be 0 (work), 1 (entropy production) or 2 (external)");
-  NQ_CHECK_ARG(T >= 2 && R >= 1 && n_sites >= 1, "need T >= 2, R >= 1, n_sites >= 1");
-  NQ_CHECK_ARG(Dl >= 1 && Dl <= 32 && Dh >= 1 && Dh <= 32, "1 <= variables per schedule component <= 32 (got %d, %d)", Dl, Dh);
-  NQ_CHECK_ARG(log_temp_ends && summary && MB0 && J_lt && J_h && loss && logP_lt && logP_h && rep_lt && rep_h, "null pointer");
-  NQ_CHECK_ARG(kind == 2 || partials || kind == 0, "partials are required for the entropy-production loss");
-  NQ_CHECK_ARG(kind != 1 || partials, "partials are required for the entropy-production loss");
-  NQ_CHECK_ARG(kind != 2 || (dL_dh_ext && dL_dl_ext && loss_ext), "kind 2 needs loss_ext, dL_dh_ext, dL_dl_ext");
-  IsingGradArgs a{};
-  a.kind = kind; a.T = T; a.Dl = Dl; a.Dh = Dh; a.broadcast0 = broadcast0; a.R = R;
-  a.n_sites = (double)n_sites;
-  a.lt0 = (double)log_temp_ends[0]; a.ltf = (double)log_temp_ends[1]; a.h0 = (double)field0;
-  a.exp_lt0 = (float)exp((double)log_temp_ends[0]); a.exp_ltf = (float)exp((double)log_temp_ends[1]);
-  a.summary = summary; a.partials = partials; a.MB0 = (const long long*)MB0;
-  a.J_lt = J_lt; a.J_h = J_h; a.dL_dh_ext = dL_dh_ext; a.dL_dl_ext = dL_dl_ext; a.loss_ext = loss_ext;
-  a.loss = loss; a.logP_lt = logP_lt; a.logP_h = logP_h; a.rep_lt = rep_lt; a.rep_h = rep_h;
-  ising_grad_kernel<<<(unsigned)R, 128, 0, (cudaStream_t)stream>>>(a);
-  NQ_LAUNCHED();
-  return NQ_OK;
+  NQ_CHECK_ARG(log_temp_ends != nullptr, "log_temp_ends is null");
+  return grad_assemble(kind, T, R, n_sites, broadcast0, log_temp_ends, field0, nullptr, nullptr, summary, partials, MB0,
+                       J_lt, Dl, J_h, Dh, dL_dh_ext, dL_dl_ext, loss_ext, loss, logP_lt, logP_h, rep_lt, rep_h, stream);
+}
+
+extern "C" int nq_ising_grad_assemble_dev(int32_t kind, int32_t T, int64_t R, int64_t n_sites, int32_t broadcast0,
+                                          const float* log_temp /*device [T]*/, const float* field /*device [T]*/,
+                                          const float* summary, const float* partials, const int64_t* MB0,
+                                          const double* J_lt, int32_t Dl, const double* J_h, int32_t Dh,
+                                          float* loss, double* logP_lt, double* logP_h, double* rep_lt, double* rep_h,
+                                          void* stream) {
+  NQ_RANGE();
+  NQ_CHECK_ARG(kind == 0 || kind == 1, "kind must be 0 (work) or 1 (entropy production)");
+  NQ_CHECK_ARG(log_temp && field, "schedule tables are null");
+  return grad_assemble(kind, T, R, n_sites, broadcast0, nullptr, 0.f, log_temp, field, summary, partials, MB0, J_lt, Dl,
+                       J_h, Dh, nullptr, nullptr, nullptr, loss, logP_lt, logP_h, rep_lt, rep_h, stream);
 }

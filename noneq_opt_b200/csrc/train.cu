@@ -45,6 +45,90 @@ __global__ void schedule_affine_kernel(const float* __restrict__ basis, const fl
   }
 }
 
+// table[i] = ((scale[i] * sum_j variables[j] * basis[i][j]) + offset1[i]) + offset2[i], one binary32 rounding per
+// operation: ConstrainEndpoints (envelope * wrapped + linear, parameterization.py:295-322) around Chebyshev
+// (:175-179) inside AddBaseline (wrapped + baseline, :325-344) -- the schedule composition of the Ising drivers
+// (run_ising_opt.py:45-66).  scale / offset1 / offset2 are nullable.
+__global__ void schedule_compose_kernel(const float* __restrict__ basis, const float* __restrict__ variables,
+                                        const float* __restrict__ scale, const float* __restrict__ offset1,
+                                        const float* __restrict__ offset2, long long K, int D, float* __restrict__ table) {
+  extern __shared__ float w_s[];
+  for (int j = threadIdx.x; j < D; j += blockDim.x) w_s[j] = variables[j];
+  __syncthreads();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < K; i += (long long)gridDim.x * blockDim.x) {
+    const float* row = basis + i * D;
+    float v = 0.f;
+    for (int j = 0; j < D; ++j) v = __fadd_rn(v, __fmul_rn(w_s[j], row[j]));
+    if (scale) v = __fmul_rn(scale[i], v);
+    if (offset1) v = __fadd_rn(v, offset1[i]);
+    if (offset2) v = __fadd_rn(v, offset2[i]);
+    table[i] = v;
+  }
+}
+
+// Per-sweep class tables of the Glauber sweep on the device -- the arithmetic of noneq_opt_b200.ising.class_tables
+// (itself flip_logits + distrax.Bernoulli, ising.py:93-96, 114-117): float32 operations in the reference's order,
+// transcendentals evaluated in binary64 and rounded once to float32.  One thread per (sweep, class).
+//   thr[t][slot] = ceil(sigmoid32(logit) * 2^23);  lut[t][0..3][slot] = logit, log_sigmoid32(-logit),
+//   log_sigmoid32(logit), sigmoid(logit) in binary64;  slot = 8 * (spin up) + #up-neighbours
+__device__ __forceinline__ float exp32(float x) { return (float)exp((double)x); }
+__device__ __forceinline__ float log_sigmoid32(float x) {
+  const float a = -x;
+  const float l1p = (float)log1p((double)exp32(-fabsf(a)));
+  return -__fadd_rn(fmaxf(a, 0.f), l1p);
+}
+__global__ void ising_class_tables_kernel(const float* __restrict__ log_temp, const float* __restrict__ field, int T,
+                                          int ndim, uint32_t* __restrict__ thr, double* __restrict__ lut) {
+  const int ncls = 2 * ndim + 1;
+  const long long n = (long long)(T - 1) * 16;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(q / 16), slot = (int)(q % 16), up = slot >> 3, n_up = slot & 7;
+    uint32_t th = 0u;
+    double l0 = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;
+    if (n_up < ncls) {
+      const float lt = log_temp[t + 1], h = field[t + 1];
+      const float einv = exp32(-lt);
+      const float sp = up ? 1.0f : -1.0f;
+      const float nsum = (float)(2 * n_up - 2 * ndim);
+      const float logit = __fmul_rn(__fmul_rn(__fmul_rn(-2.0f, sp), __fadd_rn(nsum, h)), einv);
+      const float prob = __fdiv_rn(1.0f, __fadd_rn(1.0f, exp32(-logit)));
+      th = (uint32_t)ceil((double)prob * 8388608.0);
+      l0 = (double)logit;
+      l1 = (double)log_sigmoid32(-logit);
+      l2 = (double)log_sigmoid32(logit);
+      l3 = 1.0 / (1.0 + exp(-(double)logit));
+    }
+    thr[(size_t)t * 16 + slot] = th;
+    double* L = lut + (size_t)t * 4 * 16;
+    L[slot] = l0; L[16 + slot] = l1; L[32 + slot] = l2; L[48 + slot] = l3;
+  }
+}
+
+// mean over the batch of the per-replica gradient (w_logp * logP + w_rep * reparam), replica terms rounded to
+// float32 first (what vmap(grad) returns) and averaged in binary64 (fixed order) -> float32 [Dl + Dh]
+__global__ void __launch_bounds__(256) ising_grad_mean_kernel(const double* __restrict__ logP_lt, const double* __restrict__ logP_h,
+                                                              const double* __restrict__ rep_lt, const double* __restrict__ rep_h,
+                                                              long long R, int Dl, int Dh, double w_logp, double w_rep,
+                                                              float* __restrict__ out) {
+  __shared__ double red_s[8];
+  const int j = blockIdx.x;                       // one CTA per variable
+  const bool is_h = j >= Dl;
+  const int c = is_h ? j - Dl : j, D = is_h ? Dh : Dl;
+  const double* a = is_h ? logP_h : logP_lt;
+  const double* b = is_h ? rep_h : rep_lt;
+  double s = 0.0;
+  for (long long r = threadIdx.x; r < R; r += blockDim.x)
+    s += (double)(float)(w_logp * a[r * D + c] + w_rep * b[r * D + c]);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red_s[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < 8; ++w) tot += red_s[w];
+    out[j] = (float)(tot / (double)R);
+  }
+}
+
 struct AdamArgs {
   double step_size, decay_steps, decay_rate, b1, b2, eps, max_norm, w0, w1, denom;
   int P;
@@ -144,6 +228,42 @@ extern "C" int nq_adam_step(const NqAdamDesc* d, int32_t P, const double* grad_s
   AdamArgs a{d->step_size, d->decay_steps, d->decay_rate, d->b1, d->b2, d->eps, d->max_norm, d->w0, d->w1, d->denom,
              P, grad_sums0, grad_sums1, grad_f32, x, m, v, (long long*)step_dev, grad_out};
   adam_step_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a);
+  NQ_LAUNCHED();
+  return NQ_OK;
+}
+
+extern "C" int nq_schedule_compose(const float* basis, const float* variables, const float* scale, const float* offset1,
+                                   const float* offset2, int64_t K, int32_t D, float* table, void* stream) {
+  NQ_RANGE();
+  NQ_CHECK_ARG(basis && variables && table, "null pointer");
+  NQ_CHECK_ARG(K >= 1 && D >= 1 && D <= 4096, "need K >= 1 and 1 <= D <= 4096 (got K=%lld D=%d)", (long long)K, D);
+  const long long blocks = (K + 255) / 256;
+  schedule_compose_kernel<<<(unsigned)(blocks > 148 * 8 ? 148 * 8 : blocks), 256, D * sizeof(float), (cudaStream_t)stream>>>(
+      basis, variables, scale, offset1, offset2, K, D, table);
+  NQ_LAUNCHED();
+  return NQ_OK;
+}
+
+extern "C" int nq_ising_class_tables(const float* log_temp, const float* field, int32_t T, int32_t ndim, uint32_t* thr,
+                                     double* lut, void* stream) {
+  NQ_RANGE();
+  NQ_CHECK_ARG(log_temp && field && thr && lut, "null pointer");
+  NQ_CHECK_ARG(T >= 2 && ndim >= 1 && ndim <= 3, "need T >= 2 and 1 <= ndim <= 3");
+  const long long n = (long long)(T - 1) * 16, blocks = (n + 127) / 128;
+  ising_class_tables_kernel<<<(unsigned)(blocks > 148 * 8 ? 148 * 8 : blocks), 128, 0, (cudaStream_t)stream>>>(
+      log_temp, field, T, ndim, thr, lut);
+  NQ_LAUNCHED();
+  return NQ_OK;
+}
+
+extern "C" int nq_ising_grad_mean(const double* logP_lt, const double* logP_h, const double* rep_lt, const double* rep_h,
+                                  int64_t R, int32_t Dl, int32_t Dh, double w_logp, double w_rep, float* mean_out,
+                                  void* stream) {
+  NQ_RANGE();
+  NQ_CHECK_ARG(logP_lt && logP_h && rep_lt && rep_h && mean_out, "null pointer");
+  NQ_CHECK_ARG(R >= 1 && Dl >= 1 && Dh >= 1, "need R, Dl, Dh >= 1");
+  ising_grad_mean_kernel<<<(unsigned)(Dl + Dh), 256, 0, (cudaStream_t)stream>>>(logP_lt, logP_h, rep_lt, rep_h, R, Dl, Dh,
+                                                                              w_logp, w_rep, mean_out);
   NQ_LAUNCHED();
   return NQ_OK;
 }

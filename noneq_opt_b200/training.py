@@ -171,3 +171,194 @@ class LangevinTrainer:
   @property
   def coeffs(self):
     return self.variables
+
+
+# ================================================================================ Ising
+def _ising_component(param, times):
+  """(variables [D] f32, basis [T, D] f32, scale | None, offset1 | None, offset2 | None) such that
+  value(times) = ((scale * (basis @ variables)) + offset1) + offset2 in the float32 operation order of the
+  parameterisation itself -- exact (bit-equal to `param(times)`) for the drivers' composition
+  AddBaseline(ConstrainEndpoints(Chebyshev)) and its sub-forms; any other affine Parameterization goes
+  through its Jacobian and value at zero (equal up to float32 rounding)."""
+  F32 = np.float32
+  times = np.asarray(times, F32)
+  offset2 = None
+  inner = param
+  if isinstance(inner, p10n.AddBaseline):
+    offset2 = np.asarray(inner.baseline(times), F32)
+    inner = inner.wrapped
+  scale = offset1 = None
+  if isinstance(inner, p10n.ConstrainEndpoints) and isinstance(inner.wrapped, p10n.Chebyshev):
+    x0, x1 = (F32(v) for v in inner.domain)
+    scale = inner._envelope(times)
+    offset1 = (F32(inner.y0) + (times - x0) / (x1 - x0) * F32(inner.y1 - inner.y0)).astype(F32)
+    inner = inner.wrapped
+  if isinstance(inner, p10n.Chebyshev) and np.ndim(inner.weights) == 1:
+    return np.asarray(inner.weights, F32).copy(), np.asarray(inner.jacobian(times), F32), scale, offset1, offset2
+  # generic affine form of the whole component
+  leaves = [np.asarray(l, F32).reshape(-1) for l in tree.tree_leaves(param.variables)]
+  v0 = np.concatenate(leaves).astype(F32)
+  jac = np.asarray(param.jacobian(times), F32)
+  off = (np.asarray(param(times), np.float64) - jac.astype(np.float64) @ v0.astype(np.float64)).astype(F32)
+  return v0, jac, None, off, None
+
+
+class IsingTrainer:
+  """One CUDA graph per training step of the Ising drivers (`run_ising_opt.py:77-102` around
+  `ising.get_train_step`, ising.py:263-290): per step
+
+      seed              next(seed_stream)                                     (:57-61)
+      seeds           = split(seed, batch_size)                               (:283)
+      schedule tables = params_fn(opt_state)(times)                           (:284, parameterization.py)
+      class tables    -> checkerboard sweeps -> per-replica REINFORCE / logP / reparam gradient (:179-236)
+      mean over the batch, clip_grads, Adam                                   (:286-288)
+
+  with every operand resident in HBM: chain key, replica keys, schedule variables and tables, the class
+  tables (`nq_ising_class_tables`), summaries, per-replica gradients, Adam moments and step counter.  The launch
+  sequence is issued once through the C ABI under CUDA-graph capture and replayed: no host synchronisation, no
+  host arithmetic, no allocation per step (the step-by-step `get_train_step` builds its tables with numpy and
+  reads the batch mean back).
+
+  Args: schedule (ising.IsingSchedule of Parameterizations), initial_spins (one lattice), batch_size, time_steps,
+    key (uint32[2]; `PRNGKey(seed)` of seed_stream), loss_function (ising.total_entropy_production |
+    ising.total_work), term ('reinforce' | 'logP' | 'reparam'), max_grad (clip_grads bound of get_train_step),
+    step_size / decay_steps / decay_rate / b1 / b2 / eps (adam(exponential_decay(...))),
+    seed_source: 'seed_stream' -- the reference's generator, which yields the NEW CHAIN KEY itself (:57-61) --
+      or 'split' -- `key, sub = split(key)` and the step runs on `sub`.
+  """
+
+  def __init__(self, schedule, initial_spins, batch_size, time_steps, key, *,
+               loss_function=None, term='reinforce', max_grad=1e4, step_size=0.1, decay_steps=0.0, decay_rate=1.0,
+               b1=0.9, b2=0.999, eps=1e-8, seed_source='seed_stream', use_graph=True):
+    from . import ising
+    self.device = dev = _lib.require_cuda()
+    self.lib = _lib.lib()
+    loss_function = ising.total_entropy_production if loss_function is None else loss_function
+    kind = ising._loss_kind(loss_function)
+    if kind == 'generic':
+      raise NotImplementedError('IsingTrainer runs the two closed-form losses (total_work, total_entropy_production); '
+                                'use ising.get_train_step for an arbitrary LossFn')
+    if seed_source not in ('seed_stream', 'split'):
+      raise ValueError("seed_source must be 'seed_stream' or 'split'")
+    self._kind = {'work': 0, 'entropy': 1}[kind]
+    self._seed_row = 0 if seed_source == 'seed_stream' else 1
+    self.R, self.T = int(batch_size), int(time_steps)
+    self.schedule = schedule
+    self.times = np.linspace(0, 1, self.T, dtype=np.float32)
+    f32 = dict(dtype=torch.float32, device=dev)
+    comps = [_ising_component(schedule.log_temp, self.times), _ising_component(schedule.field, self.times)]
+    self.Dl, self.Dh = int(comps[0][0].shape[0]), int(comps[1][0].shape[0])
+    if self.Dl > 32 or self.Dh > 32:
+      raise ValueError(f'at most 32 variables per schedule component (got {self.Dl}, {self.Dh})')
+    P = self.Dl + self.Dh
+    self.variables = torch.from_numpy(np.concatenate([comps[0][0], comps[1][0]])).to(dev)
+
+    def up(a):
+      return None if a is None else torch.from_numpy(np.ascontiguousarray(a, np.float32)).to(dev)
+    self._comp = [tuple(up(a) for a in c[1:]) for c in comps]      # (basis, scale, offset1, offset2) per component
+    self._J = [torch.from_numpy(np.ascontiguousarray(np.asarray(p.jacobian(self.times), np.float64))).to(dev)
+               for p in (schedule.log_temp, schedule.field)]
+    self.log_temp, self.field = torch.empty(self.T, **f32), torch.empty(self.T, **f32)
+    # lattice: packed once, its spin / bond sums measured once (the initial state is the same every step)
+    spins = ising._as_cuda(initial_spins)
+    shape = tuple(int(v) for v in spins.shape)
+    if any(v % 2 for v in shape):
+      raise ValueError(f'All entries in `shape` must be even; got {shape}.')
+    self._shape, ndim = shape, len(shape)
+    self._bits = ising._pack(spins, ndim).reshape(1, -1)
+    words = (int(np.prod(shape)) + 31) // 32
+    dims = (C.c_int32 * 3)(*(list(shape) + [1] * (3 - ndim)))
+    square = ndim == 2 and shape[0] == shape[1]
+    self._desc = _lib.NqIsingDesc(L=shape[0], T=self.T, R=self.R, spins0_broadcast=1, sweep_key_mode=0,
+                                  ndim=0 if square else ndim, dims=dims)
+    self._ndim = ndim
+    self._MB0 = torch.empty((1, 2), dtype=torch.int64, device=dev)
+    _lib.check(self.lib.nq_ising_measure(_lib.ptr(self._bits), ndim, dims, 1, _lib.ptr(self._MB0), _lib.stream_arg()))
+    R, Tm1 = self.R, self.T - 1
+    self._thr = torch.empty((Tm1, 16), dtype=torch.int32, device=dev)
+    self._lut = torch.empty((Tm1, 4, 16), dtype=torch.float64, device=dev)
+    self.final_bits = torch.empty((R, words), dtype=torch.int32, device=dev)
+    self.summary_raw = torch.zeros((_lib.NQ_IS_NSUMMARY, R, Tm1), **f32)
+    self._partials = torch.zeros((_lib.NQ_IS_NPARTIAL, R, Tm1), **f32)
+    self._ws_bytes = self.lib.nq_ising_workspace_bytes(C.byref(self._desc))
+    self._ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=dev) if self._ws_bytes else None
+    self.loss = torch.empty(R, **f32)
+    self._g = [torch.empty((R, d), dtype=torch.float64, device=dev) for d in (self.Dl, self.Dh, self.Dl, self.Dh)]
+    self.grad = torch.zeros(P, **f32)          # batch-mean gradient (before clipping)
+    self.grad_clipped = torch.zeros(P, **f32)
+    self.adam_m, self.adam_v = torch.zeros(P, **f32), torch.zeros(P, **f32)
+    self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
+    self.key = nqrandom.as_key_tensor(key, dev).reshape(2).clone()
+    self._keys2 = torch.empty((2, 2), dtype=self.key.dtype, device=dev)
+    self.seeds = torch.empty((R, 2), dtype=self.key.dtype, device=dev)
+    w_logp, w_rep = {'reinforce': (1.0, 1.0), 'logP': (1.0, 0.0), 'reparam': (0.0, 1.0)}[term]
+    self._w = (w_logp, w_rep)
+    self._adam = _lib.NqAdamDesc(float(step_size), float(decay_steps), float(decay_rate), float(b1), float(b2),
+                                 float(eps), float(max_grad or 0.0), 1.0, 0.0, 1.0)
+    self._n_sites = int(np.prod(shape))
+    self._graph = None
+    self._use_graph = bool(use_graph)
+    self.launches_per_step = None
+
+  def _enqueue(self):
+    lib, st, ptr, check = self.lib, _lib.stream_arg(), _lib.ptr, _lib.check
+    check(lib.nq_random_split_dev(ptr(self.key), 2, 0, 2, ptr(self._keys2), st))                       # seed_stream :57-61
+    self.key.copy_(self._keys2[0])
+    check(lib.nq_random_split_dev(ptr(self._keys2[self._seed_row]), self.R, 0, self.R, ptr(self.seeds), st))   # :283
+    for tab, (basis, scale, off1, off2), o, D in ((self.log_temp, self._comp[0], 0, self.Dl),
+                                                  (self.field, self._comp[1], self.Dl, self.Dh)):
+      check(lib.nq_schedule_compose(ptr(basis), ptr(self.variables[o:o + D]), ptr(scale), ptr(off1), ptr(off2), self.T, D,
+                                    ptr(tab), st))                                                      # :284
+    check(lib.nq_ising_class_tables(ptr(self.log_temp), ptr(self.field), self.T, self._ndim, ptr(self._thr),
+                                    ptr(self._lut), st))
+    check(lib.nq_ising_run(C.byref(self._desc), ptr(self._thr), ptr(self._lut), ptr(self.field), ptr(self.log_temp),
+                           ptr(self._bits), ptr(self.seeds), ptr(self.final_bits), ptr(self.summary_raw),
+                           ptr(self._partials), None, None, ptr(self._ws), self._ws_bytes, st))         # :153-173
+    check(lib.nq_ising_grad_assemble_dev(self._kind, self.T, self.R, self._n_sites, 1, ptr(self.log_temp),
+                                         ptr(self.field), ptr(self.summary_raw), ptr(self._partials), ptr(self._MB0),
+                                         ptr(self._J[0]), self.Dl, ptr(self._J[1]), self.Dh, ptr(self.loss),
+                                         ptr(self._g[0]), ptr(self._g[1]), ptr(self._g[2]), ptr(self._g[3]), st))   # :179-198
+    check(lib.nq_ising_grad_mean(ptr(self._g[0]), ptr(self._g[1]), ptr(self._g[2]), ptr(self._g[3]), self.R, self.Dl,
+                                 self.Dh, self._w[0], self._w[1], ptr(self.grad), st))                  # :286
+    check(lib.nq_adam_step(C.byref(self._adam), self.Dl + self.Dh, None, None, ptr(self.grad), ptr(self.variables),
+                           ptr(self.adam_m), ptr(self.adam_v), ptr(self.step_count), ptr(self.grad_clipped), st))  # :288
+
+  _capture = LangevinTrainer._capture
+  step = LangevinTrainer.step
+
+  @property
+  def summary(self):
+    """IsingSummary [batch, T-1] of the LAST step (device tensors; views of the trainer's buffer)."""
+    from . import ising
+    return ising.IsingSummary(*[self.summary_raw[f] for f in range(_lib.NQ_IS_NSUMMARY)])
+
+  def current_schedule(self):
+    """The schedule pytree with the current variables (one device-to-host copy of Dl + Dh floats)."""
+    w = self.variables.cpu().numpy()
+    leaves, treedef = tree.tree_flatten(self.schedule)
+    out, o = [], 0
+    for leaf in leaves:
+      size = int(np.prod(np.shape(leaf))) if np.shape(leaf) else 1
+      out.append(w[o:o + size].reshape(np.shape(leaf)).copy())
+      o += size
+    return tree.tree_unflatten(treedef, out)
+
+  def run(self, training_steps, record_summaries=False):
+    """`training_steps` steps back to back, no host synchronisation.  Returns dict(mean_loss [n],
+    variables [n + 1, Dl + Dh] (row j = before step j), summaries [n, 7, batch, T-1] if asked) as device tensors."""
+    n = int(training_steps)
+    hist = torch.empty((n + 1, self.Dl + self.Dh), dtype=torch.float32, device=self.device)
+    mean_loss = torch.empty(n, dtype=torch.float32, device=self.device)
+    summaries = (torch.empty((n,) + tuple(self.summary_raw.shape), dtype=torch.float32, device=self.device)
+                 if record_summaries else None)
+    for j in range(n):
+      hist[j].copy_(self.variables)
+      self.step()
+      mean_loss[j] = self.loss.mean()
+      if summaries is not None:
+        summaries[j].copy_(self.summary_raw)
+    hist[n].copy_(self.variables)
+    out = dict(mean_loss=mean_loss, variables=hist)
+    if summaries is not None:
+      out['summaries'] = summaries
+    return out

@@ -112,3 +112,106 @@ def test_graph_capture_of_the_persistent_scheduler(cuda):
   np.testing.assert_array_equal(runs[0][1], runs[1][1])
   assert runs[0][2] == runs[1][2] == 7      # split3, split(B), schedule, ring init, persistent kernel, finalize, adam
   assert np.all(np.diff(runs[1][1]) < 0)     # three Adam steps on the linear protocol lower the mean work
+
+
+# ================================================================================ Ising (training.IsingTrainer)
+def _ising_rel(a, b):
+  return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.mark.parametrize('ndim', [1, 2, 3])
+def test_device_class_tables_are_bit_equal_to_the_host_tables(cuda, ndim):
+  """nq_ising_class_tables (thresholds and log-sigmoid tables built on the device from device schedule tables)
+  against ising.class_tables (numpy) over a dense (log-temperature, field) grid: same float32 operation order,
+  binary64 transcendentals rounded once -- every threshold and every table entry must be bit-equal."""
+  import ctypes as C
+  from noneq_opt_b200 import _lib, ising
+  rs = np.random.RandomState(ndim)
+  lts = np.linspace(-1.6, 3.2, 97, dtype=np.float32)
+  hs = np.linspace(-3.5, 3.5, 83, dtype=np.float32)
+  lt = np.concatenate([[0.3], np.repeat(lts, len(hs)), rs.uniform(-2, 3, 3000)]).astype(np.float32)
+  h = np.concatenate([[0.0], np.tile(hs, len(lts)), rs.uniform(-4, 4, 3000)]).astype(np.float32)
+  T = len(lt)
+  thr_h, lut_h = ising.class_tables(lt, h, ndim)
+  lt_d, h_d = torch.from_numpy(lt).cuda(), torch.from_numpy(h).cuda()
+  thr_d = torch.empty((T - 1, 16), dtype=torch.int32, device='cuda')
+  lut_d = torch.empty((T - 1, 4, 16), dtype=torch.float64, device='cuda')
+  _lib.check(_lib.lib().nq_ising_class_tables(_lib.ptr(lt_d), _lib.ptr(h_d), T, ndim, _lib.ptr(thr_d), _lib.ptr(lut_d),
+                                              _lib.stream_arg()))
+  np.testing.assert_array_equal(thr_d.cpu().numpy().view(np.uint32), thr_h)
+  np.testing.assert_array_equal(lut_d.cpu().numpy().view(np.uint64), lut_h.view(np.uint64))
+
+
+def test_ising_trainer_follows_the_reference_source_through_graph_replay(cuda):
+  """tests/golden/reference_train_step.npz -- three steps of the reference's own get_train_step (ising.py:263-290),
+  generated by make_reference_golden.py -- followed by training.IsingTrainer: one CUDA-graph replay per step,
+  no host arithmetic and no synchronisation inside a step."""
+  import os
+  from noneq_opt_b200 import ising, parameterization as p10n, training
+  g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_train_step.npz'))
+  c = {k.split('/')[1]: g[k] for k in g.files if k.startswith('train/')}
+  sched = ising.IsingSchedule(p10n.Chebyshev(c['w_lt']), p10n.Chebyshev(c['w_h']))
+  tr = training.IsingTrainer(sched, -np.ones((16, 16), np.float32), int(c['B']), int(c['T']), c['seed'],
+                             loss_function=ising.total_entropy_production, step_size=float(c['lr']), max_grad=1e4,
+                             seed_source='split')
+  for j in range(3):
+    tr.step()
+    got = tr.variables.cpu().numpy().reshape(2, -1)
+    assert _ising_rel(got, c['weights'][j]) < 2e-5, (j, _ising_rel(got, c['weights'][j]))
+    ep = tr.summary.entropy_production.cpu().numpy()
+    assert np.abs(ep - c['entropy_production'][j]).max() <= 2e-4 * max(1.0, np.abs(c['entropy_production'][j]).max())
+  assert tr._graph is not None and tr.launches_per_step >= 8
+  assert int(tr.step_count.item()) == 3
+
+
+@pytest.mark.parametrize('loss,term,use_graph', [('total_entropy_production', 'reinforce', True),
+                                                 ('total_work', 'reinforce', True),
+                                                 ('total_entropy_production', 'logP', False)])
+def test_ising_trainer_equals_the_host_train_step(cuda, loss, term, use_graph):
+  """The drivers' schedule composition AddBaseline(ConstrainEndpoints(Chebyshev(w), 0, 0), baseline)
+  (run_ising_opt.py:45-66), seed_stream keys, clip_grads(max_grad = 1), adam(exponential_decay(0.1, n, 0.01)):
+  the device-resident step against ising.get_train_step* on the host.  Schedule tables: bit-equal (same float32
+  order); variables after every step: equal to float32 rounding of the batch mean."""
+  from noneq_opt_b200 import ising, optimizers, parameterization as p10n, training
+  L, R, T, n, D = 32, 24, 21, 4, 8
+  rs = np.random.RandomState(3)
+  w0 = (0.05 * rs.normal(size=(2, D))).astype(np.float32)
+  sched = ising.IsingSchedule(
+      p10n.AddBaseline(p10n.ConstrainEndpoints(p10n.Chebyshev(w0[0]), 0., 0.), ising.log_temp_baseline(min_temp=0.65)),
+      p10n.AddBaseline(p10n.ConstrainEndpoints(p10n.Chebyshev(w0[1]), 0., 0.), ising.field_baseline()))
+  spins0 = -np.ones((L, L), np.float32)
+  loss_fn = getattr(ising, loss)
+  opt = optimizers.adam(optimizers.exponential_decay(0.1, n, 0.01))
+  state = opt.init_fn(sched)
+  factory = {'reinforce': ising.get_train_step_REINFORCE, 'logP': ising.get_train_step_logP}[term]
+  step_fn = factory(opt, spins0, R, T, loss_fn, 'rev', max_grad=1.0)
+  stream = ising.seed_stream(0)
+  tr = training.IsingTrainer(sched, spins0, R, T, J.PRNGKey(0), loss_function=loss_fn, term=term, max_grad=1.0,
+                             step_size=0.1, decay_steps=n, decay_rate=0.01, use_graph=use_graph)
+  times = np.linspace(0, 1, T, dtype=np.float32)
+  for j in range(n):
+    host_tables = opt.params_fn(state)(times)
+    state, summary, mean_grad = step_fn(state, j, next(stream))
+    tr.step()
+    np.testing.assert_array_equal(tr.log_temp.cpu().numpy(), np.asarray(host_tables.log_temp))   # tables of THIS step
+    np.testing.assert_array_equal(tr.field.cpu().numpy(), np.asarray(host_tables.field))
+    for f in ising.IsingSummary._fields:
+      assert torch.equal(getattr(tr.summary, f), getattr(summary, f)), f
+    p = opt.params_fn(state)
+    want = np.concatenate([np.asarray(p.log_temp.wrapped.wrapped.weights), np.asarray(p.field.wrapped.wrapped.weights)])
+    got = tr.variables.cpu().numpy()
+    assert _ising_rel(got, want) < 5e-6, (j, _ising_rel(got, want))
+    mg = np.concatenate([np.asarray(mean_grad.log_temp.wrapped.wrapped.weights),
+                         np.asarray(mean_grad.field.wrapped.wrapped.weights)])
+    assert _ising_rel(tr.grad.cpu().numpy(), mg) < 5e-6
+  cur = tr.current_schedule()
+  np.testing.assert_array_equal(np.asarray(cur.log_temp.wrapped.wrapped.weights), tr.variables[:D].cpu().numpy())
+
+
+def test_ising_trainer_rejects_what_it_cannot_run(cuda):
+  from noneq_opt_b200 import ising, parameterization as p10n, training
+  sched = ising.IsingSchedule(p10n.Chebyshev(np.zeros(4, np.float32)), p10n.Chebyshev(np.zeros(4, np.float32)))
+  with pytest.raises(NotImplementedError):
+    training.IsingTrainer(sched, -np.ones((8, 8), np.float32), 2, 5, J.PRNGKey(0), loss_function=lambda a, b, s: s.work.sum())
+  with pytest.raises(ValueError):
+    training.IsingTrainer(sched, -np.ones((7, 8), np.float32), 2, 5, J.PRNGKey(0))
