@@ -173,6 +173,14 @@ int nq_langevin_stationary(const NqLangevinDesc* desc /*host*/, float r0,
 int nq_langevin_apply(const NqLangevinDesc* desc /*host*/, float r0, float* x, uint32_t* rng,
                       float* log_prob, int64_t n, void* stream);
 
+/* apply_fn on rank-generic states (simulate.py:66-97): position [n_states][n_particles][dim], ONE key per
+ * state; the draw is jax.random.normal(split, [1, n_particles, dim]) (one threefry stream over all elements),
+ * log_prob [n_states] the sum of Normal.log_prob over every element.  The reference's energy closures read
+ * position[0][0] only (potentials.py:27-52), so element 0 feels landscape + trap and the others diffuse freely. */
+int nq_langevin_apply_nd(const NqLangevinDesc* desc, float r0, float* position, uint32_t* rng /*[n_states][2]*/,
+                         float* log_prob /*nullable [n_states]*/, int64_t n_states, int32_t n_particles, int32_t dim,
+                         void* stream);
+
 /* ------------------------------------------------------------------ Ising */
 #define NQ_ISING_NCLASS 10 /* (spin in {-1,+1}) x (neighbour sum in {-4,-2,0,2,4}) */
 /* class table slot = 8*(s>0) + (nsum+4)/2 ; slots 5-7 and 13-15 unused */

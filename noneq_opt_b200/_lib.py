@@ -68,6 +68,7 @@ SIGNATURES = {
                                      _P, _P, C.c_size_t, _P]),
     'nq_langevin_stationary': (C.c_int, [C.POINTER(NqLangevinDesc), C.c_float, _P, _P, C.c_int64, _P, _P, _P]),
     'nq_langevin_apply': (C.c_int, [C.POINTER(NqLangevinDesc), C.c_float, _P, _P, _P, C.c_int64, _P]),
+    'nq_langevin_apply_nd': (C.c_int, [C.POINTER(NqLangevinDesc), C.c_float, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     'nq_ising_words_per_lattice': (C.c_size_t, [C.c_int32]),
     'nq_ising_workspace_bytes': (C.c_size_t, [C.POINTER(NqIsingDesc)]),
     'nq_ising_run': (C.c_int, [C.POINTER(NqIsingDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,

@@ -251,8 +251,10 @@ def fit_linear_to_cheby(end_time, dt, r0_init, r0_final, degree):
 
 # ------------------------------------------------------------------------------ integrator API
 def brownian(energy_or_force, shift, dt, kT=0.1, gamma=0.1):
-  """(init_fn, apply_fn) of the Euler-Maruyama Brownian integrator; states may be batched:
-  position `[..., 1, 1]`, rng `[..., 2]`."""
+  """(init_fn, apply_fn) of the Euler-Maruyama Brownian integrator (barrier_crossing.py:28-94 = simulate.py:33-99).
+  States may be batched: position `[..., N, dim]`, rng `[..., 2]` -- one key per state, as in the reference, whose
+  draw for a state is `jax.random.normal(split, [1, N, dim])`.  N = dim = 1 (the hot path) runs `nq_langevin_apply`,
+  any other particle count / dimension `nq_langevin_apply_nd`; `log_prob` is the sum over all elements (:90)."""
   energy = as_energy(energy_or_force)
   sh = as_shift(shift)
 
@@ -263,12 +265,26 @@ def brownian(energy_or_force, shift, dt, kT=0.1, gamma=0.1):
     device = _lib.require_cuda()
     r0 = float(kwargs.get('r0', 0.0))
     pos = _dev_f32(state.position, device)
+    if pos.dim() < 2:
+      raise ValueError('state.position must have shape [..., N, dim]')
+    desc = _desc(energy, sh, 1, 0, dt, kT, float(np.asarray(state.mass)), gamma)
+    n_part, dim = int(pos.shape[-2]), int(pos.shape[-1])
+    if n_part * dim != 1:      # rank-generic state (simulate.py:66-97): one key per [N, dim] state
+      batch = tuple(pos.shape[:-2])
+      n_states = int(np.prod(batch)) if batch else 1
+      x = pos.reshape(n_states, n_part * dim).clone()
+      rng = nqrandom.as_key_tensor(state.rng, device).reshape(-1, 2).clone()
+      if rng.shape[0] != n_states:
+        raise ValueError('state.position and state.rng disagree on the batch size')
+      lp = torch.empty(n_states, dtype=torch.float32, device=device)
+      _lib.check(_lib.lib().nq_langevin_apply_nd(C.byref(desc), r0, _lib.ptr(x), _lib.ptr(rng), _lib.ptr(lp), n_states,
+                                                 n_part, dim, _lib.stream_arg()))
+      return BrownianState(x.reshape(pos.shape), state.mass, rng.reshape(batch + (2,)), lp.reshape(batch))
     x = pos.reshape(-1).clone()
     rng = nqrandom.as_key_tensor(state.rng, device).reshape(-1, 2).clone()
     if rng.shape[0] != x.shape[0]:
       raise ValueError('state.position and state.rng disagree on the batch size')
     lp = torch.empty_like(x)
-    desc = _desc(energy, sh, 1, 0, dt, kT, float(np.asarray(state.mass)), gamma)
     _lib.check(_lib.lib().nq_langevin_apply(C.byref(desc), r0, _lib.ptr(x), _lib.ptr(rng), _lib.ptr(lp),
                                             x.shape[0], _lib.stream_arg()))
     batch = pos.shape[:-2]

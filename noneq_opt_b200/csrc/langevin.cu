@@ -91,14 +91,15 @@ struct PotLaunchers {
   ReplayLauncher replay;
   StationaryLauncher stationary;
   ApplyLauncher apply;
+  ApplyNdLauncher apply_nd;
 };
 
 static PotLaunchers launchers(int potential) {
   switch (potential) {
-    case NQ_POT_SPRING: return {pot_spring_main, pot_spring_pair, pot_spring_persistent, pot_spring_replay, pot_spring_stationary, pot_spring_apply};
+    case NQ_POT_SPRING: return {pot_spring_main, pot_spring_pair, pot_spring_persistent, pot_spring_replay, pot_spring_stationary, pot_spring_apply, pot_spring_apply_nd};
     case NQ_POT_BIOMOLECULE:
-      return {pot_biomolecule_main, pot_biomolecule_pair, pot_biomolecule_persistent, pot_biomolecule_replay, pot_biomolecule_stationary, pot_biomolecule_apply};
-    default: return {pot_shifted_main, pot_shifted_pair, pot_shifted_persistent, pot_shifted_replay, pot_shifted_stationary, pot_shifted_apply};
+      return {pot_biomolecule_main, pot_biomolecule_pair, pot_biomolecule_persistent, pot_biomolecule_replay, pot_biomolecule_stationary, pot_biomolecule_apply, pot_biomolecule_apply_nd};
+    default: return {pot_shifted_main, pot_shifted_pair, pot_shifted_persistent, pot_shifted_replay, pot_shifted_stationary, pot_shifted_apply, pot_shifted_apply_nd};
   }
 }
 
@@ -379,6 +380,23 @@ extern "C" int nq_langevin_apply(const NqLangevinDesc* desc, float r0, float* x,
   NQ_CHECK_ARG(n >= 1 && x && rng, "bad arguments");
   const int blocks = (int)((n + kThreads - 1) / kThreads);
   launchers(c.potential).apply(c, r0, x, rng, log_prob, n, blocks, desc->math_mode == NQ_MATH_FAST, (cudaStream_t)stream);
+  NQ_LAUNCHED();
+  return NQ_OK;
+}
+
+extern "C" int nq_langevin_apply_nd(const NqLangevinDesc* desc, float r0, float* position, uint32_t* rng, float* log_prob,
+                                    int64_t n_states, int32_t n_particles, int32_t dim, void* stream) {
+  NQ_RANGE();
+  NQ_CHECK_ARG(desc != nullptr, "desc is null");
+  NqLangevinDesc d1 = *desc;
+  if (d1.steps < 1) d1.steps = 1;
+  LangevinConsts c;
+  int rc = make_langevin_consts(&d1, &c);
+  if (rc) return rc;
+  NQ_CHECK_ARG(n_states >= 1 && n_states <= 0x7fffffffll && position && rng, "bad arguments");
+  NQ_CHECK_ARG(n_particles >= 1 && dim >= 1 && (long long)n_particles * dim <= 0x3fffffffll, "bad state shape %d x %d",
+               n_particles, dim);
+  launchers(c.potential).apply_nd(c, r0, position, rng, log_prob, n_states, n_particles * dim, (cudaStream_t)stream);
   NQ_LAUNCHED();
   return NQ_OK;
 }

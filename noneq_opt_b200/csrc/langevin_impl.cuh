@@ -1096,6 +1096,64 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const LangevinConsts c,
   if (log_prob) log_prob[gid] = lp;
 }
 
+// apply_fn on a rank-generic state: position [N][dim] (E = N * dim elements), ONE key per state (simulate.py:66-97,
+// barrier_crossing.py:66-92).  dist.sample(seed=split) draws jax.random.normal(split, [1, N, dim]): element e
+// consumes word e of threefry_2x32(split, iota(E)) -- counter pairing (e, e + ceil(E/2)), odd sizes padded -- so a
+// thread owns a pair.  The reference's energy closures read position[0][0] only (potentials.py:27-52): element 0
+// feels landscape + trap, every other element has zero force and diffuses freely.  log_prob sums
+// Normal.log_prob = -((dR/sigma) - (mean/sigma))^2 / 2 - log_norm over all elements (tfp's form, exact here;
+// binary64 accumulation, rounded once).  One CTA per state.
+template <int POT>
+__global__ void __launch_bounds__(128) apply_nd_kernel(const LangevinConsts c, float r0, float* pos, uint32_t* rng_io,
+                                                       float* log_prob, long long n_states, int E) {
+  __shared__ uint32_t key_s[4];
+  __shared__ double red_s[4];
+  const long long b = blockIdx.x;
+  if (b >= n_states) return;
+  float* x = pos + b * E;
+  if (threadIdx.x == 0) {
+    uint32_t n0, n1, s0, s1;
+    split2(rng_io[2 * b], rng_io[2 * b + 1], n0, n1, s0, s1);   // key, split = random.split(state.rng)  :79
+    key_s[0] = n0; key_s[1] = n1; key_s[2] = s0; key_s[3] = s1;
+  }
+  __syncthreads();
+  const KeySchedule ks = key_schedule(key_s[2], key_s[3]);
+  const int half = (E + 1) / 2;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const int j = i + half;
+    uint32_t y0, y1;
+    threefry2x32(ks, (uint32_t)i, j < E ? (uint32_t)j : 0u, y0, y1);
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const int e = w ? j : i;
+      if (e >= E) continue;
+      const float xi = normal_from_bits<false>(w ? y1 : y0);
+      const float xe = x[e];
+      float mean = 0.f;
+      if (e == 0) {   // force on position[0][0] in the reference's order (:60, 67-69)
+        Landscape<POT, false> land;
+        land.eval(c, xe);
+        mean = __fmul_rn(2.0f, half_mean<POT, false>(c, land, xe, r0));
+      }
+      const float dR = __fadd_rn(__fmul_rn(xi, c.sigma), mean);
+      const float z = __fsub_rn(__fdiv_rn(dR, c.sigma), __fdiv_rn(mean, c.sigma));
+      acc += (double)__fsub_rn(__fmul_rn(-0.5f, __fmul_rn(z, z)), c.log_norm);
+      float xn = __fadd_rn(xe, dR);
+      if (c.shift_kind == NQ_SHIFT_PERIODIC) xn = py_mod(xn, c.box);
+      x[e] = xn;
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red_s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (log_prob) log_prob[b] = (float)((red_s[0] + red_s[1]) + (red_s[2] + red_s[3]));
+    rng_io[2 * b] = key_s[0];
+    rng_io[2 * b + 1] = key_s[1];
+  }
+}
+
 // per-potential launchers (defined in langevin_pot*.cu through NQ_DEFINE_POT_LAUNCHERS)
 using MainLauncher = int (*)(const LangevinConsts&, const LangevinIO&, int blocks, bool fast, bool record, cudaStream_t);
 using PairLauncher = int (*)(const LangevinConsts&, const LangevinIO&, int blocks, bool fast, cudaStream_t);
@@ -1106,6 +1164,7 @@ using StationaryLauncher = int (*)(const LangevinConsts&, float r0, const float*
                                    float*, int blocks, bool fast, cudaStream_t);
 using ApplyLauncher = int (*)(const LangevinConsts&, float r0, float*, uint32_t*, float*, long long, int blocks,
                               bool fast, cudaStream_t);
+using ApplyNdLauncher = int (*)(const LangevinConsts&, float r0, float*, uint32_t*, float*, long long, int E, cudaStream_t);
 
 #define NQ_MAIN_CASE(POT, DD)                                                                          \
   case DD:                                                                                             \
@@ -1186,6 +1245,11 @@ using ApplyLauncher = int (*)(const LangevinConsts&, float r0, float*, uint32_t*
     if (fast) apply_kernel<POT, true><<<blocks, kThreads, 0, st>>>(c, r0, x, rng, lp, n);              \
     else apply_kernel<POT, false><<<blocks, kThreads, 0, st>>>(c, r0, x, rng, lp, n);                  \
     return 0;                                                                                          \
+  }                                                                                                    \
+  int NAME##_apply_nd(const LangevinConsts& c, float r0, float* x, uint32_t* rng, float* lp,           \
+                      long long n, int E, cudaStream_t st) {                                           \
+    apply_nd_kernel<POT><<<(unsigned)n, 128, 0, st>>>(c, r0, x, rng, lp, n, E);                        \
+    return 0;                                                                                          \
   }
 
 #define NQ_DECLARE_POT_LAUNCHERS(NAME)                                                                 \
@@ -1196,7 +1260,8 @@ using ApplyLauncher = int (*)(const LangevinConsts&, float r0, float*, uint32_t*
   int NAME##_replay(const LangevinConsts&, const ReplayIO&, dim3, size_t, bool, cudaStream_t);         \
   int NAME##_stationary(const LangevinConsts&, float, const float*, const uint32_t*, long long, float*, \
                         float*, int, bool, cudaStream_t);                                              \
-  int NAME##_apply(const LangevinConsts&, float, float*, uint32_t*, float*, long long, int, bool, cudaStream_t);
+  int NAME##_apply(const LangevinConsts&, float, float*, uint32_t*, float*, long long, int, bool, cudaStream_t); \
+  int NAME##_apply_nd(const LangevinConsts&, float, float*, uint32_t*, float*, long long, int, cudaStream_t);
 
 NQ_DECLARE_POT_LAUNCHERS(pot_spring)
 NQ_DECLARE_POT_LAUNCHERS(pot_biomolecule)

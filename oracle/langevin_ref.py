@@ -183,6 +183,26 @@ def brownian_apply(pot, sc, x, rng, r0, shift='free', dtype=F32):
   return xn, new_rng, lp, dR, mean
 
 
+def brownian_apply_nd(pot, sc, position, rng, r0, shift='free', dtype=F32):
+  """apply_fn (simulate.py:82-97 = barrier_crossing.py:77-92) on ONE rank-generic state: position [N, dim],
+  rng uint32[2].  The reference's energy closures read position[0][0] only (potentials.py:27-52), so -grad E is
+  zero everywhere else.  dist.sample(seed=split) = jax.random.normal(split, [1, N, dim]) * sigma + mean;
+  log_prob = sum over all elements of Normal.log_prob (:90).  Returns (position', rng', log_prob, dR)."""
+  d = dtype
+  position = np.asarray(position, d)
+  N, dim = position.shape
+  F = np.zeros((N, dim), d)
+  F[0, 0] = force(pot, position[0:1, 0], r0, d)[0]
+  mean = ((F * sc.nu).astype(d) * sc.dt).astype(d)
+  (new_rng, sub) = J.split(np.asarray(rng, np.uint32), 2)
+  xi = J.normal(sub, (1, N, dim)).astype(d).reshape(N, dim)
+  dR = ((xi * sc.sigma).astype(d) + mean).astype(d)
+  z = ((dR / sc.sigma).astype(d) - (mean / sc.sigma).astype(d)).astype(d)
+  lp = ((d(-0.5) * (z * z).astype(d)).astype(d) - sc.log_norm).astype(d)
+  xn = apply_shift(position.reshape(-1), dR.reshape(-1), shift, d).reshape(N, dim)
+  return xn, new_rng, d(lp.astype(np.float64).sum()), dR
+
+
 def make_schedule_chebyshev(S, coeffs, r0_init, r0_final, dtype=F32):
   """MakeSchedule_chebyshev(arange(S+1), ...) :145-151 -> r[S+1]; also the [S-1, D] Jacobian.
 

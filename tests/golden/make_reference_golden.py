@@ -158,9 +158,68 @@ def schedule_cases():
                        constant=to_np(ref_p10n.Constant(jnp.array(0.7))(x))))
 
 
+def multi_particle_cases():
+  """simulate.brownian (simulate.py:33-99) on rank-generic states [N, dim] with the reference's own energy closures
+  (which read position[0][0]: potentials.py:27-52): four apply_fn steps, positions / keys / log_prob after each."""
+  from noneq_opt import simulate as ref_simulate
+  kT = 4.183
+  beta, x_m = 1.0 / kT, 14.0
+  kappa = 21.3863 / (beta * x_m ** 2)
+  out = {}
+  for name, energy, shape, r0, dt, kT_, gamma, box in (
+      ('spring_7x3', ref_potentials.V_spring(2.0), (7, 3), 0.5, 1e-3, 1.0, 0.1, None),
+      ('shifted_4x1', ref_potentials.V_biomolecule_shifted(kappa, kappa, x_m, 0., 1.5, beta), (4, 1), 3.0, 1e-8, kT, kT / 1e7, None),
+      ('spring_periodic_5x2', ref_potentials.V_spring(1.0), (5, 2), 1.0, 1e-2, 1.0, 0.5, 3.0)):
+    _, shift = space.periodic(box) if box else space.free()
+    init_fn, apply_fn = ref_simulate.brownian(energy, shift, dt, kT_, gamma)
+    R0 = jnp.array((np.arange(np.prod(shape), dtype=np.float32).reshape(shape) * 0.25 + 0.5).astype(np.float32))
+    state = init_fn(jax.random.PRNGKey(9), R0)
+    pos, keys, lps = [], [], []
+    for k in range(4):
+      state = apply_fn(state, jnp.array(np.float32(k * dt)), r0=r0)
+      pos.append(to_np(state.position)); keys.append(np.asarray(to_np(state.rng))); lps.append(np.float32(to_np(state.log_prob)))
+    out[name] = dict(R0=to_np(R0), r0=np.float32(r0), dt=dt, kT=kT_, gamma=gamma, box=np.float32(box or 0.),
+                     positions=np.stack(pos), keys=np.stack(keys), log_probs=np.array(lps, np.float32))
+  return out
+
+
+def ising_long_case():
+  """simulate_ising + estimate_gradient_rev over 200 sweeps (T = 201) of a 16 x 16 lattice under the drivers' schedule
+  composition: pins the per-sweep key derivation split(seed, T-1), the float32 summary bookkeeping and the REINFORCE
+  gradient at a config-like horizon to the reference's own code."""
+  L, T, R = 16, 201, 2
+  w = (0.1 * np.random.RandomState(0).normal(size=(2, 8))).astype(np.float32)
+  schedule = ref_ising.IsingSchedule(
+      ref_p10n.AddBaseline(ref_p10n.ConstrainEndpoints(ref_p10n.Chebyshev(jnp.array(w[0])), 0., 0.), ref_ising.log_temp_baseline()),
+      ref_p10n.AddBaseline(ref_p10n.ConstrainEndpoints(ref_p10n.Chebyshev(jnp.array(w[1])), 0., 0.), ref_ising.field_baseline()))
+  times = jnp.linspace(0, 1, T)
+  params = schedule(times)
+  spins0 = -jnp.ones([L, L])
+  seeds = jax.random.split(jax.random.PRNGKey(0), R)
+  finals, states, summaries, grads = [], [], [], {'total_entropy_production': [], 'total_work': []}
+  for r in range(R):
+    final_state, (summary, traj) = ref_ising.simulate_ising(params, spins0, seeds[r], return_states=True)
+    finals.append(to_np(final_state.spins))
+    states.append(to_np(traj.spins)[[0, 49, 99, 149, 199]])
+    summaries.append(np.stack([to_np(getattr(summary, f)) for f in summary._fields]))
+    for loss in grads:
+      g, _ = ref_ising.estimate_gradient_rev(getattr(ref_ising, loss))(schedule, times, spins0, seeds[r])
+      grads[loss].append(np.stack([to_np(g.log_temp.wrapped.wrapped.weights), to_np(g.field.wrapped.wrapped.weights)]))
+  return dict(long=dict(L=L, T=T, w=w, log_temp=to_np(params.log_temp), field=to_np(params.field), seeds=np.asarray(seeds),
+                        final_spins=np.stack(finals), states=np.stack(states), state_sweeps=np.array([1, 50, 100, 150, 200]),
+                        summary=np.stack(summaries), grad_entropy=np.stack(grads['total_entropy_production']),
+                        grad_work=np.stack(grads['total_work'])))
+
+
 if __name__ == '__main__':
-  for prefix, cases in (('reference_langevin', langevin_cases()), ('reference_ising', ising_cases()),
-                        ('reference_schedules', schedule_cases()), ('reference_train_step', train_step_case())):
+  only = sys.argv[1:]      # e.g. `make_reference_golden.py reference_extra` regenerates one file
+  jobs = (('reference_langevin', langevin_cases), ('reference_ising', ising_cases),
+          ('reference_schedules', schedule_cases), ('reference_train_step', train_step_case),
+          ('reference_extra', lambda: dict(multi_particle_cases(), **ising_long_case())))
+  for prefix, make in jobs:
+    if only and prefix not in only:
+      continue
+    cases = make()
     flat = {f'{k}/{f}': v for k, d in cases.items() for f, v in d.items()}
     np.savez_compressed(os.path.join(HERE, prefix + '.npz'), **flat)
     print(prefix, {k: {f: np.shape(v) for f, v in d.items()} for k, d in cases.items()})

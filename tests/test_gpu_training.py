@@ -123,7 +123,9 @@ def _ising_rel(a, b):
 def test_device_class_tables_are_bit_equal_to_the_host_tables(cuda, ndim):
   """nq_ising_class_tables (thresholds and log-sigmoid tables built on the device from device schedule tables)
   against ising.class_tables (numpy) over a dense (log-temperature, field) grid: same float32 operation order,
-  binary64 transcendentals rounded once -- every threshold and every table entry must be bit-equal."""
+  binary64 transcendentals rounded once -- every integer threshold and every float32-valued table entry (logit,
+  log_sigmoid(-+logit)) must be bit-equal; the binary64 sigmoid row (used for the derivative partials only) may
+  differ by the last bits of the two libraries' binary64 exp (CUDA's is not correctly rounded): <= 4 ulp."""
   import ctypes as C
   from noneq_opt_b200 import _lib, ising
   rs = np.random.RandomState(ndim)
@@ -139,7 +141,10 @@ def test_device_class_tables_are_bit_equal_to_the_host_tables(cuda, ndim):
   _lib.check(_lib.lib().nq_ising_class_tables(_lib.ptr(lt_d), _lib.ptr(h_d), T, ndim, _lib.ptr(thr_d), _lib.ptr(lut_d),
                                               _lib.stream_arg()))
   np.testing.assert_array_equal(thr_d.cpu().numpy().view(np.uint32), thr_h)
-  np.testing.assert_array_equal(lut_d.cpu().numpy().view(np.uint64), lut_h.view(np.uint64))
+  lut_g = lut_d.cpu().numpy()
+  np.testing.assert_array_equal(lut_g[:, :3].view(np.uint64), lut_h[:, :3].view(np.uint64))
+  ulp = np.abs(lut_g[:, 3].view(np.int64) - lut_h[:, 3].view(np.int64))
+  assert ulp.max() <= 4, ulp.max()
 
 
 def test_ising_trainer_follows_the_reference_source_through_graph_replay(cuda):

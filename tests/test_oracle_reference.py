@@ -124,3 +124,56 @@ def test_protocol_algebra_matches_the_reference_source():
     np.testing.assert_allclose(mod.AddBaseline(mod.ConstrainEndpoints(cheb, 0., 0.), lt_base)(x), c['composed'], atol=3e-7)
     np.testing.assert_allclose(mod.ChangeDomain(cheb, 2., 5.)(x25), c['change_domain'], atol=2e-7)
     np.testing.assert_allclose(mod.Constant(np.float32(0.7))(x), c['constant'], atol=0)
+
+
+# ---- reference_extra.npz: rank-generic Brownian states and a 200-sweep Ising run (make_reference_golden.py)
+def _extra_pot(name):
+  return {'spring_7x3': L.V_spring(2.0), 'shifted_4x1': L.V_biomolecule_shifted(KAPPA, KAPPA, XM, 0., 1.5, BETA),
+          'spring_periodic_5x2': L.V_spring(1.0)}[name]
+
+
+@pytest.mark.parametrize('name', ['spring_7x3', 'shifted_4x1', 'spring_periodic_5x2'])
+def test_multi_particle_apply_reproduces_the_reference_source(name):
+  """simulate.brownian (simulate.py:33-99) on [N, dim] states: one key per state, jax.random.normal(split, [1, N, dim]),
+  log_prob summed over every element; the energy closures read position[0][0] only."""
+  c = case('reference_extra.npz', name)
+  sc = L.step_constants(float(c['dt']), float(c['kT']), 1.0, float(c['gamma']))
+  shift = ('periodic', float(c['box'])) if float(c['box']) > 0 else 'free'
+  x, key = c['R0'], J.PRNGKey(9)
+  for k in range(4):
+    x, key, lp, _ = L.brownian_apply_nd(_extra_pot(name), sc, x, key, float(c['r0']), shift)
+    np.testing.assert_array_equal(key, c['keys'][k])
+    assert rel(x, c['positions'][k]) < 1e-6
+    assert abs(float(lp) - float(c['log_probs'][k])) <= 2e-6 * abs(float(c['log_probs'][k]))
+
+
+def test_ising_oracle_reproduces_the_reference_source_over_200_sweeps():
+  """T = 201 under the drivers' schedule composition: spin history bit-exact (5 intermediate lattices + the last),
+  summaries to a few ulp, both loss gradients -- numpy oracle and its C form."""
+  from oracle import c_oracle
+  c = case('reference_extra.npz', 'long')
+  L_, T = int(c['L']), int(c['T'])
+  times = np.linspace(0, 1, T, dtype=np.float32)
+  lt = P.AddBaseline(P.ConstrainEndpoints(P.Chebyshev(c['w'][0]), 0., 0.), P.log_temp_baseline())(times)
+  h = P.AddBaseline(P.ConstrainEndpoints(P.Chebyshev(c['w'][1]), 0., 0.), P.field_baseline())(times)
+  np.testing.assert_allclose(lt, c['log_temp'], atol=2e-7)
+  np.testing.assert_allclose(h, c['field'], atol=2e-7)
+  s0 = -np.ones((L_, L_), np.int32)
+  sweeps = [int(v) for v in c['state_sweeps']]
+  fin_c, summ_c, snaps_c = c_oracle.ising(c['log_temp'], c['field'], s0.astype(np.int8), c['seeds'], snapshots=sweeps)
+  np.testing.assert_array_equal(fin_c, c['final_spins'])
+  np.testing.assert_array_equal(snaps_c, c['states'])
+  jac = [P.ConstrainEndpoints(P.Chebyshev(np.asarray(c['w'][i], np.float64), np.float64), 0., 0.).jacobian(times.astype(np.float64))
+         for i in (0, 1)]
+  for r in range(2):
+    fin, summ, states = I.simulate_ising(c['log_temp'], c['field'], s0, c['seeds'][r], return_states=True)
+    np.testing.assert_array_equal(fin, c['final_spins'][r])
+    np.testing.assert_array_equal(states[[s - 1 for s in sweeps]], c['states'][r])
+    for i, f in enumerate(I.IsingSummary._fields):
+      want = c['summary'][r, i]
+      tol = 0 if f == 'magnetization' else 8 * np.spacing(np.float32(max(L_ * L_, np.abs(want).max())))
+      assert np.abs(getattr(summ, f) - want).max() <= tol, f
+      assert np.abs(summ_c[r, i] - want).max() <= tol, f
+    for loss, key in (('total_entropy_production', 'grad_entropy'), ('total_work', 'grad_work')):
+      o = I.closed_form_gradient(loss, c['log_temp'], c['field'], jac[0], jac[1], s0, c['seeds'][r])
+      assert rel(o['grad'][0], c[key][r, 0]) < 1e-4 and rel(o['grad'][1], c[key][r, 1]) < 1e-4
