@@ -443,6 +443,18 @@ __global__ void __launch_bounds__(WARP_TEAM ? 32 * NQ_ISING_TEAMS : 1024, WARP_T
   if (SEG && seg > 0) {
     M = __ldcg(sh.seg_mb + 2 * rep);
     B = __ldcg(sh.seg_mb + 2 * rep + 1);
+    if (kDebugChecks) {   // the lattice handed over by the previous segment must be the one (M, B) describe
+      int up = 0;
+      for (int u = tid; u < 2 * L * NW; u += tsize) up += __popc(lat[u]);
+      up = __reduce_add_sync(0xffffffffu, up);
+      __shared__ int dbg_up_s;
+      if (threadIdx.x == 0) dbg_up_s = 0;
+      __syncthreads();
+      if (lane == 0) atomicAdd(&dbg_up_s, up);
+      __syncthreads();
+      NQ_DBG_ASSERT(M == 2ll * dbg_up_s - (long long)L * L);
+      __syncthreads();
+    }
   } else {
     int hA[10], hF[10];
 #pragma unroll

@@ -405,7 +405,12 @@ constexpr int pad4(int D) { return (D + 3) / 4 * 4; }
 // Steps [k_begin, k_end] of the 64 trajectories of group `block`.  first: initialise from x0 / seeds
 // (+ equilibration); otherwise restore the carry from `state`.  last: write the outputs and the
 // group's partial sums; otherwise save the carry.  state layout: [word][npad] (coalesced).
-constexpr int state_words(int D) { return 9 + 2 * (D > 0 ? D : 1); }
+constexpr int state_words(int D) { return 9 + 2 * (D > 0 ? D : 1) + (kDebugChecks ? 1 : 0); }
+// debug builds: the carry ends with a checksum of (position, key chain, chunk index) -- a chunk that started before
+// its predecessor's carry was complete and visible (an ordering bug of the FIFO hand-over) trips the assert
+__device__ __forceinline__ uint32_t carry_checksum(float x, uint32_t k0, uint32_t k1, uint32_t s0, uint32_t s1, long long next_k) {
+  return (__float_as_uint(x) * 0x9E3779B1u) ^ (k0 + 0x85EBCA6Bu * k1) ^ (s0 * 0xC2B2AE35u + s1) ^ (uint32_t)next_k;
+}
 
 // The steps of one staged tile (r_s / phi_s / tab_s hold steps t0 .. t0 + len - 1).  Per step: work increment at
 // the position before the kick, the kick, log-prob and gradient moments.  The log-prob sum is carried as
@@ -586,11 +591,14 @@ __device__ __forceinline__ void langevin_chunk(const LangevinConsts& c_in, const
       gA[j] = __uint_as_float(sp[(9 + j) * npad]);
       gB[j] = __uint_as_float(sp[(9 + DA + j) * npad]);
     }
+    if (kDebugChecks && live)
+      NQ_DBG_ASSERT(sp[(9 + 2 * DA) * npad] == carry_checksum(x, rng.k0, rng.k1, rng.s0, rng.s1, k_begin));
   }
 
   for (long long t0 = k_begin; t0 <= k_end; t0 += kTile) {
     const int len = (int)min((long long)kTile, k_end - t0 + 1);
     __syncthreads();
+    NQ_DBG_ASSERT(t0 >= 1 && t0 - 1 + len <= c.S && len >= 1 && len <= kTile);
     for (int i = threadIdx.x; i <= len; i += kThreads) r_s[i] = io.r_table[t0 - 1 + i];
     if (FAST) {
       // dW_k = (k_s/2)[(x-r_k)^2 - (x-r_{k-1})^2] = a_k x + b_k,  a_k = k_s (r_{k-1} - r_k),  b_k = -a_k (r_{k-1} + r_k)/2
@@ -632,6 +640,7 @@ __device__ __forceinline__ void langevin_chunk(const LangevinConsts& c_in, const
         sp[(9 + j) * npad] = __float_as_uint(gA[j]);
         sp[(9 + DA + j) * npad] = __float_as_uint(gB[j]);
       }
+      if (kDebugChecks) sp[(9 + 2 * DA) * npad] = carry_checksum(x, rng.k0, rng.k1, rng.s0, rng.s1, k_end + 1);
     }
     return;
   }
@@ -717,6 +726,7 @@ __global__ void __launch_bounds__(kPairThreads) langevin_pair_kernel(const Lange
   constexpr int DPS = GRAD ? pad4(D) : 4;
   constexpr int kFull = 1, kEmpty = 3;   // barrier ids kFull + h, kEmpty + h (0 is __syncthreads)
   __shared__ float ring_s[2][kRingHalf][32];
+  __shared__ long long ring_tag_s[kDebugChecks ? 2 * kRingHalf : 1];   // debug: global step index held by each ring slot
   __shared__ float r_s[kTile + 1];
   __shared__ __align__(16) float4 tab_s[FAST ? kTile : 1];
   __shared__ __align__(16) float phi_s[GRAD ? kTile * DPS : 4];
@@ -744,6 +754,7 @@ __global__ void __launch_bounds__(kPairThreads) langevin_pair_kernel(const Lange
       for (int i = 0; i < len; ++i) {
         const uint32_t bits = rng.next();
         ring_s[h][i][lane] = FAST ? fast_normal(bits) : normal_from_bits<false>(bits);
+        if (kDebugChecks && lane == 0) ring_tag_s[h * kRingHalf + i] = ch * kRingHalf + i;
       }
       __threadfence_block();
       named_bar_arrive(kFull + h, kPairThreads);
@@ -762,6 +773,8 @@ __global__ void __launch_bounds__(kPairThreads) langevin_pair_kernel(const Lange
       named_bar_sync(kFull + h, kPairThreads);
     }
     const float z = ring_s[h][pos][lane];
+    // debug: the slot must hold exactly the draw of this step (not yet overwritten, already produced)
+    if (kDebugChecks) NQ_DBG_ASSERT(((volatile long long*)ring_tag_s)[h * kRingHalf + pos] == chunk * kRingHalf + pos);
     if (++pos == kRingHalf) {
       pos = 0;
       ++chunk;
