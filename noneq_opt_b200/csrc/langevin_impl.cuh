@@ -702,15 +702,39 @@ __global__ void __launch_bounds__(kThreads, min_blocks(D)) langevin_kernel(const
 // latency-bound: one step costs ~1050 cycles (STRICT) because the three threefry blocks + normal draw
 // and the force / work chain are issued back to back from ONE in-order instruction stream, although
 // the random stream does not depend on the positions.  Here every group of 32 trajectories gets
-// TWO warps: a producer that runs the key chain and turns each step's bits into the standard normal
-// draw, and a consumer that integrates.  They meet in a shared-memory ring of two 32-step halves
-// guarded by four named barriers (FULL / EMPTY per half), so the two dependent chains of a step
-// overlap in time.  Per-trajectory results are bit-identical to langevin_kernel (same functions,
-// same order).  Measured (scripts/latency_scan.py): 1050 -> 670 cycles per step STRICT, 740 -> 555
-// FAST; the producer alone needs 665 / 550 (three interleaved threefry blocks are ALU-pipe bound even
-// for a single warp), the consumer alone 595 / 455.
-constexpr int kPairThreads = 64;  // warp 0: consumer, warp 1: producer
+// THREE warps in a pipeline:
+//   key warp    the serial key chain  key, sub = split(key)  (:79) -- two independent threefry blocks per step,
+//               the only step-to-step dependence of the random stream (~390 cycles per step: the floor);
+//   draw warp   bits = threefry(sub, (0, 0)); xi = sqrt(2) erf_inv(...) (:88) -- no dependence between steps, so it
+//               works on four steps at a time (instruction-level parallelism instead of a second draw warp);
+//   consumer    integration, work, log-prob and gradient moments.
+// They meet in two shared-memory rings of two 32-step halves (sub-keys; draws), each guarded by four named
+// barriers (FULL / EMPTY per half).  Per-trajectory results are bit-identical to langevin_kernel (same
+// functions, same order).  Round 1 shipped the two-warp form (key chain + draws in one producer warp):
+// 670 cycles per step STRICT at config 1, set by the producer (scripts/latency_scan.py).
+constexpr int kPairThreads = 96;  // warp 0: consumer, warp 1: draw, warp 2: key chain
+constexpr int kBarCount = 64;     // every named barrier joins two warps
 constexpr int kRingHalf = 32;     // steps per ring half
+
+// STRICT normal draws of four independent words at once: the central erf_inv polynomials in straight-line code (so
+// that the four threefry blocks and the four polynomial chains interleave), tail-range lanes patched afterwards
+__device__ __forceinline__ void normal4_strict(const uint32_t (&bits)[4], float (&z)[4]) {
+  float u[4], w[4];
+  bool tail = false;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    u[j] = uniform_pm1_from_bits(bits[j]);
+    w[j] = erfinv_w<false>(u[j]);
+    z[j] = __fmul_rn(1.41421356237309504880f, __fmul_rn(erfinv_poly_central<false>(w[j]), u[j]));
+    asm volatile("" : "+f"(z[j]));
+    tail |= !(w[j] < 5.0f);
+  }
+  if (tail) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (!(w[j] < 5.0f)) z[j] = __fmul_rn(1.41421356237309504880f, __fmul_rn(erfinv_poly_tail<false>(w[j]), u[j]));
+  }
+}
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -724,40 +748,78 @@ __global__ void __launch_bounds__(kPairThreads) langevin_pair_kernel(const Lange
   constexpr bool GRAD = D > 0;
   constexpr int DA = GRAD ? D : 1;
   constexpr int DPS = GRAD ? pad4(D) : 4;
-  constexpr int kFull = 1, kEmpty = 3;   // barrier ids kFull + h, kEmpty + h (0 is __syncthreads)
+  constexpr int kFull = 1, kEmpty = 3;   // draw ring: barrier ids kFull + h, kEmpty + h (0 is __syncthreads)
+  constexpr int kFullK = 5, kEmptyK = 7; // sub-key ring
   __shared__ float ring_s[2][kRingHalf][32];
+  __shared__ uint32_t key_ring_s[2][kRingHalf][2][32];
   __shared__ long long ring_tag_s[kDebugChecks ? 2 * kRingHalf : 1];   // debug: global step index held by each ring slot
   __shared__ float r_s[kTile + 1];
   __shared__ __align__(16) float4 tab_s[FAST ? kTile : 1];
   __shared__ __align__(16) float phi_s[GRAD ? kTile * DPS : 4];
 
   const int lane = threadIdx.x & 31;
-  const bool producer = threadIdx.x >= 32;
+  const int role = threadIdx.x >> 5;     // 0 consumer, 1 draw, 2 key chain
   const long long gid = (long long)blockIdx.x * 32 + lane;
   const bool live = gid < io.n;
   const long long idx = live ? gid : io.n - 1;
   const long long total = c.Neq + c.S;
   const long long n_chunks = (total + kRingHalf - 1) / kRingHalf;
 
-  if (producer) {
-    RngPipeFor<FAST> rng;
-    rng.one = c.one;
+  if (role == 2) {   // ---- key chain
+    uint32_t k0, k1, s0, s1;
     {
       uint32_t n0, n1, r0, r1;
       split2(io.seeds[2 * idx], io.seeds[2 * idx + 1], n0, n1, r0, r1);   // barrier_crossing.py:133,138
-      rng.prime(r0, r1);
+      split2(r0, r1, k0, k1, s0, s1);                                     // the split of the first step (:79)
     }
     for (long long ch = 0; ch < n_chunks; ++ch) {
       const int h = (int)(ch & 1);
-      if (ch >= 2) named_bar_sync(kEmpty + h, kPairThreads);   // the consumer is done with this half
+      if (ch >= 2) named_bar_sync(kEmptyK + h, kBarCount);   // the draw warp has read this half
       const int len = (int)min((long long)kRingHalf, total - ch * kRingHalf);
       for (int i = 0; i < len; ++i) {
-        const uint32_t bits = rng.next();
-        ring_s[h][i][lane] = FAST ? fast_normal(bits) : normal_from_bits<false>(bits);
-        if (kDebugChecks && lane == 0) ring_tag_s[h * kRingHalf + i] = ch * kRingHalf + i;
+        key_ring_s[h][i][0][lane] = s0;
+        key_ring_s[h][i][1][lane] = s1;
+        uint32_t n0, n1;
+        split2(k0, k1, n0, n1, s0, s1);   // key, split = split(state.rng) of the NEXT step
+        k0 = n0; k1 = n1;
       }
       __threadfence_block();
-      named_bar_arrive(kFull + h, kPairThreads);
+      named_bar_arrive(kFullK + h, kBarCount);
+    }
+    return;
+  }
+  if (role == 1) {   // ---- draws
+    for (long long ch = 0; ch < n_chunks; ++ch) {
+      const int h = (int)(ch & 1);
+      named_bar_sync(kFullK + h, kBarCount);                 // sub-keys of this half are there
+      if (ch >= 2) named_bar_sync(kEmpty + h, kBarCount);    // the consumer is done with this half of the draws
+      const int len = (int)min((long long)kRingHalf, total - ch * kRingHalf);
+      int i = 0;
+      for (; i + 4 <= len; i += 4) {
+        uint32_t bits[4], unused;
+        float z[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          threefry2x32(key_schedule(key_ring_s[h][i + j][0][lane], key_ring_s[h][i + j][1][lane]), 0u, 0u, bits[j], unused);
+        if (FAST) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) z[j] = fast_normal(bits[j]);
+        } else {
+          normal4_strict(bits, z);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ring_s[h][i + j][lane] = z[j];
+      }
+      for (; i < len; ++i) {
+        uint32_t bits, unused;
+        threefry2x32(key_schedule(key_ring_s[h][i][0][lane], key_ring_s[h][i][1][lane]), 0u, 0u, bits, unused);
+        ring_s[h][i][lane] = FAST ? fast_normal(bits) : normal_from_bits<false>(bits);
+      }
+      if (kDebugChecks && lane == 0)
+        for (int q = 0; q < len; ++q) ring_tag_s[h * kRingHalf + q] = ch * kRingHalf + q;
+      __threadfence_block();
+      if (ch + 2 < n_chunks) named_bar_arrive(kEmptyK + h, kBarCount);   // the key warp may refill this half
+      named_bar_arrive(kFull + h, kBarCount);
     }
     return;
   }
@@ -769,8 +831,8 @@ __global__ void __launch_bounds__(kPairThreads) langevin_pair_kernel(const Lange
     const int h = (int)(chunk & 1);
     if (pos == 0) {
       // release the half finished last (its values have all been used) once a later chunk needs it
-      if (chunk >= 1 && chunk + 1 < n_chunks) named_bar_arrive(kEmpty + (h ^ 1), kPairThreads);
-      named_bar_sync(kFull + h, kPairThreads);
+      if (chunk >= 1 && chunk + 1 < n_chunks) named_bar_arrive(kEmpty + (h ^ 1), kBarCount);
+      named_bar_sync(kFull + h, kBarCount);
     }
     const float z = ring_s[h][pos][lane];
     // debug: the slot must hold exactly the draw of this step (not yet overwritten, already produced)

@@ -254,7 +254,7 @@ class IsingTrainer:
     self.variables = torch.from_numpy(np.concatenate([comps[0][0], comps[1][0]])).to(dev)
 
     def up(a):
-      return None if a is None else torch.from_numpy(np.ascontiguousarray(a, np.float32)).to(dev)
+      return None if a is None else torch.from_numpy(np.array(a, dtype=np.float32, order="C")).to(dev)
     self._comp = [tuple(up(a) for a in c[1:]) for c in comps]      # (basis, scale, offset1, offset2) per component
     self._J = [torch.from_numpy(np.ascontiguousarray(np.asarray(p.jacobian(self.times), np.float64))).to(dev)
                for p in (schedule.log_temp, schedule.field)]

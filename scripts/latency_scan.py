@@ -11,13 +11,18 @@ S = 2000
 for mode in ('strict', 'fast'):
   bc.set_math_mode(mode)
   for name, (pot, coeffs, r0, r1, dt, kT, gamma) in pots.items():
-    for B in (1000, 9472, 12288, 16384, 24000):
+    for B in (1000, 4736, 9472, 12288, 16384, 24000):
       seeds = nqr.split(nqr.PRNGKey(0), B)
       x0 = torch.full((B,), r0, device='cuda')
-      for rep in range(3):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        bc.gradient_terms(pot, coeffs, x0, seeds, r0, r1, 0, shift, S, dt, kT, 1.0, gamma)
-        e1.record(); torch.cuda.synchronize()
-      ms = e0.elapsed_time(e1)
-      print(f'{mode:6s} {name:8s} B={B:6d}: {ms:7.3f} ms  {1e6 * ms / S:7.1f} ns/step  {ms * 1e-3 * 1.965e9 / S:6.0f} cycles/step')
+      res = {}
+      for form, pair_max in (('pipeline', '65536'), ('one-warp', '0')):   # three-warp pipeline vs langevin_kernel
+        os.environ['NQ_PAIR_MAX'] = pair_max
+        for rep in range(3):
+          e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+          e0.record()
+          bc.gradient_terms(pot, coeffs, x0, seeds, r0, r1, 0, shift, S, dt, kT, 1.0, gamma)
+          e1.record(); torch.cuda.synchronize()
+        res[form] = e0.elapsed_time(e1)
+      del os.environ['NQ_PAIR_MAX']
+      print(f'{mode:6s} {name:8s} B={B:6d}: ' + '  '.join(
+          f'{form} {ms:7.3f} ms {ms * 1e-3 * 1.965e9 / S:5.0f} cycles/step' for form, ms in res.items()))
