@@ -111,6 +111,7 @@ struct IsingShape {
   long long* seg_mb;     // [R][2] spin sum, bond sum carried between segments
   uint32_t* seg_lat;     // [R][2][L][NW] colour planes carried between segments
   unsigned seg_max_polls;  // bound of a wait for the previous segment, in polls of 256 ns; 0 = unbounded
+  unsigned seg_units;      // tickets per segment index: R (CTA team) or R / teams-per-CTA (warp teams)
 };
 
 struct IsingIO {
@@ -347,7 +348,7 @@ __device__ __forceinline__ void sweep_keys(const KeySchedule& ks_rep, int t, int
 // memory -- same code, for lattices whose 2 x L x L/64 words exceed 227 KB (L >= 2048).
 template <bool WARP_TEAM, bool GLOBAL_LAT = false, bool SEG = false>
 __global__ void __launch_bounds__(WARP_TEAM ? 32 * NQ_ISING_TEAMS : 1024, WARP_TEAM ? NQ_ISING_MINB : 1) ising_fast_kernel(const IsingShape sh, const IsingIO io) {
-  static_assert(!SEG || (!WARP_TEAM && !GLOBAL_LAT), "segments are scheduled per CTA with the lattice in shared memory");
+  static_assert(!SEG || !GLOBAL_LAT, "segments are scheduled per CTA with the lattice in shared memory");
   extern __shared__ uint32_t smem[];
   uint32_t* spread = smem;
   const int L = sh.L, NW = sh.NW, T = sh.T;
@@ -366,7 +367,8 @@ __global__ void __launch_bounds__(WARP_TEAM ? 32 * NQ_ISING_TEAMS : 1024, WARP_T
   // Pair-threshold tables (two sweep-parity buffers).  They depend on the sweep only, so the warp teams of a CTA
   // -- which start every sweep together -- share ONE copy (team 0's area) and build it cooperatively.
   uint2* thr_s = reinterpret_cast<uint2*>((WARP_TEAM ? smem + 4 * 256 : team_base) + smem_lat_words);
-  const long long live = sh.R - (long long)blockIdx.x * nteams;
+  // (segment-scheduled warp teams: R is a multiple of the teams per CTA, every team is live)
+  const long long live = SEG ? nteams : sh.R - (long long)blockIdx.x * nteams;
   const int btid = WARP_TEAM ? team * 32 + lane : threadIdx.x;                                   // index among the builders
   const int bsize = WARP_TEAM ? 32 * (int)(live < nteams ? live : nteams) : blockDim.x;
   // per-sweep class histograms [parity][half][active|flipped][16]: per team (warp teams) or per CTA
@@ -386,17 +388,20 @@ __global__ void __launch_bounds__(WARP_TEAM ? 32 * NQ_ISING_TEAMS : 1024, WARP_T
   long long rep = (long long)blockIdx.x * nteams + team;
   int seg = 0, t_first = 1, t_end = T;
   if (SEG) {
-    const unsigned total = (unsigned)sh.R * (unsigned)sh.n_seg;
+    // ticket it -> segment it / U of work unit it % U; a unit is a replica (CTA team) or the nteams replicas a CTA of
+    // warp teams runs in lock step
+    const unsigned U = sh.seg_units;
+    const unsigned total = U * (unsigned)sh.n_seg;
     if (threadIdx.x == 0) {
       const unsigned it = atomicAdd(&sh.seg_ctl[0], 1u);
-      if (it < total && it >= (unsigned)sh.R) {
-        // the previous segment of this replica was handed out R tickets ago: it is running or done
-        const volatile unsigned* done = sh.seg_ctl + 1 + it % (unsigned)sh.R;
-        const unsigned want = it / (unsigned)sh.R;
+      if (it < total && it >= U) {
+        // the previous segment of this unit was handed out U tickets ago: it is running or done
+        const volatile unsigned* done = sh.seg_ctl + 1 + it % U;
+        const unsigned want = it / U;
         // bounded wait (NQ_WAIT_POLLS; 0 = unbounded): when it runs out the launch is abandoned cleanly --
         // status word set, every CTA leaves at its next ticket, ising_status_kernel turns the summaries into
         // NaN -- instead of a __trap() that would poison the caller's CUDA context
-        volatile unsigned* dead = sh.seg_ctl + 1 + sh.R;
+        volatile unsigned* dead = sh.seg_ctl + 1 + U;
         unsigned polls = 0;
         bool lost = false;
         while (*done < want) {
@@ -404,16 +409,16 @@ __global__ void __launch_bounds__(WARP_TEAM ? 32 * NQ_ISING_TEAMS : 1024, WARP_T
           if ((sh.seg_max_polls && ++polls > sh.seg_max_polls) || *dead) { lost = true; break; }
         }
         __threadfence();
-        if (lost) atomicExch(sh.seg_ctl + 1 + sh.R, 1u);
+        if (lost) atomicExch(sh.seg_ctl + 1 + U, 1u);
       }
-      ticket_s = (it < total && *(volatile unsigned*)(sh.seg_ctl + 1 + sh.R) == 0u) ? it : 0xffffffffu;
+      ticket_s = (it < total && *(volatile unsigned*)(sh.seg_ctl + 1 + U) == 0u) ? it : 0xffffffffu;
     }
     __syncthreads();
     const unsigned it = ticket_s;
     __syncthreads();
     if (it >= total) return;
-    rep = it % (unsigned)sh.R;
-    seg = it / (unsigned)sh.R;
+    rep = (long long)(it % U) * nteams + team;
+    seg = it / U;
     t_first = 1 + (int)((long long)seg * (T - 1) / sh.n_seg);
     t_end = 1 + (int)((long long)(seg + 1) * (T - 1) / sh.n_seg);
   } else if (rep >= sh.R) {
@@ -447,13 +452,17 @@ __global__ void __launch_bounds__(WARP_TEAM ? 32 * NQ_ISING_TEAMS : 1024, WARP_T
       int up = 0;
       for (int u = tid; u < 2 * L * NW; u += tsize) up += __popc(lat[u]);
       up = __reduce_add_sync(0xffffffffu, up);
-      __shared__ int dbg_up_s;
-      if (threadIdx.x == 0) dbg_up_s = 0;
-      __syncthreads();
-      if (lane == 0) atomicAdd(&dbg_up_s, up);
-      __syncthreads();
-      NQ_DBG_ASSERT(M == 2ll * dbg_up_s - (long long)L * L);
-      __syncthreads();
+      if (WARP_TEAM) {
+        NQ_DBG_ASSERT(M == 2ll * up - (long long)L * L);
+      } else {
+        __shared__ int dbg_up_s;
+        if (threadIdx.x == 0) dbg_up_s = 0;
+        __syncthreads();
+        if (lane == 0) atomicAdd(&dbg_up_s, up);
+        __syncthreads();
+        NQ_DBG_ASSERT(M == 2ll * dbg_up_s - (long long)L * L);
+        __syncthreads();
+      }
     }
   } else {
     int hA[10], hF[10];
@@ -564,7 +573,7 @@ __global__ void __launch_bounds__(WARP_TEAM ? 32 * NQ_ISING_TEAMS : 1024, WARP_T
   if (SEG && seg + 1 < sh.n_seg) {
     uint32_t* dst = sh.seg_lat + (size_t)rep * lat_words;
     for (int u = tid; u < lat_words; u += tsize) dst[u] = lat[u];
-    if (threadIdx.x == 0) {  // warp 0 carries M, B (emit_summary)
+    if (tid == 0) {  // the warp that ran emit_summary carries M, B (warp 0 of a CTA team; every warp team's own)
       sh.seg_mb[2 * rep] = M;
       sh.seg_mb[2 * rep + 1] = B;
     }
@@ -582,7 +591,7 @@ __global__ void __launch_bounds__(WARP_TEAM ? 32 * NQ_ISING_TEAMS : 1024, WARP_T
   __syncthreads();  // every thread's stores are ordered before thread 0's fence + publish
   if (threadIdx.x == 0) {
     __threadfence();
-    atomicExch(&sh.seg_ctl[1 + rep], (unsigned)(seg + 1));
+    atomicExch(&sh.seg_ctl[1 + rep / nteams], (unsigned)(seg + 1));
   }
   }
 }
@@ -937,6 +946,7 @@ static size_t fast_smem_bytes(int L, bool warp_team, int nteams, bool global_lat
 struct SegPlan {
   int n_seg = 1;
   int grid = 0;
+  unsigned units = 0;
   size_t ctl_bytes = 0, mb_bytes = 0, lat_bytes = 0;
   size_t bytes() const { return ctl_bytes + mb_bytes + lat_bytes; }
 };
@@ -944,27 +954,38 @@ template <bool W, bool G, bool S>
 __global__ void ising_fast_kernel(const IsingShape, const IsingIO);
 static SegPlan plan_segments(int L, long long R, int T) {
   SegPlan p;
-  if (L <= 128 || R * 64 >= 0x7fffffffll || T - 1 < 2) return p;
-  const size_t smem = fast_smem_bytes(L, false, 1);
+  if (R * 64 >= 0x7fffffffll || T - 1 < 2) return p;
+  const bool warp_team = L <= 128;
+  const int nteams = warp_team ? NQ_ISING_TEAMS : 1;
+  if (warp_team && R % nteams) return p;   // the teams of a CTA run their segments in lock step: whole CTAs only
+  const size_t smem = fast_smem_bytes(L, warp_team, nteams);
   if (smem > 227 * 1024) return p;
   const int units = (L / 2) * (L / 64);
-  const int threads = units >= 1024 ? 1024 : ((units + 31) / 32) * 32;
+  const int threads = warp_team ? 32 * nteams : (units >= 1024 ? 1024 : ((units + 31) / 32) * 32);
   int dev = 0, sms = 0, occ = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess ||
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-      cudaFuncSetAttribute(ising_fast_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ising_fast_kernel<false, false, true>, threads, smem) != cudaSuccess) {
+  bool ok = cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess;
+  if (ok && warp_team)
+    ok = cudaFuncSetAttribute(ising_fast_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ising_fast_kernel<true, false, true>, threads, smem) == cudaSuccess;
+  else if (ok)
+    ok = cudaFuncSetAttribute(ising_fast_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ising_fast_kernel<false, false, true>, threads, smem) == cudaSuccess;
+  if (!ok) {
     cudaGetLastError();  // no device (host-only symbol checks): no plan
     return p;
   }
-  // with two or more CTAs per SM a lone CTA in the last round already runs faster: measured no gain
-  if (occ != 1) return p;
-  const long long slots = sms;
-  if (slots <= 0 || R <= slots || R % slots == 0) return p;
-  double best = (double)((R + slots - 1) / slots);
+  // CTA team with two or more CTAs per SM: a lone CTA in the last round already runs faster -- measured no gain.
+  // Warp teams (several CTAs per SM by design): the last, partly filled wave runs with fewer warps per SM and a
+  // lower ALU-pipe utilisation (profiles/r01h_ising_warp_full.csv: SMs active 55.6M .. 64.4M cycles), segments pay.
+  if (occ < 1 || (!warp_team && occ != 1)) return p;
+  const long long slots = (long long)sms * occ;      // resident CTAs
+  const long long U = R / nteams;                     // work units (CTAs' worth of replicas)
+  if (slots <= 0 || U <= slots || U % slots == 0) return p;
+  double best = (double)((U + slots - 1) / slots);
   const int n_max = T - 1 < 64 ? T - 1 : 64;
   for (int n = 2; n <= n_max; ++n) {
-    const double rounds = (double)((R * n + slots - 1) / slots) / n;
+    const double rounds = (double)((U * n + slots - 1) / slots) / n;
     if (rounds < 0.97 * best) {
       best = rounds;
       p.n_seg = n;
@@ -978,9 +999,10 @@ static SegPlan plan_segments(int L, long long R, int T) {
   // keep a segment under ~512 sweeps: a CTA that has to wait for the previous segment of its replica
   // waits at most one segment, which must stay far below the kernel's bounded-wait limit.  Doubling
   // n never lengthens the schedule (ceil(2Rn/s)/(2n) <= ceil(Rn/s)/n).
-  while ((T - 1) / p.n_seg > 512 && 2 * p.n_seg <= T - 1 && R * 2 * p.n_seg < 0x7fffffffll) p.n_seg *= 2;
+  while ((T - 1) / p.n_seg > 512 && 2 * p.n_seg <= T - 1 && U * 2 * p.n_seg < 0x7fffffffll) p.n_seg *= 2;
   p.grid = (int)slots;
-  p.ctl_bytes = (((size_t)R + 2) * 4 + 15) / 16 * 16;
+  p.units = (unsigned)U;
+  p.ctl_bytes = (((size_t)U + 2) * 4 + 15) / 16 * 16;
   p.mb_bytes = (size_t)R * 2 * 8;
   p.lat_bytes = (size_t)R * 2 * L * (L / 64) * 4;
   return p;
@@ -1050,7 +1072,7 @@ extern "C" int nq_ising_run(const NqIsingDesc* desc, const uint32_t* thr, const 
   NQ_CHECK_ARG(desc->sweep_key_mode == 0 || (desc->sweep_key_mode == 1 && T == 2), "sweep_key_mode 1 needs T == 2");
   const int L = dims[0];
   IsingShape sh{L, L / 64, T, desc->R, desc->spins0_broadcast, desc->sweep_key_mode, ndim, dims[0], dims[1], dims[2],
-                (int)N, nullptr, nullptr, 1u, 1, nullptr, nullptr, nullptr, 0u};
+                (int)N, nullptr, nullptr, 1u, 1, nullptr, nullptr, nullptr, 0u, 0u};
   IsingIO io{thr, lut, field, log_temp, spins0, seeds, spins_out, summary, partials, counts, states};
   cudaStream_t st = (cudaStream_t)stream;
   const bool square2d = ndim == 2 && dims[0] == dims[1];
@@ -1071,14 +1093,12 @@ extern "C" int nq_ising_run(const NqIsingDesc* desc, const uint32_t* thr, const 
       sh.lat_global = (uint32_t*)workspace;
       NQ_CUDA(cudaFuncSetAttribute(ising_fast_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       ising_fast_kernel<false, true><<<blocks, threads, smem, st>>>(sh, io);
-    } else if (warp_team) {
-      NQ_CUDA(cudaFuncSetAttribute(ising_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      ising_fast_kernel<true><<<blocks, threads, smem, st>>>(sh, io);
     } else {
       const SegPlan plan = plan_segments(L, desc->R, T);
       if (plan.n_seg > 1 && workspace != nullptr && workspace_bytes >= plan.bytes() && getenv("NQ_ISING_NO_SEGMENTS") == nullptr) {
         char* ws = (char*)workspace;
         sh.n_seg = plan.n_seg;
+        sh.seg_units = plan.units;
         sh.seg_ctl = (unsigned*)ws;
         sh.seg_mb = (long long*)(ws + plan.ctl_bytes);
         sh.seg_lat = (uint32_t*)(ws + plan.ctl_bytes + plan.mb_bytes);
@@ -1087,9 +1107,13 @@ extern "C" int nq_ising_run(const NqIsingDesc* desc, const uint32_t* thr, const 
           sh.seg_max_polls = env ? (unsigned)strtoul(env, nullptr, 10) : (1u << 24);
         }
         NQ_CUDA(cudaMemsetAsync(sh.seg_ctl, 0, plan.ctl_bytes, st));
-        ising_fast_kernel<false, false, true><<<plan.grid, threads, smem, st>>>(sh, io);
-        ising_status_kernel<<<64, 256, 0, st>>>(sh.seg_ctl + 1 + desc->R, io.summary,
+        if (warp_team) ising_fast_kernel<true, false, true><<<plan.grid, threads, smem, st>>>(sh, io);
+        else ising_fast_kernel<false, false, true><<<plan.grid, threads, smem, st>>>(sh, io);
+        ising_status_kernel<<<64, 256, 0, st>>>(sh.seg_ctl + 1 + plan.units, io.summary,
                                                 (size_t)NQ_IS_NSUMMARY * desc->R * (T - 1));
+      } else if (warp_team) {
+        NQ_CUDA(cudaFuncSetAttribute(ising_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ising_fast_kernel<true><<<blocks, threads, smem, st>>>(sh, io);
       } else {
         NQ_CUDA(cudaFuncSetAttribute(ising_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ising_fast_kernel<false><<<blocks, threads, smem, st>>>(sh, io);

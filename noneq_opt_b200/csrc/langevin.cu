@@ -139,7 +139,7 @@ static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 constexpr long long kPairLimit = 65536;   // nq_langevin_workspace_bytes sizes the partial rows for 32-trajectory CTAs up to here
 static long long pair_max() {
   const char* env = getenv("NQ_PAIR_MAX");
-  const long long v = env ? atoll(env) : 9472;   // 296 CTAs x 2 warps = one warp per SM sub-partition; beyond it the
+  const long long v = env ? atoll(env) : 12288;  // measured (scripts/latency_scan.py, r02): the three-warp pipeline wins up to here; beyond it the
                                                   // one-warp kernel is as fast (STRICT) or faster (FAST) -- measured
   return v > kPairLimit ? kPairLimit : v;
 }

@@ -3,6 +3,9 @@
 
   python scripts/summarize_ncu.py launches gpurun_out/launches.csv profiles/r01_launches.md
   python scripts/summarize_ncu.py full gpurun_out/prof_langevin_r1.ncu-rep profiles/r01_langevin_full.csv
+  python scripts/summarize_ncu.py opcodes gpurun_out/prof.ncu-rep profiles/r02_x_opcodes.md <units per launch> <unit name>
+      per-opcode EXECUTED thread-instructions per unit of work (trajectory-step / spin-update), by pipe and by role,
+      from the source page of a capture taken with --import-source on
 """
 import collections
 import csv
@@ -69,5 +72,63 @@ def full(src, dst):
   print(open(dst).read())
 
 
+ALU_OPS = {'SHF', 'LOP3', 'IADD3', 'VIADD', 'ISETP', 'FSETP', 'LEA', 'I2FP', 'FSEL', 'FMNMX', 'PRMT', 'PLOP3', 'SEL', 'VIMNMX',
+           'POPC', 'FLO', 'BREV', 'IABS', 'FCHK', 'I2F', 'F2I', 'F2F', 'FRND', 'MOV', 'SHL', 'SHR', 'P2R', 'R2P', 'BMSK', 'SGXT',
+           'IMNMX', 'VABSDIFF', 'LOP', 'VOTE', 'REDUX'}
+FMA_OPS = {'FFMA', 'FMUL', 'FADD', 'IMAD', 'HFMA2', 'DFMA', 'DADD', 'DMUL'}
+
+
+def _role(op):
+  base = op.split('.')[0]
+  if base in ('SHF', 'LOP3', 'IADD3', 'VIADD', 'PRMT', 'POPC', 'LEA') or op.startswith(('IMAD.IADD', 'IMAD.MOV', 'IMAD.SHL', 'IMAD.U32', 'IMAD.WIDE', 'IMAD.X', 'IMAD.HI')) or base == 'IMAD':
+    return 'integer (threefry hash, bit-sliced lattice, addresses)'
+  if base == 'MUFU':
+    return 'transcendental (MUFU)'
+  if base in ('FFMA', 'FMUL', 'FADD', 'FSETP', 'FSEL', 'FMNMX', 'I2FP', 'F2F', 'FCHK', 'HFMA2', 'FRND', 'DFMA', 'DADD', 'DMUL', 'F2I', 'I2F'):
+    return 'floating point'
+  if base in ('LDS', 'STS', 'LDG', 'STG', 'LDC', 'LDCU', 'LDL', 'STL', 'ATOMS', 'ATOMG', 'RED', 'ATOM', 'LDSM', 'MEMBAR', 'ERRBAR', 'CGAERRBAR', 'CCTL'):
+    return 'memory'
+  return 'control / loop / uniform'
+
+
+def opcodes(src, dst, units, unit_name='unit'):
+  import re
+  units = float(units)
+  out = subprocess.run(['ncu', '-i', src, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+  rows = list(csv.reader(io.StringIO(out)))
+  kernel = rows[0][1] if rows and len(rows[0]) > 1 else '?'
+  hdr = rows[1]
+  ix = {h: i for i, h in enumerate(hdr)}
+  tot, roles = collections.Counter(), collections.Counter()
+  for r in rows[2:]:
+    if len(r) < len(hdr):
+      continue
+    m = re.match(r'(@!?U?P\d\s+)?([A-Z0-9_.]+)', r[ix['Source']].strip())
+    if not m:
+      continue
+    op = m.group(2)
+    n = int(r[ix['Instructions Executed']] or 0) * 32 / units
+    key = op.split('.')[0] if not op.startswith(('IMAD', 'LDS', 'MUFU', 'BAR')) else '.'.join(op.split('.')[:2])
+    tot[key] += n
+    roles[_role(op)] += n
+  total = sum(tot.values())
+  alu = sum(v for k, v in tot.items() if k.split('.')[0] in ALU_OPS)
+  with open(dst, 'w') as f:
+    f.write(f'# executed thread-instructions per {unit_name}, by SASS opcode\n\n`{kernel}`\n\nsource: `{src}` '
+            f'(ncu --set full --import-source on, source page, "Instructions Executed" x 32 / {units:.6g} {unit_name}s per launch)\n\n')
+    f.write(f'**total {total:.1f}**, of which on the half-rate ALU pipe **{alu:.1f}**\n\n| role | instr / {unit_name} |\n|---|---:|\n')
+    for k, v in roles.most_common():
+      f.write(f'| {k} | {v:.1f} |\n')
+    f.write(f'\n| opcode | instr / {unit_name} | pipe |\n|---|---:|---|\n')
+    for k, v in tot.most_common():
+      if v < 0.005:
+        continue
+      base = k.split('.')[0]
+      pipe = 'ALU' if base in ALU_OPS else ('FMA' if base in FMA_OPS else ('XU' if base == 'MUFU' else ''))
+      f.write(f'| {k} | {v:.2f} | {pipe} |\n')
+  print(open(dst).read())
+  return total, alu, kernel
+
+
 if __name__ == '__main__':
-  {'launches': launches, 'full': full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+  {'launches': launches, 'full': full, 'opcodes': opcodes}[sys.argv[1]](*sys.argv[2:])

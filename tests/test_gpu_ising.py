@@ -387,11 +387,14 @@ def test_arbitrary_loss_function_through_torch_autograd(cuda):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('L,R,T', [(512, 149, 9), (1024, 150, 6), (512, 149, 1100)])
+@pytest.mark.parametrize('L,R,T', [(512, 149, 9), (1024, 150, 6), (512, 149, 1100), (64, 2400, 9), (128, 2404, 41),
+                                   (64, 4096, 1001)])
 def test_segment_scheduled_run_is_bit_identical(cuda, L, R, T, monkeypatch):
   """When R is not a multiple of the resident CTAs, nq_ising_run cuts every replica's sweeps into
-  segments handed out through a ticket counter (lattice, M and B carried through the workspace).
-  Outputs must be bit-identical to the one-CTA-per-replica launch, and one replica to the oracle."""
+  segments handed out through a ticket counter (lattice, M and B carried through the workspace) -- per
+  replica for the CTA-team kernel (L >= 256), per CTA of four lock-stepped replicas for the warp-team kernel
+  (L <= 128; the last case is configs[2]).  Outputs must be bit-identical to the unsegmented launch, and one
+  replica to the oracle."""
   import torch
   from noneq_opt_b200 import ising
   lt = np.log(np.linspace(2.6, 2.0, T).astype(np.float32))
