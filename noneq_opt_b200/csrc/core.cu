@@ -88,7 +88,8 @@ extern "C" int nq_allreduce_f64(void* nccl_comm, double* buf, int64_t n, void* s
   NQ_CHECK_ARG(nccl_comm != nullptr && buf != nullptr && n >= 1, "need a communicator, a buffer and n >= 1");
   NcclAllReduceFn fn = find_nccl_allreduce();
   if (!fn) {
-    set_error("libnccl.so.2 is not loadable in this process: %s", dlerror());
+    const char* why = dlerror();   // NULL once any dlopen succeeded: then the library loaded but lacks the symbol
+    set_error("ncclAllReduce is not available in this process: %s", why ? why : "libnccl loaded, symbol ncclAllReduce missing");
     return NQ_ERR_CUDA;
   }
   const int rc = fn(buf, buf, (size_t)n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, nccl_comm, (cudaStream_t)stream);

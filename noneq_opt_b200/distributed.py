@@ -31,7 +31,11 @@ def init_from_env(backend: str = 'nccl'):
 
 
 def shard_range(n_total: int, rank: int, world_size: int) -> Tuple[int, int]:
-  """(first, count) of the contiguous slice rank `rank` owns; slices differ by at most one."""
+  """(first, count) of the contiguous slice rank `rank` owns; slices differ by at most one.  Every rank must own at
+  least one trajectory / replica: an empty shard would fail its kernel launch BEFORE the all-reduce and leave the
+  other ranks waiting in the collective, so the mismatch is rejected on all ranks up front."""
+  if int(n_total) < int(world_size):
+    raise ValueError(f'{n_total} trajectories / replicas cannot be sharded over {world_size} ranks (every rank needs one)')
   base, rem = divmod(int(n_total), int(world_size))
   first = rank * base + min(rank, rem)
   return first, base + (1 if rank < rem else 0)

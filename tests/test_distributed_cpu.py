@@ -12,7 +12,10 @@ from noneq_opt_b200 import distributed as nqd
 
 
 def test_shard_range_partitions_exactly():
-  for n, ws in [(10, 3), (100000, 8), (7, 8), (10_000_000, 8), (5, 1)]:
+  import pytest
+  with pytest.raises(ValueError):      # an empty shard would hang the other ranks in the all-reduce
+    nqd.shard_range(7, 0, 8)
+  for n, ws in [(10, 3), (100000, 8), (8, 8), (10_000_000, 8), (5, 1)]:
     spans = [nqd.shard_range(n, r, ws) for r in range(ws)]
     assert spans[0][0] == 0 and sum(c for _, c in spans) == n
     for (f0, c0), (f1, _) in zip(spans, spans[1:]):
