@@ -181,10 +181,19 @@ __device__ __forceinline__ void histogram(const Planes& p, uint32_t F, int (&hA)
 // ALLMAD: every threefry addition as IMAD (FMA pipe).  Measured on B200: +5 % for the 1024-thread
 // CTA-per-replica kernel (ALU pipe 81 % busy, FMA pipe 20 %), -5 % for the warp-per-replica kernel
 // (which is closer to its issue limit), so it is chosen per kernel.
-template <bool ALLMAD>
+// MODE 0: plain threefry; 1 (ALLMAD): every addition as IMAD; 2 (INJ): only the key injections as IMADs, with the
+// injection words ks_b + i formed once per half-sweep (threefry2x32_inj) -- the warp-team kernel's IADD3s
+// (3.5 per spin-update on the binding ALU pipe, profiles/r02e_ising_c3_noseg_opcodes.md) move to the FMA pipe.
+#ifndef NQ_ISING_WARP_MODE
+#define NQ_ISING_WARP_MODE 2
+#endif
+template <int MODE>
 __device__ __forceinline__ void update_unit(uint32_t* lat, const IsingShape& sh, const uint32_t* spread,
                                             const uint2* thr2, const KeySchedule& ks, int c, int i, int w,
                                             int (&hA)[10], int (&hF)[10]) {
+  constexpr bool ALLMAD = MODE == 1;
+  KeyInject kinj;
+  if (MODE == 2) kinj = key_inject(ks.ks0, ks.ks1, sh.one);
   const int L = sh.L, NW = sh.NW, i2 = i + L / 2;
   Planes pa, pb;
   load_planes(lat, sh, c, i, w, pa);
@@ -224,6 +233,7 @@ __device__ __forceinline__ void update_unit(uint32_t* lat, const IsingShape& sh,
         const uint32_t ctr = cbase + 2u * (8u * q + 2u * j + e);
         uint32_t y0, y1;
         if (ALLMAD) threefry2x32_allmad(ks, ctr, ctr + half, y0, y1, sh.one);
+        else if (MODE == 2) threefry2x32_inj<false>(kinj, ctr + ks.ks0, ctr + half + ks.ks1, sh.one, y0, y1);
         else threefry2x32(ks, ctr, ctr + half, y0, y1);
         const uint32_t da = (y0 >> 9) - (e ? ta.y : ta.x);
         const uint32_t db = (y1 >> 9) - (e ? tb.y : tb.x);
@@ -516,7 +526,7 @@ __global__ void __launch_bounds__(WARP_TEAM ? 32 * NQ_ISING_TEAMS : 1024, WARP_T
       for (int k = 0; k < 10; ++k) hA[k] = hF[k] = 0;
       for (int u = tid; u < units; u += tsize) {
         const int i = u / NW, w = u - i * NW;
-        update_unit<!WARP_TEAM>(lat, sh, spread, thr_cur, kh[c], c, i, w, hA, hF);
+        update_unit<WARP_TEAM ? NQ_ISING_WARP_MODE : 1>(lat, sh, spread, thr_cur, kh[c], c, i, w, hA, hF);
       }
 #pragma unroll
       for (int k = 0; k < 10; ++k) {
@@ -957,7 +967,12 @@ static SegPlan plan_segments(int L, long long R, int T) {
   if (R * 64 >= 0x7fffffffll || T - 1 < 2) return p;
   const bool warp_team = L <= 128;
   const int nteams = warp_team ? NQ_ISING_TEAMS : 1;
-  if (warp_team && R % nteams) return p;   // the teams of a CTA run their segments in lock step: whole CTAs only
+  // Warp-team segments are OFF unless NQ_ISING_WARP_SEGMENTS=1: measured at config 3 (profiles/r02e_ising_c3_*_full.csv)
+  // 33.8 ms segmented against 32.8 ms for the plain 1.73-wave launch.  The SMs of the second, partly filled wave hold
+  // three CTAs instead of four and -- the kernel being bound by the ALU pipe, not by latency -- finish them
+  // proportionally sooner, so the wave tail the segments were meant to remove costs ~1 % (6.92 CTA-runs per SM
+  // against a maximum of 7), while the segmented form adds a CTA-wide ticket barrier per segment.
+  if (warp_team && (getenv("NQ_ISING_WARP_SEGMENTS") == nullptr || R % nteams)) return p;   // (lock-stepped teams: whole CTAs only)
   const size_t smem = fast_smem_bytes(L, warp_team, nteams);
   if (smem > 227 * 1024) return p;
   const int units = (L / 2) * (L / 64);
