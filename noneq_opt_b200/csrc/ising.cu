@@ -187,6 +187,15 @@ __device__ __forceinline__ void histogram(const Planes& p, uint32_t F, int (&hA)
 #ifndef NQ_ISING_WARP_MODE
 #define NQ_ISING_WARP_MODE 2
 #endif
+#ifndef NQ_ISING_CTA_MODE
+#define NQ_ISING_CTA_MODE 1
+#endif
+// 1: the 23 uniform bits jax keeps of a word (bits >> 9) as the high half of bits * 2^23 (IMAD.HI, FMA pipe, fused
+// with the subtraction of the threshold) instead of a shift on the binding ALU pipe; the 2^23 comes from the
+// run-time 1 so that ptxas cannot turn the multiply back into a shift
+#ifndef NQ_ISING_MULHI
+#define NQ_ISING_MULHI 0
+#endif
 template <int MODE>
 __device__ __forceinline__ void update_unit(uint32_t* lat, const IsingShape& sh, const uint32_t* spread,
                                             const uint2* thr2, const KeySchedule& ks, int c, int i, int w,
@@ -206,6 +215,7 @@ __device__ __forceinline__ void update_unit(uint32_t* lat, const IsingShape& sh,
   // (the subtraction can issue on the FMA pipe; the ALU pipe, which bounds this kernel, sees one
   // shift instead of compare + select + or).
   uint32_t Fa = 0, Fb = 0, Na = 0, Nb = 0;
+  const uint32_t two23 = sh.one << 23;
 #if NQ_ISING_BLOCKS_PER_ITER == 8
 #pragma unroll 1
   for (int q = 3; q >= 0; --q) {
@@ -235,8 +245,8 @@ __device__ __forceinline__ void update_unit(uint32_t* lat, const IsingShape& sh,
         if (ALLMAD) threefry2x32_allmad(ks, ctr, ctr + half, y0, y1, sh.one);
         else if (MODE == 2) threefry2x32_inj<false>(kinj, ctr + ks.ks0, ctr + half + ks.ks1, sh.one, y0, y1);
         else threefry2x32(ks, ctr, ctr + half, y0, y1);
-        const uint32_t da = (y0 >> 9) - (e ? ta.y : ta.x);
-        const uint32_t db = (y1 >> 9) - (e ? tb.y : tb.x);
+        const uint32_t da = (NQ_ISING_MULHI ? __umulhi(y0, two23) : (y0 >> 9)) - (e ? ta.y : ta.x);
+        const uint32_t db = (NQ_ISING_MULHI ? __umulhi(y1, two23) : (y1 >> 9)) - (e ? tb.y : tb.x);
         Fa = __funnelshift_l(da, Fa, 1);
         Fb = __funnelshift_l(db, Fb, 1);
       }
@@ -526,7 +536,7 @@ __global__ void __launch_bounds__(WARP_TEAM ? 32 * NQ_ISING_TEAMS : 1024, WARP_T
       for (int k = 0; k < 10; ++k) hA[k] = hF[k] = 0;
       for (int u = tid; u < units; u += tsize) {
         const int i = u / NW, w = u - i * NW;
-        update_unit<WARP_TEAM ? NQ_ISING_WARP_MODE : 1>(lat, sh, spread, thr_cur, kh[c], c, i, w, hA, hF);
+        update_unit<WARP_TEAM ? NQ_ISING_WARP_MODE : NQ_ISING_CTA_MODE>(lat, sh, spread, thr_cur, kh[c], c, i, w, hA, hF);
       }
 #pragma unroll
       for (int k = 0; k < 10; ++k) {
