@@ -115,6 +115,20 @@ static int partial_row(int D) { return 8 + 2 * (D > 0 ? pad4(kernel_D(D)) : 4); 
 // for small ensembles (hand-off overhead in the latency-bound regime) and, in STRICT mode, for
 // ensembles of many waves (it keeps 12 CTAs per SM resident).  NQ_PERSISTENT = 0 / 1 forces the choice;
 // NQ_PERSISTENT_CHUNK and NQ_PERSISTENT_PER_SM override the two parameters.
+// The thresholds below are per SM (measured on B200, 148 SMs; they scale with the SM count of the device the
+// call runs on).  The NQ_* environment overrides exist for the A/B tests and scans under tests/ and scripts/;
+// every form gives bit-identical results, so they are tuning knobs, not semantics.
+static int sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      sms = n;
+    else
+      return 148;   // no device (host-only argument checks)
+  }
+  return sms;
+}
 static long long chunk_steps(bool fast) {
   const char* env = getenv("NQ_PERSISTENT_CHUNK");
   const long long v = env ? atoll(env) : (fast ? 256 : 128);
@@ -122,13 +136,16 @@ static long long chunk_steps(bool fast) {
 }
 static long long persistent_ctas_per_sm(bool fast, long long n) {
   const char* env = getenv("NQ_PERSISTENT_PER_SM");
-  return env ? atoll(env) : kCtaScale * (fast ? 6 : (n <= 130000 ? 8 : 10));
+  // STRICT: 8 CTAs of 64 per SM up to ~880 trajectories per SM (config 2 is 676), 10 beyond; FAST: 6
+  return env ? atoll(env) : kCtaScale * (fast ? 6 : (n <= 880ll * sm_count() ? 8 : 10));
 }
 static bool use_persistent(long long n, long long S, bool record, bool fast) {
   if (record || S < 2 * chunk_steps(fast)) return false;
   const char* env = getenv("NQ_PERSISTENT");
-  if (env != nullptr) return env[0] == '1' && n >= 148ll * kThreads * 2;
-  return n > 40000 && (fast || n <= 300000);
+  if (env != nullptr) return env[0] == '1' && n >= (long long)sm_count() * kThreads * 2;
+  // from ~270 trajectories per SM (below: hand-off overhead in the latency regime) to ~2030 per SM in STRICT
+  // mode (above: the static launch keeps 11 CTAs per SM resident over many waves and is faster)
+  return n > 270ll * sm_count() && (fast || n <= 2030ll * sm_count());
 }
 static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
@@ -139,8 +156,9 @@ static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 constexpr long long kPairLimit = 65536;   // nq_langevin_workspace_bytes sizes the partial rows for 32-trajectory CTAs up to here
 static long long pair_max() {
   const char* env = getenv("NQ_PAIR_MAX");
-  const long long v = env ? atoll(env) : 12288;  // measured (scripts/latency_scan.py, r02): the three-warp pipeline wins up to here; beyond it the
-                                                  // one-warp kernel is as fast (STRICT) or faster (FAST) -- measured
+  // ~83 trajectories per SM (12 288 on B200): measured (scripts/latency_scan.py, r02), the three-warp pipeline wins
+  // up to here; beyond it the one-warp kernel is as fast (STRICT) or faster (FAST)
+  const long long v = env ? atoll(env) : 83ll * sm_count() + 4;
   return v > kPairLimit ? kPairLimit : v;
 }
 static bool use_pair(long long n, bool record) { return !record && n <= pair_max(); }

@@ -500,7 +500,7 @@ def test_periodic_shift_gradient_vs_oracle(cuda):
 @pytest.mark.parametrize('n,D,potential', [(1, 13, 'shifted'), (37, 5, 'spring'), (1000, 13, 'shifted'), (530, 32, 'biomolecule'),
                                            (200, 1, 'spring'), (64, 20, 'shifted'), (90, 0, 'shifted')])
 def test_small_ensemble_pair_kernel_equals_main_kernel(cuda, monkeypatch, n, D, potential):
-  """Ensembles up to 9472 trajectories run a producer warp (key chain + normal draws) and a consumer
+  """Ensembles up to 12 288 trajectories run a key-chain warp, a draw warp and a consumer
   warp (integration) per 32 trajectories, meeting in a shared-memory ring (langevin_pair_kernel).
   STRICT results per trajectory are bit-identical to the one-warp kernel; the float64 sums differ only
   by grouping."""
@@ -541,7 +541,7 @@ def test_small_ensemble_pair_kernel_equals_main_kernel(cuda, monkeypatch, n, D, 
 
 
 def test_small_ensemble_gradient_pass_records_positions(cuda, monkeypatch):
-  """Up to 9472 trajectories the estimators get the `positions` they return (barrier_crossing.py:213, 223)
+  """Up to 12 288 trajectories the estimators get the `positions` they return (barrier_crossing.py:213, 223)
   from the same fused pass (nq_langevin_grad_record, written by the integration warp of the pair kernel);
   they must be the positions of the forward-record kernel bit for bit, and larger ensembles must fall back."""
   import ctypes as C
