@@ -211,7 +211,7 @@ def run_reference(args):
                                 normalisation='whole host: the same all-core CPU rate at every --gpus N (the host does '
                                               'not grow with N); divide the native value by n_gpus for a per-GPU ratio'),
               e2e=dict(value=value, unit='traj-steps/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-  print(json.dumps(line), flush=True)
+  emit(line)
 
 
 def workload_config(n_gpus):
@@ -313,8 +313,8 @@ def run_native(args):
   value = units / (ms * 1e-3)
   if args.no_extras:     # kernel variants (scripts/variant_strict.sh): the device-resident leg only
     if rank == 0:
-      print(json.dumps(dict(metric='langevin_traj_steps_per_s', value=value, ms_per_step=ms, math_mode=args.math,
-                            n_gpus=ws, mean_work=float(mom[1] / mom[0]))), flush=True)
+      emit(dict(metric='langevin_traj_steps_per_s', value=value, ms_per_step=ms, math_mode=args.math,
+                n_gpus=ws, mean_work=float(mom[1] / mom[0])))
     if ws > 1:
       dist.barrier()
       dist.destroy_process_group()
@@ -394,7 +394,7 @@ def run_native(args):
         cpu_i = cpu_baseline_ising()
         line['ising']['c3_64x64_4096rep_1000sweeps_grad']['cpu_baseline'] = cpu_i['c3']
         line['ising']['c4_1024x1024_256rep']['cpu_baseline'] = cpu_i['c4']
-    print(json.dumps(line), flush=True)
+    emit(line)
   if ws > 1:
     dist.barrier()
     dist.destroy_process_group()
@@ -613,7 +613,25 @@ def cpu_baseline():
                      'the reference itself (JAX-CPU) is not installable in this image')
 
 
+def _json_stdout():
+  """The one JSON line goes to the REAL stdout; everything libraries print on fd 1 meanwhile (NCCL's version banner,
+  for one) is sent to stderr, so that stdout holds the line and nothing else."""
+  sys.stdout.flush()
+  real = os.fdopen(os.dup(1), 'w')
+  os.dup2(2, 1)
+  return real
+
+
+OUT = None
+
+
+def emit(line):
+  print(json.dumps(line), file=OUT or sys.stdout, flush=True)
+
+
 def main():
+  global OUT
+  OUT = _json_stdout()
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
   ap.add_argument('--steps', type=int, default=10)

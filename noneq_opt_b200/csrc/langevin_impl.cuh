@@ -54,7 +54,10 @@ static_assert(kThreads == 32 || kThreads == 64, "32 or 64 trajectories per CTA")
 constexpr int min_blocks(int D) { return kCtaScale * (D <= 8 ? 16 : (D <= 16 ? 11 : (D <= 24 ? 8 : 6))); }
 // The persistent kernel keeps at most 10 CTAs per SM resident, so STRICT may use up to 96 registers
 // (fewer constant reloads: +2.7 % at config 2); FAST is faster with the 80-register schedule (measured).
-constexpr int persistent_min_blocks(int D, bool fast) { return (fast || D > 16) ? min_blocks(D) : 10 * kCtaScale; }
+#ifndef NQ_PERSIST_MINB_STRICT
+#define NQ_PERSIST_MINB_STRICT 10
+#endif
+constexpr int persistent_min_blocks(int D, bool fast) { return (fast || D > 16) ? min_blocks(D) : NQ_PERSIST_MINB_STRICT * kCtaScale; }
 
 struct LangevinConsts {
   int potential, shift_kind;

@@ -87,6 +87,13 @@ class Parameterization:
     from . import tree
     return int(sum(np.asarray(l).size for l in tree.tree_leaves(self.variables)))
 
+  @property
+  def is_affine(self):
+    """value(x) = jacobian(x) @ variables + const?  True for every class of the reference except a Spline with
+    trainable knots; wrappers inherit it from what they wrap."""
+    w = getattr(self, 'wrapped', None)
+    return w.is_affine if isinstance(w, Parameterization) else True
+
 
 class Constant(Parameterization):
   value: np.ndarray
@@ -380,8 +387,13 @@ class Spline(Parameterization):
   k=spline_degree, endpoints=spline_endpoints)`, which is not available offline; this class builds
   the spline from its definition (`_spline_matrix`).  Cubic not-a-knot / natural splines are unique
   and agree with scipy's CubicSpline (tests/test_host_logic.py); for degree 2 the closing condition
-  is an assumption about jax_cosmo's convention -- parity unpinned.  `variable_knots=True` (knots as
-  trainable variables) is not supported: the value is not affine in the knots."""
+  is an assumption about jax_cosmo's convention -- parity unpinned.
+
+  `variable_knots=True` (:192, 195-198) makes the interior knots trainable too: `variables` is then
+  {'knots', 'values'} (pytree leaf order: knots, values -- dict keys sort) and `jacobian` carries the columns
+  d spline(x) / d knot_k in front of the value columns.  The value is NOT affine in the knots, which is fine for
+  the gradient estimators (they only need the Jacobian at the current variables: chain rule) but not for the
+  device-resident trainers, whose on-device schedule rebuild assumes an affine protocol (`is_affine`)."""
   knots: np.ndarray
   values: np.ndarray
   x0: np.ndarray = 0.
@@ -393,10 +405,21 @@ class Spline(Parameterization):
   variable_knots: bool = False
   _VARIABLES = ('values',)
 
-  def __post_init__(self):
+  @property
+  def variables(self):
+    v = dict(values=self.values)
     if self.variable_knots:
-      raise NotImplementedError('Spline(variable_knots=True) is not supported: the kernels need a protocol '
-                                'that is affine in its variables')
+      v['knots'] = self.knots
+    return v
+
+  @property
+  def constants(self):
+    names = set(self.variables)
+    return {f.name: getattr(self, f.name) for f in dataclasses.fields(self) if f.name not in names}
+
+  @property
+  def is_affine(self):
+    return not self.variable_knots
 
   @property
   def domain(self):
@@ -447,4 +470,19 @@ class Spline(Parameterization):
     return y if np.ndim(x) else y[0]
 
   def jacobian(self, x):
-    return self._matrix(x)[:, 1:-1].astype(F32)
+    Jv = self._matrix(x)[:, 1:-1]
+    if not self.variable_knots:
+      return Jv.astype(F32)
+    # d spline(x) / d knot_k: central differences of the float64 construction (smooth in the knots; the step is
+    # 1e-6 of the neighbouring knot spacing, truncation error ~1e-12 relative), columns in front of the values'
+    xs = np.atleast_1d(_f32(x)).astype(np.float64)
+    xk, y = self.x.astype(np.float64), self.y.astype(np.float64)
+    k, ep = int(self.spline_degree), self.spline_endpoints
+    Jk = np.zeros((xs.shape[0], xk.shape[0] - 2))
+    for j in range(1, xk.shape[0] - 1):
+      h = 1e-6 * min(xk[j] - xk[j - 1], xk[j + 1] - xk[j])
+      up, dn = xk.copy(), xk.copy()
+      up[j] += h
+      dn[j] -= h
+      Jk[:, j - 1] = (_spline_matrix(up, k, ep, xs) @ y - _spline_matrix(dn, k, ep, xs) @ y) / (2 * h)
+    return np.concatenate([Jk, Jv], 1).astype(F32)

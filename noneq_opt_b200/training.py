@@ -28,6 +28,10 @@ def _affine_form(coeffs, S):
   """(variables [D], basis [S-1, D], offset [S-1] | None): the trap protocol on the reference's
   scaled step grid as an affine function of its variables (every Parameterization in scope is)."""
   if isinstance(coeffs, p10n.Parameterization):
+    if not coeffs.is_affine:
+      raise NotImplementedError('the device-resident trainer rebuilds the protocol table on the device as basis @ variables '
+                                '+ offset: the protocol must be affine in its variables (Spline(variable_knots=True) is not; '
+                                'use the step-by-step estimators)')
     tv = np.arange(S + 1)[1:-1]
     scaled = ((tv - 1).astype(np.float32) / np.float32(tv[-1] - 1)).astype(np.float32)
     leaves = [np.asarray(l, np.float32).reshape(-1) for l in tree.tree_leaves(coeffs.variables)]
@@ -196,6 +200,9 @@ def _ising_component(param, times):
   if isinstance(inner, p10n.Chebyshev) and np.ndim(inner.weights) == 1:
     return np.asarray(inner.weights, F32).copy(), np.asarray(inner.jacobian(times), F32), scale, offset1, offset2
   # generic affine form of the whole component
+  if not param.is_affine:
+    raise NotImplementedError('IsingTrainer rebuilds the schedule tables on the device as basis @ variables + offset: every '
+                              'schedule component must be affine in its variables (Spline(variable_knots=True) is not)')
   leaves = [np.asarray(l, F32).reshape(-1) for l in tree.tree_leaves(param.variables)]
   v0 = np.concatenate(leaves).astype(F32)
   jac = np.asarray(param.jacobian(times), F32)

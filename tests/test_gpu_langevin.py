@@ -385,6 +385,17 @@ def test_spline_protocol_gradient(cuda):
   assert grad.shape == (6,)
   assert rel(w.cpu().numpy(), o['total_work']) < POS_RTOL
   assert rel(grad.cpu().numpy(), o['grad']) < GRAD_RTOL
+  # variable_knots=True (parameterization.py:192-198): the gradient gains the knot columns (leaf order knots, values)
+  # -- the same trajectories, the Jacobian at the current variables (chain rule; the value is not affine in the knots)
+  proto_k = p10n.Spline(proto.knots, proto.values, 0., 1., 5., 10., spline_degree=3, variable_knots=True)
+  ok = L.estimate_gradient(L.V_spring(1.0), proto_k, x0, J.PRNGKey(2), 5., 10., 10, S, 2.5e-3, 1.0, 1.0, 1.0)
+  grad_k, (_, (_, _, wk)) = est(proto_k, x0.reshape(B, 1, 1), J.PRNGKey(2))
+  assert grad_k.shape == (12,) and torch.equal(wk, w)
+  assert rel(grad_k.cpu().numpy(), ok['grad']) < GRAD_RTOL
+  assert rel(grad_k.cpu().numpy()[6:], o['grad']) < GRAD_RTOL
+  from noneq_opt_b200 import training
+  with pytest.raises(NotImplementedError):
+    training.LangevinTrainer(B, bc.V_spring(1.0), proto_k, 5., 10., 10, shift, S, 2.5e-3, 1.0, 1.0, 1.0, J.PRNGKey(0))
 
 
 def test_piecewise_linear_protocol_gradient(cuda):

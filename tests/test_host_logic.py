@@ -98,12 +98,31 @@ def test_spline_parameterization():
   J = sp2.jacobian(xs)
   bumped = p10n.Spline(kn, v + np.float32(0.5) * np.eye(6, dtype=np.float32)[3], 0., 1., 0.5, -0.5)
   np.testing.assert_allclose((bumped(xs) - sp2(xs)) / 0.5, J[:, 3], atol=1e-5)
+  # variable_knots=True (parameterization.py:192-198): the knots join the variables; leaf order knots, values
+  from noneq_opt_b200 import tree
+  for k in (2, 3):
+    spv = p10n.Spline(kn, v, 0., 1., 0.5, -0.5, spline_degree=k, variable_knots=True)
+    assert set(spv.variables) == {'values', 'knots'} and 'knots' not in spv.constants and not spv.is_affine
+    names = {f.name for f in __import__('dataclasses').fields(spv)}
+    assert set(spv.variables) | set(spv.constants) == names and not set(spv.variables) & set(spv.constants)
+    leaves, treedef = tree.tree_flatten(spv)
+    np.testing.assert_array_equal(leaves[0], kn)
+    np.testing.assert_array_equal(leaves[1], v)
+    assert tree.tree_unflatten(treedef, leaves) == spv and spv.n_variables == 12
+    Jv = spv.jacobian(xs)
+    assert Jv.shape == (101, 12)
+    np.testing.assert_array_equal(Jv[:, 6:], p10n.Spline(kn, v, 0., 1., 0.5, -0.5, spline_degree=k).jacobian(xs))
+    M = lambda knots: p10n._spline_matrix(np.concatenate([[0.], knots, [1.]]), k, 'not-a-knot', xs.astype(np.float64)) @ spv.y.astype(np.float64)
+    for j in (0, 3, 5):      # against a wide central difference of the float64 construction
+      e = np.zeros(6); e[j] = 1e-4
+      fd = (M(kn.astype(np.float64) + e) - M(kn.astype(np.float64) - e)) / 2e-4
+      np.testing.assert_allclose(Jv[:, j], fd, atol=2e-5 * max(1.0, np.abs(fd).max()))
+  assert p10n.AddBaseline(p10n.ConstrainEndpoints(spv, 0., 0.), lambda t: t).is_affine is False
+  assert p10n.ConstrainEndpoints(p10n.Chebyshev(np.zeros(3, np.float32)), 0., 0.).is_affine
   eq = p10n.Spline.equidistant(4, 0., 2., 1., 3., spline_degree=3)
   np.testing.assert_allclose(eq(np.linspace(0, 2, 9, dtype=np.float32)), np.linspace(1, 3, 9), atol=1e-6)
   fb = p10n.Spline.from_baseline(lambda t: np.float32(2) * t, 3, 0., 1.)
   np.testing.assert_allclose(fb(xs), 2 * xs, atol=1e-6)
-  with pytest.raises(NotImplementedError):
-    p10n.Spline(kn, v, variable_knots=True)
   with pytest.raises(ValueError):
     p10n.Spline(kn[::-1].copy(), v)(xs)
 
