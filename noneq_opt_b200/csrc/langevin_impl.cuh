@@ -43,7 +43,10 @@ namespace nq {
 #define NQ_LANGEVIN_UNROLL 1
 #endif
 constexpr int kUnroll = NQ_LANGEVIN_UNROLL;
-constexpr int kTile = 128;    // steps staged per shared-memory tile
+#ifndef NQ_LANGEVIN_TILE
+#define NQ_LANGEVIN_TILE 128
+#endif
+constexpr int kTile = NQ_LANGEVIN_TILE;    // steps staged per shared-memory tile
 #ifndef NQ_LANGEVIN_THREADS
 #define NQ_LANGEVIN_THREADS 64
 #endif
@@ -52,10 +55,11 @@ constexpr int kCtaScale = 64 / kThreads;       // CTAs per 64 trajectories
 static_assert(kThreads == 32 || kThreads == 64, "32 or 64 trajectories per CTA");
 // resident CTAs per SM the register budget is held to, so that config 2 (1563 CTAs of 64) is one wave
 constexpr int min_blocks(int D) { return kCtaScale * (D <= 8 ? 16 : (D <= 16 ? 11 : (D <= 24 ? 8 : 6))); }
-// The persistent kernel keeps at most 10 CTAs per SM resident, so STRICT may use up to 96 registers
-// (fewer constant reloads: +2.7 % at config 2); FAST is faster with the 80-register schedule (measured).
+// The persistent STRICT kernel runs 8 CTAs per SM at config 2 (measured best), so it may use up to 128 registers:
+// 108 are used, +3 % over the 96-register build of round 1 (gpurun_out/variants_r02j.log: 8.39 against 8.14e10);
+// FAST is faster with the 80-register schedule (measured).
 #ifndef NQ_PERSIST_MINB_STRICT
-#define NQ_PERSIST_MINB_STRICT 10
+#define NQ_PERSIST_MINB_STRICT 8
 #endif
 constexpr int persistent_min_blocks(int D, bool fast) { return (fast || D > 16) ? min_blocks(D) : NQ_PERSIST_MINB_STRICT * kCtaScale; }
 
@@ -211,6 +215,11 @@ struct RngPipeT {
       const KeyInject ks = key_inject(s0, s1, one);
       threefry2x32_inj<INJ == 2>(ks, ks.ks0, ks.ks1, one, bits, unused);   // normal(split, [1,1,1]) :88
       split2_inj<INJ == 2>(k0, k1, one, n0, n1, t0, t1);       // key, split = split(state.rng) of the NEXT step :79
+    } else if (NQ_TF_WIDE_MASK != 0u) {   // experiment: see threefry2x32_w
+      threefry2x32_w(key_schedule(s0, s1), 0u, 0u, one, bits, unused);
+      const KeySchedule kk = key_schedule(k0, k1);
+      threefry2x32_w(kk, 0u, 2u, one, n0, t0);
+      threefry2x32_w(kk, 1u, 3u, one, n1, t1);
     } else {
       threefry2x32(key_schedule(s0, s1), 0u, 0u, bits, unused);  // normal(split, [1,1,1]) :88
       split2(k0, k1, n0, n1, t0, t1);                            // key, split = split(state.rng) of the NEXT step :79
