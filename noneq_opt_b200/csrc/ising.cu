@@ -623,6 +623,232 @@ __global__ void ising_status_kernel(const unsigned* status, float* summary, size
     summary[i] = __int_as_float(0x7fc00000);
 }
 
+// ------------------------------------------------------------------------------ bit-packed 3-D kernel
+// The fast path for cubic / cuboid lattices d0 x d1 x d2 (the reference's own 3-D test shape is 64^3,
+// tests/ising_test.py:71; sum_neighbors / even_odd_masks are rank-generic, ising.py:75-106).  Same design as the 2-D
+// CTA-team kernel -- lattice bit-packed in shared memory as two colour planes, a 32-bit word = 32 simultaneously
+// updatable sites of one row, jax's counter pairing (p, p + N/2) = rows (i, j) and (i + d0/2, j) served by ONE threefry
+// block, integer thresholds, bit-sliced neighbour counts, class histograms by popc -- with "rows" = the d0 * d1
+// lines along the last axis, six neighbour words per word (j -+ 1, i -+ 1 whole words; k -+ 1 in-row, one of them
+// funnel-shifted) and 2 x 7 site classes (spin, #up-neighbours 0..6).
+// Requires d2 % 64 == 0 (whole words per colour per row), d1 even, d0 % 4 == 0 (the counter partner has the same
+// colour) and 2 d0 d1 d2 / 64 words of shared memory.
+struct Shape3 {
+  int d0, d1, NW;   // NW = d2 / 64 words per row per colour
+};
+
+__device__ __forceinline__ void count_planes6(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f, Planes& p) {
+  const uint32_t s1 = a ^ b ^ c, k1 = (a & b) | (c & (a ^ b));   // a + b + c = s1 + 2 k1
+  const uint32_t s2 = d ^ e ^ f, k2 = (d & e) | (f & (d ^ e));
+  p.C0 = s1 ^ s2;
+  const uint32_t t = s1 & s2;
+  p.C1 = k1 ^ k2 ^ t;
+  p.C2 = (k1 & k2) | (t & (k1 ^ k2));
+}
+
+__device__ __forceinline__ void load_planes3(const uint32_t* lat, const Shape3& g, int c, int i, int j, int w, Planes& p) {
+  const int NW = g.NW, rows = g.d0 * g.d1, r = i * g.d1 + j;
+  const uint32_t* own = lat + (size_t)c * rows * NW;
+  const uint32_t* oth = lat + (size_t)(1 - c) * rows * NW;
+  const int ju = j == 0 ? g.d1 - 1 : j - 1, jd = j == g.d1 - 1 ? 0 : j + 1;
+  const int iu = i == 0 ? g.d0 - 1 : i - 1, id = i == g.d0 - 1 ? 0 : i + 1;
+  const uint32_t X = oth[r * NW + w];
+  uint32_t Xs;
+  if ((((i + j) & 1) == 0) == (c == 0)) {  // second in-row neighbour is site k+1
+    const uint32_t Xn = oth[r * NW + (w + 1 == NW ? 0 : w + 1)];
+    Xs = __funnelshift_r(X, Xn, 1);
+  } else {  // site k-1
+    const uint32_t Xp = oth[r * NW + (w == 0 ? NW - 1 : w - 1)];
+    Xs = __funnelshift_l(Xp, X, 1);
+  }
+  p.S = own[r * NW + w];
+  count_planes6(oth[(i * g.d1 + ju) * NW + w], oth[(i * g.d1 + jd) * NW + w], oth[(iu * g.d1 + j) * NW + w],
+                oth[(id * g.d1 + j) * NW + w], X, Xs, p);
+}
+
+// per-class popcounts, 7 neighbour counts per spin value: h[k] spin down, h[7 + k] spin up
+__device__ __forceinline__ void histogram7(const Planes& p, uint32_t F, int (&hA)[14], int (&hF)[14]) {
+  const uint32_t n2 = ~p.C2, n1 = ~p.C1, n0 = ~p.C0;
+  const uint32_t E[7] = {n2 & n1 & n0, n2 & n1 & p.C0, n2 & p.C1 & n0, n2 & p.C1 & p.C0,
+                         p.C2 & n1 & n0, p.C2 & n1 & p.C0, p.C2 & p.C1 & n0};
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const uint32_t up = E[k] & p.S, down = E[k] & ~p.S;
+    hA[k] += __popc(down);
+    hA[7 + k] += __popc(up);
+    hF[k] += __popc(down & F);
+    hF[7 + k] += __popc(up & F);
+  }
+}
+
+// word w of rows (i, j) and (i + d0/2, j) of colour c: 32 threefry blocks, 64 site updates
+__device__ __forceinline__ void update_unit3(uint32_t* lat, const Shape3& g, const uint32_t* spread, const uint2* thr2,
+                                             const KeySchedule& ks, uint32_t one, int c, int i, int j, int w,
+                                             int (&hA)[14], int (&hF)[14]) {
+  const int NW = g.NW, rows = g.d0 * g.d1, i2 = i + g.d0 / 2, d2 = 64 * NW;
+  Planes pa, pb;
+  load_planes3(lat, g, c, i, j, w, pa);
+  load_planes3(lat, g, c, i2, j, w, pb);
+  const int rp = (i + j) & 1;                      // (i2 + j) has the same parity: d0 / 2 is even
+  const int off = c == 0 ? 1 - rp : rp;
+  const uint32_t cbase = (uint32_t)(i * g.d1 + j) * d2 + 2u * (32u * w) + off;
+  const uint32_t half = (uint32_t)rows * d2 / 2;
+  uint32_t Fa = 0, Fb = 0;
+#pragma unroll 1
+  for (int q = 3; q >= 0; --q) {
+    const uint32_t Na = class_nibbles(spread, pa, q), Nb = class_nibbles(spread, pb, q);
+#pragma unroll
+    for (int jj = 3; jj >= 0; --jj) {
+      const uint2 ta = thr_pair(thr2, Na, jj), tb = thr_pair(thr2, Nb, jj);
+#pragma unroll
+      for (int e = 1; e >= 0; --e) {
+        const uint32_t ctr = cbase + 2u * (8u * q + 2u * jj + e);
+        uint32_t y0, y1;
+        threefry2x32_allmad(ks, ctr, ctr + half, y0, y1, one);
+        const uint32_t da = (y0 >> 9) - (e ? ta.y : ta.x);
+        const uint32_t db = (y1 >> 9) - (e ? tb.y : tb.x);
+        Fa = __funnelshift_l(da, Fa, 1);
+        Fb = __funnelshift_l(db, Fb, 1);
+      }
+    }
+  }
+  uint32_t* own = lat + (size_t)c * rows * NW;
+  own[(i * g.d1 + j) * NW + w] = pa.S ^ Fa;
+  own[(i2 * g.d1 + j) * NW + w] = pb.S ^ Fb;
+  histogram7(pa, Fa, hA, hF);
+  histogram7(pb, Fb, hA, hF);
+}
+
+// Shared memory: spread[4][256] | lattice[2][d0 d1][NW] | pair thresholds[2][256] (uint2) | hist[2][2][2][16] | 2 ints
+__global__ void __launch_bounds__(1024, 1) ising_fast3d_kernel(const IsingShape sh, const IsingIO io) {
+  extern __shared__ uint32_t smem[];
+  const Shape3 g{sh.d0, sh.d1, sh.d2 / 64};
+  const int NW = g.NW, rows = g.d0 * g.d1, d2 = sh.d2, T = sh.T;
+  const int plane_words = rows * NW;
+  uint32_t* spread = smem;
+  uint32_t* lat = smem + 4 * 256;
+  uint2* thr_s = reinterpret_cast<uint2*>(lat + 2 * plane_words);
+  int* hist_s = reinterpret_cast<int*>(lat + 2 * plane_words + 2 * 256 * 2);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x, tsize = blockDim.x;
+  const long long rep = blockIdx.x;
+  const size_t ext_words = (size_t)sh.N / 32;
+  const int row_ext = d2 / 32;
+
+  for (int v = tid; v < 4 * 256; v += tsize) spread[v] = spread8_to_nibbles(v & 255) << (v >> 8);
+  for (int v = tid; v < 2 * 2 * 2 * kIsingClasses + 2; v += tsize) hist_s[v] = 0;
+  // ---- load the lattice (row-major bits -> colour planes); colour 0 = odd index sum (the reference's "even" mask)
+  const uint32_t* ext0 = io.spins0 + (sh.broadcast0 ? 0 : rep * ext_words);
+  for (int u = tid; u < plane_words; u += tsize) {
+    const int r = u / NW, w = u - r * NW;
+    uint32_t c0, c1;
+    split_colours((r / g.d1 + r % g.d1) & 1, ext0[r * row_ext + 2 * w], ext0[r * row_ext + 2 * w + 1], c0, c1);
+    lat[u] = c0;
+    lat[plane_words + u] = c1;
+  }
+  if (T > 1) build_pair_table(thr_s + 256, io.thr, tid, tsize);   // sweep t = 1 -> parity buffer 1
+  __syncthreads();
+
+  // ---- initial spin sum M and bond sum B (each bond joins a colour-0 and a colour-1 site)
+  long long M, B;
+  {
+    int hA[14], hF[14];
+#pragma unroll
+    for (int k = 0; k < 14; ++k) hA[k] = hF[k] = 0;
+    int up = 0;
+    for (int u = tid; u < plane_words; u += tsize) {
+      const int r = u / NW, w = u - r * NW;
+      Planes p;
+      load_planes3(lat, g, 0, r / g.d1, r % g.d1, w, p);
+      histogram7(p, 0u, hA, hF);
+      up += __popc(lat[u]) + __popc(lat[plane_words + u]);
+    }
+    int b = 0;
+#pragma unroll
+    for (int k = 0; k < 14; ++k) b += (k >= 7 ? 1 : -1) * (2 * (k % 7) - 6) * hA[k];
+    up = __reduce_add_sync(0xffffffffu, up);
+    b = __reduce_add_sync(0xffffffffu, b);
+    int* tmp = hist_s + 2 * 2 * 2 * kIsingClasses;
+    if (lane == 0) { atomicAdd(&tmp[0], up); atomicAdd(&tmp[1], b); }
+    __syncthreads();
+    M = 2ll * tmp[0] - (long long)sh.N;
+    B = tmp[1];
+  }
+
+  const KeySchedule ks_rep = key_schedule(io.seeds[2 * rep], io.seeds[2 * rep + 1]);
+  const int units = (g.d0 / 2) * g.d1 * NW;
+  for (int t = 1; t < T; ++t) {
+    KeySchedule kh[2];
+    sweep_keys(ks_rep, t, T, sh.direct_keys != 0, kh[0], kh[1]);
+    const uint2* thr_cur = thr_s + (t & 1) * 256;
+    if (t + 1 < T) build_pair_table(thr_s + ((t + 1) & 1) * 256, io.thr + (size_t)t * kIsingClasses, tid, tsize);
+    for (int c = 0; c < 2; ++c) {
+      int hA[14], hF[14];
+#pragma unroll
+      for (int k = 0; k < 14; ++k) hA[k] = hF[k] = 0;
+      for (int u = tid; u < units; u += tsize) {
+        const int r = u / NW, w = u - r * NW;
+        update_unit3(lat, g, spread, thr_cur, kh[c], sh.one, c, r / g.d1, r % g.d1, w, hA, hF);
+      }
+      int* hs = hist_s + ((t & 1) * 2 + c) * 2 * kIsingClasses;
+#pragma unroll
+      for (int k = 0; k < 14; ++k) {
+        const int a = __reduce_add_sync(0xffffffffu, hA[k]), f = __reduce_add_sync(0xffffffffu, hF[k]);
+        if (lane == 0) {
+          if (a) atomicAdd(&hs[k], a);
+          if (f) atomicAdd(&hs[kIsingClasses + k], f);
+        }
+      }
+      __syncthreads();
+    }
+    if (io.states) {  // return_states=True: the lattice after this sweep, row-major bits
+      uint32_t* dst = io.states + ((size_t)rep * (T - 1) + (t - 1)) * ext_words;
+      for (int u = tid; u < plane_words; u += tsize) {
+        const int r = u / NW, w = u - r * NW;
+        uint32_t lo, hi;
+        merge_colours((r / g.d1 + r % g.d1) & 1, lat[u], lat[plane_words + u], lo, hi);
+        dst[r * row_ext + 2 * w] = lo;
+        dst[r * row_ext + 2 * w + 1] = hi;
+      }
+    }
+    if (warp == 0) {
+      int a2[2], f2[2];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        int* hs = hist_s + ((t & 1) * 2 + c) * 2 * kIsingClasses;
+        a2[c] = lane < 14 ? hs[lane] : 0;
+        f2[c] = lane < 14 ? hs[kIsingClasses + lane] : 0;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        int* hs = hist_s + ((t & 1) * 2 + c) * 2 * kIsingClasses;
+        if (lane < 14) { hs[lane] = 0; hs[kIsingClasses + lane] = 0; }
+      }
+      emit_summary(a2, f2, io, sh, rep, t, M, B, lane);
+    }
+    __syncthreads();   // (states written, histograms of this parity cleared before they are used again)
+  }
+  if (io.spins_out) {
+    uint32_t* dst = io.spins_out + (size_t)rep * ext_words;
+    for (int u = tid; u < plane_words; u += tsize) {
+      const int r = u / NW, w = u - r * NW;
+      uint32_t lo, hi;
+      merge_colours((r / g.d1 + r % g.d1) & 1, lat[u], lat[plane_words + u], lo, hi);
+      dst[r * row_ext + 2 * w] = lo;
+      dst[r * row_ext + 2 * w + 1] = hi;
+    }
+  }
+}
+
+static size_t fast3d_smem_bytes(const int* dims) {
+  const size_t plane_words = (size_t)dims[0] * dims[1] * (dims[2] / 64);
+  return (4 * 256 + 2 * plane_words + 2 * 256 * 2 + 2 * 2 * 2 * kIsingClasses + 2) * 4;
+}
+static bool fast3d_ok(int ndim, const int* dims) {
+  return ndim == 3 && dims[2] % 64 == 0 && dims[1] % 2 == 0 && dims[0] % 4 == 0 && fast3d_smem_bytes(dims) <= 227 * 1024 &&
+         getenv("NQ_ISING_NO_FAST3D") == nullptr;
+}
+
 // ------------------------------------------------------------------------------ generic kernel
 // Any even-sided 1-D / 2-D / 3-D periodic lattice (the reference's tests use 10000, 256x256 and
 // 64^3): one CTA per replica, one spin per byte in shared memory (or in a global scratch when the
@@ -1068,6 +1294,7 @@ extern "C" size_t nq_ising_workspace_bytes(const NqIsingDesc* desc) {
       return plan_segments(dims[0], desc->R, desc->T).bytes();  // optional: without it the run is unsegmented
     return (size_t)desc->R * 2 * dims[0] * (dims[0] / 64) * 4;   // colour planes in global memory
   }
+  if (fast3d_ok(ndim, dims)) return 0;   // bit-packed 3-D kernel: lattice in shared memory
   if (generic_smem_bytes(N) <= 200 * 1024) return 0;
   return (size_t)desc->R * N;
 }
@@ -1144,6 +1371,12 @@ extern "C" int nq_ising_run(const NqIsingDesc* desc, const uint32_t* thr, const 
         ising_fast_kernel<false><<<blocks, threads, smem, st>>>(sh, io);
       }
     }
+  } else if (fast3d_ok(ndim, dims)) {
+    const size_t smem = fast3d_smem_bytes(dims);
+    const int units = (dims[0] / 2) * dims[1] * (dims[2] / 64);
+    const int threads = units >= 1024 ? 1024 : ((units + 31) / 32) * 32;
+    NQ_CUDA(cudaFuncSetAttribute(ising_fast3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ising_fast3d_kernel<<<(unsigned)desc->R, threads, smem, st>>>(sh, io);
   } else {
     size_t smem = generic_smem_bytes(N);
     if (smem > 200 * 1024) {   // spins live in the caller's workspace (L2-resident), tables stay in shared memory
