@@ -505,3 +505,56 @@ def test_gradient_assembly_kernel_matches_torch_contraction(cuda, loss_name, L, 
                     (t['reparam'][0], dL_dl @ Jl), (t['reparam'][1], dL_dh @ Jh)):
     scale = float(want.abs().max()) + 1e-300
     assert float((got - want).abs().max()) <= 1e-11 * scale + 1e-9
+
+
+@pytest.mark.parametrize('shape,R,T', [((64, 64, 64), 2, 4), ((4, 2, 64), 3, 6), ((8, 6, 128), 2, 5), ((12, 4, 64), 2, 4)])
+def test_bit_packed_3d_kernel_is_bit_exact(cuda, shape, R, T, monkeypatch):
+  """ising_fast3d_kernel: cuboid lattices with d2 % 64 == 0, d1 even, d0 % 4 == 0 (64^3 is the reference's own 3-D test
+  shape, tests/ising_test.py:71) run bit-packed in shared memory -- six neighbour words per word, 2 x 7 site classes,
+  one threefry block per TWO spin-updates (counter partner (i + d0/2, j, k) has the same colour).  Spin histories
+  bit-exact against the oracle, summaries within the ulp bounds, and everything equal to the byte-per-spin generic
+  kernel (NQ_ISING_NO_FAST3D=1)."""
+  from noneq_opt_b200 import ising
+  lt = np.log(np.linspace(4.2, 3.4, T).astype(np.float32))
+  h = np.linspace(-0.4, 0.5, T).astype(np.float32)
+  params = ising.IsingParameters(lt, h)
+  s0 = I.random_spins(shape, .45, J.PRNGKey(13))
+  seeds = J.split(J.PRNGKey(6), R)
+  n_sites = int(np.prod(shape))
+
+  def run():
+    final, (summary, states) = ising.simulate_ising(params, s0, seeds, return_states=True)
+    torch.cuda.synchronize()
+    return final.spins.clone(), [getattr(summary, f).clone() for f in FIELDS], states.spins.clone()
+  fin, summ, states = run()
+  assert tuple(fin.shape) == (R,) + shape and tuple(states.shape) == (R, T - 1) + shape
+  for r in range(R):
+    fin_o, summ_o, states_o = I.simulate_ising(lt, h, s0, seeds[r], return_states=True)
+    np.testing.assert_array_equal(fin[r].cpu().numpy(), fin_o)
+    np.testing.assert_array_equal(states[r].cpu().numpy(), states_o)
+    check_summary(np.stack([s[r].cpu().numpy() for s in summ]), np.stack([getattr(summ_o, f) for f in FIELDS]), n_sites)
+  monkeypatch.setenv('NQ_ISING_NO_FAST3D', '1')
+  fin_g, summ_g, states_g = run()
+  assert torch.equal(fin_g, fin) and torch.equal(states_g, states)
+  for a, b in zip(summ_g, summ):
+    assert torch.equal(a, b)
+
+
+def test_bit_packed_3d_kernel_gradients(cuda):
+  """REINFORCE gradients of both losses on a 3-D lattice that takes the bit-packed path, against the oracle's
+  closed-form gradient (binary64 on the float32 trajectory)."""
+  from noneq_opt_b200 import ising, parameterization as p10n
+  shape, T = (4, 6, 64), 7
+  w = (0.2 * np.random.RandomState(5).normal(size=(2, 5))).astype(np.float32)
+  sched = ising.IsingSchedule(p10n.Chebyshev(w[0] + np.float32([1.2, 0, 0, 0, 0])), p10n.Chebyshev(w[1]))
+  times = np.linspace(0, 1, T, dtype=np.float32)
+  params = sched(times)
+  s0 = I.random_spins(shape, .5, J.PRNGKey(3))
+  seeds = J.split(J.PRNGKey(8), 2)
+  Jlt = P.Chebyshev(np.zeros(5), np.float64).jacobian(times.astype(np.float64))
+  for loss in ('total_work', 'total_entropy_production'):
+    g, _ = ising.estimate_gradient_rev(getattr(ising, loss))(sched, times, s0, seeds)
+    got = np.concatenate([g.log_temp.weights.cpu().numpy(), g.field.weights.cpu().numpy()], -1)
+    for r in range(2):
+      o = I.closed_form_gradient(loss, np.asarray(params.log_temp), np.asarray(params.field), Jlt, Jlt, s0, seeds[r])
+      assert rel(got[r], np.concatenate(o['grad'])) < 1e-4
