@@ -54,7 +54,10 @@ constexpr int kThreads = NQ_LANGEVIN_THREADS;  // trajectories per CTA (small CT
 constexpr int kCtaScale = 64 / kThreads;       // CTAs per 64 trajectories
 static_assert(kThreads == 32 || kThreads == 64, "32 or 64 trajectories per CTA");
 // resident CTAs per SM the register budget is held to, so that config 2 (1563 CTAs of 64) is one wave
-constexpr int min_blocks(int D) { return kCtaScale * (D <= 8 ? 16 : (D <= 16 ? 11 : (D <= 24 ? 8 : 6))); }
+#ifndef NQ_STATIC_MINB_16   // resident CTAs per SM the static kernels with 9..16 coefficients are compiled for
+#define NQ_STATIC_MINB_16 11
+#endif
+constexpr int min_blocks(int D) { return kCtaScale * (D <= 8 ? 16 : (D <= 16 ? NQ_STATIC_MINB_16 : (D <= 24 ? 8 : 6))); }
 // The persistent STRICT kernel runs 8 CTAs per SM at config 2 (measured best), so it may use up to 128 registers:
 // 108 are used, +3 % over the 96-register build of round 1 (gpurun_out/variants_r02j.log: 8.39 against 8.14e10);
 // FAST is faster with the 80-register schedule (measured).
