@@ -54,17 +54,26 @@ constexpr int kThreads = NQ_LANGEVIN_THREADS;  // trajectories per CTA (small CT
 constexpr int kCtaScale = 64 / kThreads;       // CTAs per 64 trajectories
 static_assert(kThreads == 32 || kThreads == 64, "32 or 64 trajectories per CTA");
 // resident CTAs per SM the register budget is held to, so that config 2 (1563 CTAs of 64) is one wave
-#ifndef NQ_STATIC_MINB_16   // resident CTAs per SM the static kernels with 9..16 coefficients are compiled for
-#define NQ_STATIC_MINB_16 11
+// Resident CTAs per SM the kernels are compiled for (the register budget).  Measured at the config-5 shard size
+// (1.25e6 trajectories, static launch; gpurun_out/variants_r02m.log, 1e10 traj-steps/s STRICT / FAST):
+// 11 CTAs (88 registers) 8.61 / 10.1, 10: 8.34 / 10.7, 9: 8.36 / 10.7, 8 (128 registers): 8.24 / 10.8 --
+// STRICT wants the warps, FAST the registers.
+#ifndef NQ_STATIC_MINB_STRICT
+#define NQ_STATIC_MINB_STRICT 11
 #endif
-constexpr int min_blocks(int D) { return kCtaScale * (D <= 8 ? 16 : (D <= 16 ? NQ_STATIC_MINB_16 : (D <= 24 ? 8 : 6))); }
-// The persistent STRICT kernel runs 8 CTAs per SM at config 2 (measured best), so it may use up to 128 registers:
-// 108 are used, +3 % over the 96-register build of round 1 (gpurun_out/variants_r02j.log: 8.39 against 8.14e10);
-// FAST is faster with the 80-register schedule (measured).
-#ifndef NQ_PERSIST_MINB_STRICT
-#define NQ_PERSIST_MINB_STRICT 8
+#ifndef NQ_STATIC_MINB_FAST
+#define NQ_STATIC_MINB_FAST 8
 #endif
-constexpr int persistent_min_blocks(int D, bool fast) { return (fast || D > 16) ? min_blocks(D) : NQ_PERSIST_MINB_STRICT * kCtaScale; }
+constexpr int min_blocks(int D, bool fast) {
+  return kCtaScale * (D <= 8 ? 16 : (D <= 16 ? (fast ? NQ_STATIC_MINB_FAST : NQ_STATIC_MINB_STRICT) : (D <= 24 ? 8 : 6)));
+}
+// The persistent kernels run 8 (STRICT) / 6 (FAST) CTAs per SM at config 2 (measured best), so they may use up to 128
+// registers: STRICT uses 108, +3 % over the 96-register build of round 1 (gpurun_out/variants_r02j.log: 8.39 against
+// 8.14e10).
+#ifndef NQ_PERSIST_MINB
+#define NQ_PERSIST_MINB 8
+#endif
+constexpr int persistent_min_blocks(int D, bool fast) { return D > 16 ? min_blocks(D, fast) : NQ_PERSIST_MINB * kCtaScale; }
 
 struct LangevinConsts {
   int potential, shift_kind;
@@ -708,7 +717,7 @@ __device__ __forceinline__ void langevin_chunk(const LangevinConsts& c_in, const
 }
 
 template <int POT, bool FAST, int D, bool RECORD>
-__global__ void __launch_bounds__(kThreads, min_blocks(D)) langevin_kernel(const LangevinConsts c, const LangevinIO io) {
+__global__ void __launch_bounds__(kThreads, min_blocks(D, FAST)) langevin_kernel(const LangevinConsts c, const LangevinIO io) {
   langevin_chunk<POT, FAST, D, RECORD, NQ_PIN_STATIC && !FAST && !RECORD>(c, io, blockIdx.x, 1, c.S, true, true, nullptr, 0);
 }
 
