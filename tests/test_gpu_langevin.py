@@ -575,3 +575,26 @@ def test_small_ensemble_gradient_pass_records_positions(cuda, monkeypatch):
   monkeypatch.delenv('NQ_PAIR_MAX')
   assert torch.equal(pos2, pos) and torch.equal(w2, w) and torch.equal(lp2, lp)
   np.testing.assert_allclose(grad2.cpu().numpy(), grad.cpu().numpy(), rtol=1e-6)
+
+
+def test_rank_generic_state_shapes_as_in_the_reference_test(cuda):
+  """tests/simulate_test.py:14-35 (`test_shapes`: 111 particles x 3 dimensions, 35 steps) re-expressed for a descriptor
+  energy: positions keep their shape, the key advances, `log_prob` is the scalar sum over all elements that the
+  shipped source computes (simulate.py:95 -- the reference test's `(num_particles,)` expectation is stale),
+  and every step agrees with the oracle's restatement."""
+  from noneq_opt_b200 import simulate, potentials, space
+  num_particles, dimension, num_steps, dt = 111, 3, 35, 1e-3
+  _, shift_fn = space.free()
+  init_fn, apply_fn = simulate.brownian(potentials.V_spring(2.0), shift_fn, dt, 1., 1e-1)
+  state = init_fn(J.PRNGKey(9), np.ones([num_particles, dimension], np.float32))
+  sc = L.step_constants(dt, 1., 1.0, 1e-1)
+  x_o, key_o = np.ones([num_particles, dimension], np.float32), J.PRNGKey(9)
+  t = 0.
+  for _ in range(num_steps):
+    state = apply_fn(state, t, r0=0.25)
+    x_o, key_o, lp_o, _ = L.brownian_apply_nd(L.V_spring(2.0), sc, x_o, key_o, 0.25)
+    t += dt
+    assert tuple(state.position.shape) == (num_particles, dimension) and tuple(state.log_prob.shape) == ()
+    np.testing.assert_array_equal(state.rng.cpu().numpy().view(np.uint32), key_o)
+  assert rel(state.position.cpu().numpy(), x_o) < POS_RTOL
+  assert abs(float(state.log_prob) - float(lp_o)) <= POS_RTOL * abs(float(lp_o))
