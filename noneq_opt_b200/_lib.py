@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libnoneq_b200.so')
+# NQ_B200_LIB: development override (scripts/build_variants.sh: A/B runs of kernel build variants); never a fallback
+LIB_PATH = os.environ.get('NQ_B200_LIB') or os.path.join(HERE, 'libnoneq_b200.so')
 
 NQ_POT_SPRING, NQ_POT_BIOMOLECULE, NQ_POT_BIOMOLECULE_SHIFTED = 0, 1, 2
 NQ_SHIFT_FREE, NQ_SHIFT_PERIODIC = 0, 1

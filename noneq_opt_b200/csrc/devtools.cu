@@ -161,7 +161,8 @@ __device__ float normal_literal(uint32_t bits) {
 }
 
 // which: 0 logf_main(x) vs logf(x); 1 log1pf_main(-x) vs log1pf(-x); 2 div_main(c, x) vs c / x (IEEE);
-//        3 normal_from_bits<false>(p << 9) vs normal_literal(p << 9), p = the bit pattern itself.
+//        3 normal_from_bits<false>(p << 9) vs normal_literal(p << 9), p = the bit pattern itself;
+//        4 expf_main(x) vs expf(x); 5 expf_main2({x, -x}) vs {expf(x), expf(-x)}.
 // x = the float with bit pattern p, p in [first, first + count).  out[0] = mismatches, out[1] = first mismatching p.
 __global__ void math_check_kernel(int which, unsigned long long first, unsigned long long count, float c,
                                   unsigned long long* out) {
@@ -174,7 +175,15 @@ __global__ void math_check_kernel(int which, unsigned long long first, unsigned 
     if (which == 0) { a = logf_main(x); b = logf(x); }
     else if (which == 1) { a = log1pf_main(-x); b = log1pf(-x); }
     else if (which == 2) { a = div_main(c, x); b = __fdiv_rn(c, x); }
-    else { a = normal_from_bits<false>(p << 9); b = normal_literal(p << 9); }
+    else if (which == 3) { a = normal_from_bits<false>(p << 9); b = normal_literal(p << 9); }
+    else if (which == 4) { const StrictRegs sr; a = expf_main(x, sr.exp_k1, sr.exp_k252); b = expf(x); }
+    else {   // both halves of the packed form: lo = exp(x), hi = exp(-x)
+      const StrictRegs sr;
+      float hi;
+      f2_unpack(expf_main2(f2_pack(x, -x), sr.exp_k1, sr.exp_k252), a, hi);
+      b = expf(x);
+      if (__float_as_uint(hi) != __float_as_uint(expf(-x))) a = __uint_as_float(~__float_as_uint(b));
+    }
     if (__float_as_uint(a) != __float_as_uint(b)) {
       ++bad;
       if (first + i < where) where = first + i;
@@ -190,7 +199,7 @@ __global__ void math_check_kernel(int which, unsigned long long first, unsigned 
 
 extern "C" int nqdev_math_check(int32_t which, uint64_t first, uint64_t count, float c, uint64_t* out /*device [2]*/,
                                 void* stream) {
-  if (which < 0 || which > 3 || !out) return NQ_ERR_INVALID_ARGUMENT;
+  if (which < 0 || which > 5 || !out) return NQ_ERR_INVALID_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned long long init[2] = {0ull, ~0ull};
   if (cudaMemcpyAsync(out, init, sizeof(init), cudaMemcpyHostToDevice, st) != cudaSuccess) return NQ_ERR_CUDA;

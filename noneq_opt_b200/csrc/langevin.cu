@@ -1,6 +1,7 @@
 // Host side of the Langevin entry points of include/noneq_b200.h: descriptor -> kernel constants
 // (float32, reference operation order), argument checks, kernel dispatch, deterministic final
 // reduction.  Kernels: langevin_impl.cuh.
+#include <cstring>
 #include <stdlib.h>
 
 #include "langevin_impl.cuh"
@@ -57,6 +58,20 @@ int make_langevin_consts(const NqLangevinDesc* d, LangevinConsts* c) {
   // STRICT main-path window of the division / logarithm of A + B (div_main, logf_main): the numerator
   // 1 / beta must sit inside [2^-62, 2^62) too, otherwise every step takes the library functions
   c->guard_span = (c->inv_beta >= 0x1p-62f && c->inv_beta < 0x1p62f) ? 0x3e000000u : 0u;
+  // Lower edge of that window as a float compare (the hot loop's single rare-case predicate): valid only where A + B
+  // cannot leave the window at the top, i.e. both exponents are bounded above (A <= 1 for cl <= 0, B <= exp(-bde)
+  // for cr >= 0); otherwise +inf sends every step through the patch block, which tests the full window
+  {
+    const bool bounded = c->cl <= 0.f && c->cr >= 0.f && c->bde > -40.f;   // A + B < 1 + e^40 < 2^62
+    c->guard_lo = (c->guard_span != 0u && bounded) ? 0x1p-62f : __builtin_inff();
+  }
+  {
+    const StrictRegs sr;
+    c->exp_k1 = sr.exp_k1; c->exp_k252 = sr.exp_k252; c->l1p_c9 = sr.l1p_c9;
+    const float pc[2] = {c->cl, -c->cr}, pb[2] = {0.f, -c->bde};   // f32x2: low half first
+    memcpy(&c->well_c2, pc, 8);
+    memcpy(&c->well_b2, pb, 8);
+  }
   c->one = 1u;
   c->S = d->steps;
   c->Neq = d->eq_steps;

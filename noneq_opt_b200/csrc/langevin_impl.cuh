@@ -39,6 +39,12 @@
 
 namespace nq {
 
+// STRICT work increment: 0 = the reference's literal difference of two total energies (barrier_crossing.py:123-124),
+// 1 = the same quantity in closed form, (k_s/2)[(x-r_k)^2 - (x-r_{k-1})^2] = a_k x + b_k (the landscape term cancels
+// exactly), one rounding per step
+#ifndef NQ_STRICT_ALG_WORK
+#define NQ_STRICT_ALG_WORK 1
+#endif
 #ifndef NQ_LANGEVIN_UNROLL
 #define NQ_LANGEVIN_UNROLL 1
 #endif
@@ -53,6 +59,16 @@ constexpr int kTile = NQ_LANGEVIN_TILE;    // steps staged per shared-memory til
 constexpr int kThreads = NQ_LANGEVIN_THREADS;  // trajectories per CTA (small CTAs balance 1e5 trajectories over 148 SMs)
 constexpr int kCtaScale = 64 / kThreads;       // CTAs per 64 trajectories
 static_assert(kThreads == 32 || kThreads == 64, "32 or 64 trajectories per CTA");
+constexpr bool kAlgWork = NQ_STRICT_ALG_WORK != 0;
+#ifndef NQ_PACKED_GRAD   // STRICT gradient moments as FFMA2 pairs (bit-identical to the scalar FFMAs; fewer issue slots).
+// Not in FAST mode: measured 9.4e10 against 1.06e11 scalar -- ptxas shuffles the pairs through 25 extra moves per step there
+#define NQ_PACKED_GRAD 1
+#endif
+constexpr bool kPackedGrad = NQ_PACKED_GRAD != 0;
+#ifndef NQ_PACKED_LAND   // STRICT landscape: the two wells' squares, exponentials and force terms as f32x2 pairs
+#define NQ_PACKED_LAND 1
+#endif
+constexpr bool kPackedLand = NQ_PACKED_LAND != 0;
 // resident CTAs per SM the register budget is held to, so that config 2 (1563 CTAs of 64) is one wave
 // Resident CTAs per SM the kernels are compiled for (the register budget).  Measured at the config-5 shard size
 // (1.25e6 trajectories, static launch; gpurun_out/variants_r02m.log, 1e10 traj-steps/s STRICT / FAST):
@@ -86,6 +102,9 @@ struct LangevinConsts {
   // STRICT: width of the operand window [2^-62, 2^62) in which the division / logarithm of A + B take their
   // main paths (div_main, logf_main); 0 sends every step through the library functions (extreme 1 / beta)
   uint32_t guard_span;
+  f32x2 well_c2, well_b2;           // {cl, -cr} and {0, -bde}: the packed landscape's constant pairs (kPackedLand)
+  float exp_k1, exp_k252, l1p_c9;   // StrictRegs: register-held multiplicands of expf_main / log1pf_main
+  float guard_lo;   // 2^-62 when A + B is bounded above by construction (in_window_low), else +inf
   uint32_t one;   // = 1: multiplicand of the IMAD-form additions of the key chain (threefry2x32_inj)
   long long S, Neq;
 };
@@ -125,10 +144,23 @@ struct Landscape {
       ul = x;
       ur = fsub<FAST>(x, c.two_xm);
     }
+    if (!FAST && kPackedLand) {
+      // both wells side by side in FFMA2 / FMUL2 / FADD2 pairs {left, right}: every half is the scalar operation with
+      // the scalar rounding (the right well carries -cr and -bde: negation commutes with every rounding, so the pair
+      // holds a and -v bit for bit)
+      const f32x2 arg2 = f2_add(f2_mul(c.well_c2, f2_sq(f2_pack(ul, ur))), c.well_b2);
+      const f32x2 AB2 = expf_main2(arg2, c.exp_k1, c.exp_k252);
+      f2_unpack(AB2, A, B);
+      sAB = __fadd_rn(A, B);
+      g = div_main(-c.inv_beta, sAB);
+      lg = logf_main(sAB);
+      if (CHECKED && !in_window(c)) fix_range(c);
+      return;
+    }
     const float a = fmul<FAST>(c.cl, fmul<FAST>(ul, ul));
     const float v = fadd<FAST>(fmul<FAST>(c.cr, fmul<FAST>(ur, ur)), c.bde);
-    A = fexp<FAST>(a);
-    B = fexp<FAST>(-v);
+    A = FAST ? __expf(a) : expf_main(a, c.exp_k1, c.exp_k252);
+    B = FAST ? __expf(-v) : expf_main(-v, c.exp_k1, c.exp_k252);
     sAB = fadd<FAST>(A, B);
     if (!FAST) {
       // main paths, no branch (whichever of the two the caller does not use is dead code); callers patch
@@ -141,6 +173,10 @@ struct Landscape {
   // STRICT: A + B inside the operand window of div_main / logf_main?  (always true for SPRING)
   __device__ __forceinline__ bool in_window(const LangevinConsts& c) const {
     return POT == NQ_POT_SPRING || (__float_as_uint(sAB) - 0x20800000u) < c.guard_span;
+  }
+  // the same test as one float compare, for parameters whose A + B cannot exceed the window (guard_lo)
+  __device__ __forceinline__ bool in_window_low(const LangevinConsts& c) const {
+    return POT == NQ_POT_SPRING || sAB >= c.guard_lo;
   }
   __device__ __forceinline__ void fix_range(const LangevinConsts& c) {
     const float2 t = div_log_library(-c.inv_beta, sAB);
@@ -157,6 +193,12 @@ struct Landscape {
   // fewer per step.
   __device__ __forceinline__ float half_dEm(const LangevinConsts& c) const {
     if (POT == NQ_POT_SPRING) return 0.f;
+    if (!FAST && kPackedLand) {   // {ga, gb} -> {(ga cl) ul, ((-gb) cr) ur}, pairwise, then the one scalar add
+      const f32x2 t2 = f2_mul(f2_mul(f2_mul(f2_pack(g, g), f2_pack(A, B)), c.well_c2), f2_pack(ul, ur));
+      float ta, tb;
+      f2_unpack(t2, ta, tb);
+      return __fadd_rn(ta, tb);
+    }
     const float gq = FAST ? __fdividef(-c.inv_beta, sAB) : g;
     const float ga = fmul<FAST>(gq, A), gb = fmul<FAST>(gq, B);
     const float ta = fmul<FAST>(fmul<FAST>(ga, c.cl), ul);
@@ -465,6 +507,16 @@ __device__ __forceinline__ void tile_steps(StepCtx<POT, FAST, D>& s, long long t
   const LangevinConsts& c = s.c;
   const LangevinIO& io = s.io;
   float x = s.x, z = s.z, lp = s.lp, Wt = s.Wt, LPt = s.LPt;
+  // packed accumulator pairs (j, j + 1); the phi rows are zero-padded, so an odd D's spare half stays zero
+  constexpr int NP = GRAD ? (D + 1) / 2 : 1;
+  f32x2 gA2[NP], gB2[NP];
+  if (GRAD && kPackedGrad && !FAST) {
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      gA2[j] = f2_pack(s.gA[2 * j], 2 * j + 1 < D ? s.gA[2 * j + 1 < D ? 2 * j + 1 : 0] : 0.f);
+      gB2[j] = f2_pack(s.gB[2 * j], 2 * j + 1 < D ? s.gB[2 * j + 1 < D ? 2 * j + 1 : 0] : 0.f);
+    }
+  }
 #pragma unroll kUnroll
   for (int i = 0; i < len; ++i, r_addr += 4, phi_addr += 4 * DPS, tab_addr += 16) {
     if (RECORD && io.ckpt_x) {  // checkpoint BEFORE step k = t0+i when (k-1) % ckpt_every == 0
@@ -488,19 +540,28 @@ __device__ __forceinline__ void tile_steps(StepCtx<POT, FAST, D>& s, long long t
       // increment, mean -- no branch, so ptxas interleaves the three threefry blocks with the dependent
       // floating-point chains.  The two rare cases -- a draw in erf_inv's tail range (0.3 % of the lanes) and
       // A + B outside the main-path window (never, for physical parameters) -- are patched afterwards.
-      const float r_prev = lds_f32(r_addr), r_cur = lds_f32(r_addr + 4);
+      float r_prev, r_cur, wa, wb;
+      if (kAlgWork) {
+        const float4 tab = lds_f32x4(tab_addr);
+        r_cur = tab.x; wa = tab.y; wb = tab.z;
+      } else {
+        r_prev = lds_f32(r_addr);
+        r_cur = lds_f32(r_addr + 4);
+      }
       const float u = uniform_pm1_from_bits(s.rng.next());
-      const float w = erfinv_w<false>(u);
+      const float w = erfinv_w<false>(u, c.l1p_c9);
       z = __fmul_rn(1.41421356237309504880f, __fmul_rn(erfinv_poly_central<false>(w), u));
       asm volatile("" : "+f"(z));   // keep the central polynomial in the straight-line block (the compiler would sink it into the w < 5 arm)
       s.land.template eval<false>(c, x);
-      dW = work_increment<POT, FAST>(c, s.land, x, r_prev, r_cur);
+      dW = kAlgWork ? __fmaf_rn(wa, x, wb) : work_increment<POT, FAST>(c, s.land, x, r_prev, r_cur);
       float m2 = half_mean<POT, FAST>(c, s.land, x, r_cur);
-      if (!(w < 5.0f) || !s.land.in_window(c)) {
+      // ONE predicate for both rare cases: A + B <= 2 always (two exponentials of non-positive arguments), so only
+      // the lower edge of the main-path window can be missed and a float compare tests it (NaN -> patched)
+      if (!(w < 5.0f && s.land.in_window_low(c))) {
         if (!(w < 5.0f)) z = __fmul_rn(1.41421356237309504880f, __fmul_rn(erfinv_poly_tail<false>(w), u));
         if (!s.land.in_window(c)) {
           s.land.fix_range(c);
-          dW = work_increment<POT, FAST>(c, s.land, x, r_prev, r_cur);
+          if (!kAlgWork) dW = work_increment<POT, FAST>(c, s.land, x, r_prev, r_cur);
           m2 = half_mean<POT, FAST>(c, s.land, x, r_cur);
         }
       }
@@ -517,15 +578,33 @@ __device__ __forceinline__ void tile_steps(StepCtx<POT, FAST, D>& s, long long t
       // d W / d r_k = -k_s (x_{k-1} - r_k) + k_s (x_k - r_k) = k_s (x_k - x_{k-1}); that is k_s dR unless a
       // periodic shift wrapped the position
       const float a = z, b = PERIODIC ? x - x_before : dR;
+      if (kPackedGrad && !FAST) {   // two accumulators per FFMA2 (same roundings as 2 D scalar FFMAs)
+        const f32x2 a2 = f2_pack(a, a), b2 = f2_pack(b, b);
 #pragma unroll
-      for (int q = 0; q < DPS / 4; ++q) {
-        const float4 p = lds_f32x4(phi_addr + 16 * q);
-        const float pv[4] = {p.x, p.y, p.z, p.w};
+        for (int q = 0; q < DPS / 4; ++q) {
+          const float4 p = lds_f32x4(phi_addr + 16 * q);
+          if (4 * q < D) {
+            const f32x2 p01 = f2_pack(p.x, p.y);
+            gA2[2 * q] = f2_fma(a2, p01, gA2[2 * q]);
+            gB2[2 * q] = f2_fma(b2, p01, gB2[2 * q]);
+          }
+          if (4 * q + 2 < D) {
+            const f32x2 p23 = f2_pack(p.z, p.w);
+            gA2[2 * q + 1] = f2_fma(a2, p23, gA2[2 * q + 1]);
+            gB2[2 * q + 1] = f2_fma(b2, p23, gB2[2 * q + 1]);
+          }
+        }
+      } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (4 * q + e < D) {
-            s.gA[4 * q + e] = fmaf(a, pv[e], s.gA[4 * q + e]);
-            s.gB[4 * q + e] = fmaf(b, pv[e], s.gB[4 * q + e]);
+        for (int q = 0; q < DPS / 4; ++q) {
+          const float4 p = lds_f32x4(phi_addr + 16 * q);
+          const float pv[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (4 * q + e < D) {
+              s.gA[4 * q + e] = fmaf(a, pv[e], s.gA[4 * q + e]);
+              s.gB[4 * q + e] = fmaf(b, pv[e], s.gB[4 * q + e]);
+            }
           }
         }
       }
@@ -537,6 +616,18 @@ __device__ __forceinline__ void tile_steps(StepCtx<POT, FAST, D>& s, long long t
       if (io.positions && (k % io.pos_stride) == 0) io.positions[(k / io.pos_stride) * io.n + s.gid] = x;
     }
   }
+  if (GRAD && kPackedGrad && !FAST) {
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      float lo, hi;
+      f2_unpack(gA2[j], lo, hi);
+      s.gA[2 * j] = lo;
+      if (2 * j + 1 < D) s.gA[2 * j + 1 < D ? 2 * j + 1 : 0] = hi;
+      f2_unpack(gB2[j], lo, hi);
+      s.gB[2 * j] = lo;
+      if (2 * j + 1 < D) s.gB[2 * j + 1 < D ? 2 * j + 1 : 0] = hi;
+    }
+  }
   s.x = x; s.z = z; s.lp = lp; s.Wt = Wt; s.LPt = LPt;
 }
 
@@ -546,16 +637,25 @@ __device__ __forceinline__ void tile_steps(StepCtx<POT, FAST, D>& s, long long t
 __device__ __forceinline__ void pin_constants(LangevinConsts& c) {
   // (an empty inline asm vanishes before ptxas and a shuffle of a warp-uniform value is folded away; a round
   // trip through shared memory with a volatile load is opaque -- 11 loads per chunk of >= 128 steps)
-  __shared__ float pin_s[12];
-  float* f[11] = {&c.hk, &c.inv_beta, &c.cl, &c.cr, &c.bde, &c.xm, &c.two_xm, &c.nu, &c.dt, &c.sigma, &c.log_norm};
+  constexpr int N = 14;
+  __shared__ float pin_s[N];
+  float* f[N] = {&c.hk, &c.inv_beta, &c.cl, &c.cr, &c.bde, &c.xm, &c.two_xm, &c.nu, &c.dt, &c.sigma, &c.log_norm,
+                 &c.exp_k1, &c.exp_k252, &c.l1p_c9};
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int i = 0; i < 11; ++i) pin_s[i] = *f[i];
+    for (int i = 0; i < N; ++i) pin_s[i] = *f[i];
   }
   __syncthreads();
   const uint32_t base = (uint32_t)__cvta_generic_to_shared(pin_s);
 #pragma unroll
-  for (int i = 0; i < 11; ++i) *f[i] = lds_f32(base + 4 * i);
+  for (int i = 0; i < N; ++i) *f[i] = lds_f32(base + 4 * i);
+  // the constant pairs, re-read as 64-bit words so that they arrive in (and keep) aligned register pairs
+  __shared__ __align__(8) f32x2 pin2_s[2];
+  if (threadIdx.x == 0) { pin2_s[0] = c.well_c2; pin2_s[1] = c.well_b2; }
+  __syncthreads();
+  const uint32_t base2 = (uint32_t)__cvta_generic_to_shared(pin2_s);
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(c.well_c2) : "r"(base2));
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(c.well_b2) : "r"(base2 + 8));
 }
 
 template <int POT, bool FAST, int D, bool RECORD, bool PIN = false>
@@ -568,7 +668,7 @@ __device__ __forceinline__ void langevin_chunk(const LangevinConsts& c_in, const
   constexpr int DA = GRAD ? D : 1;            // accumulators per term
   constexpr int DPS = GRAD ? pad4(D) : 4;     // padded row length in shared memory
   __shared__ float r_s[kTile + 1];
-  __shared__ __align__(16) float4 tab_s[FAST ? kTile : 1];  // FAST: (r_k, a_k, b_k, -) with dW_k = a_k x + b_k
+  __shared__ __align__(16) float4 tab_s[(FAST || kAlgWork) ? kTile : 1];  // FAST: (r_k, a_k, b_k, -) with dW_k = a_k x + b_k
   __shared__ __align__(16) float phi_s[GRAD ? kTile * DPS : 4];
   __shared__ double red_s[kThreads / 32][8 + 2 * DPS];
 
@@ -624,7 +724,7 @@ __device__ __forceinline__ void langevin_chunk(const LangevinConsts& c_in, const
     __syncthreads();
     NQ_DBG_ASSERT(t0 >= 1 && t0 - 1 + len <= c.S && len >= 1 && len <= kTile);
     for (int i = threadIdx.x; i <= len; i += kThreads) r_s[i] = io.r_table[t0 - 1 + i];
-    if (FAST) {
+    if (FAST || kAlgWork) {
       // dW_k = (k_s/2)[(x-r_k)^2 - (x-r_{k-1})^2] = a_k x + b_k,  a_k = k_s (r_{k-1} - r_k),  b_k = -a_k (r_{k-1} + r_k)/2
       for (int i = threadIdx.x; i < len; i += kThreads) {
         const float r0 = io.r_table[t0 - 1 + i], r1 = io.r_table[t0 + i];
@@ -778,7 +878,7 @@ __global__ void __launch_bounds__(kPairThreads) langevin_pair_kernel(const Lange
   __shared__ uint32_t key_ring_s[2][kRingHalf][2][32];
   __shared__ long long ring_tag_s[kDebugChecks ? 2 * kRingHalf : 1];   // debug: global step index held by each ring slot
   __shared__ float r_s[kTile + 1];
-  __shared__ __align__(16) float4 tab_s[FAST ? kTile : 1];
+  __shared__ __align__(16) float4 tab_s[(FAST || kAlgWork) ? kTile : 1];
   __shared__ __align__(16) float phi_s[GRAD ? kTile * DPS : 4];
 
   const int lane = threadIdx.x & 31;
@@ -894,7 +994,7 @@ __global__ void __launch_bounds__(kPairThreads) langevin_pair_kernel(const Lange
     const int len = (int)min((long long)kTile, c.S - t0 + 1);
     __syncwarp();
     for (int i = lane; i <= len; i += 32) r_s[i] = io.r_table[t0 - 1 + i];
-    if (FAST) {
+    if (FAST || kAlgWork) {
       for (int i = lane; i < len; i += 32) {
         const float r0 = io.r_table[t0 - 1 + i], r1 = io.r_table[t0 + i];
         const float a = 2.0f * c.hk * (r0 - r1);
@@ -922,9 +1022,16 @@ __global__ void __launch_bounds__(kPairThreads) langevin_pair_kernel(const Lange
         z = next_z();
         dR = fast_step_z<POT>(c, x, z, tab.x);
       } else {
-        const float r_prev = lds_f32(r_addr), r_cur = lds_f32(r_addr + 4);
+        float r_cur;
         land.eval(c, x);
-        dW = work_increment<POT, FAST>(c, land, x, r_prev, r_cur);
+        if (kAlgWork) {
+          const float4 tab = lds_f32x4(tab_addr);
+          r_cur = tab.x;
+          dW = __fmaf_rn(tab.y, x, tab.z);
+        } else {
+          r_cur = lds_f32(r_addr + 4);
+          dW = work_increment<POT, FAST>(c, land, x, lds_f32(r_addr), r_cur);
+        }
         dR = brownian_apply_any<POT, FAST>(c, land, x, next_z(), r_cur, z, lp);
       }
       Wt += dW;

@@ -47,3 +47,16 @@ def test_normal_draw_is_the_literal_jax_formula_for_every_mantissa(cuda):
   # jax.random.normal uses the top 23 bits of the word: all 2^23 patterns
   bad, where = _check(3, 0, 1 << 23)
   assert bad == 0, f'{bad} mismatches, first at pattern {where:#x}'
+
+
+def test_expf_main_is_expf_on_every_float(cuda):
+  # the landscape's exponents are non-positive, but the sequence is libdevice's whole expf: all 2^32 patterns
+  # (NaN payloads included -- both return the same quiet NaN)
+  bad, where = _check(4, 0, 1 << 32)
+  assert bad == 0, f'{bad} mismatches, first at pattern {where:#x}'
+
+
+def test_packed_expf_pair_is_expf_in_both_halves(cuda):
+  # expf_main2 (FFMA2 / FADD2 / FMUL2 on a register pair): {exp(x), exp(-x)} for every float x
+  bad, where = _check(5, 0, 1 << 32)
+  assert bad == 0, f'{bad} mismatches, first at pattern {where:#x}'
