@@ -96,6 +96,13 @@ typedef struct NqLangevinDesc {
 
 size_t nq_langevin_workspace_bytes(int64_t n, int32_t D);
 
+/* Builds the per-device normal-draw table of the STRICT kernels (jax.random.normal, jax/_src/random.py _normal_real:
+ * sqrt(2) erf_inv(uniform(-1, 1)), reads 23 bits of each random word; the table holds its value for all 2^23
+ * patterns, 32 MB, computed on the device by the same code the other kernels evaluate per draw).  Every STRICT
+ * Langevin entry point builds it on first use; call this explicitly before CAPTURING such calls in a CUDA graph
+ * (the build allocates and synchronises `stream`, which capture forbids).  Idempotent. */
+int nq_langevin_prepare(void* stream);
+
 /* run_brownian_opt (barrier_crossing.py:97-143) for n trajectories, given the trap table
  * r_table[S+1] (MakeSchedule_chebyshev :145-151, built by the host) and the per-trajectory
  * seeds (rows of jax.random.split(seed, B), :221).  The kernel performs the

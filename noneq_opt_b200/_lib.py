@@ -56,6 +56,7 @@ SIGNATURES = {
     'nq_random_uniform': (C.c_int, [_KEY, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_float, _P, _P]),
     'nq_random_normal': (C.c_int, [_KEY, C.c_int64, C.c_int64, C.c_int64, _P, _P]),
     'nq_langevin_workspace_bytes': (C.c_size_t, [C.c_int64, C.c_int32]),
+    'nq_langevin_prepare': (C.c_int, [_P]),
     'nq_langevin_forward': (C.c_int, [C.POINTER(NqLangevinDesc), _P, _P, _P, C.c_int64, _P, _P, _P,
                                       _P, C.c_int64, _P, _P, _P, _P, C.c_size_t, _P]),
     'nq_langevin_grad': (C.c_int, [C.POINTER(NqLangevinDesc), _P, _P, C.c_int32, _P, _P, C.c_int64,

@@ -849,6 +849,227 @@ static bool fast3d_ok(int ndim, const int* dims) {
          getenv("NQ_ISING_NO_FAST3D") == nullptr;
 }
 
+// ------------------------------------------------------------------------------ bit-packed 1-D kernel
+// Periodic chains of N sites with N % 4 == 0 (the reference's own 1-D test shape is 10 000, tests/ising_test.py:71;
+// sum_neighbors / even_odd_masks are rank-generic, ising.py:75-106).  Same design as the 2-D / 3-D kernels: two colour
+// planes in shared memory (colour 0 = odd sites, the reference's "even" mask, updated first), bit-sliced neighbour
+// counts, integer thresholds through the nibble tables, class histograms by popc, 2 x 3 site classes.  jax's counter
+// pairing (p, p + N/2) joins two sites of the same colour because N/2 is even; to make the partner a whole word away
+// whatever N is, each colour plane is stored as two HALVES of Ph = N/4 sites, each padded to Wh = ceil(Ph / 32) words
+// (padding bits stay zero): site j = h Ph + k of a colour is bit k % 32 of word h Wh + k / 32, and ONE threefry block
+// (p, p + N/2) serves bit k of both halves -- half a block per spin-update here too.  Only the two half ends need
+// care: the neighbour of a half's last site is bit 0 of the other half (the chain closes through them).
+struct Shape1 {
+  int Ph, Wh, tail;   // sites per half, words per half, Ph % 32 (0 = the last word is full)
+};
+
+// colour plane c: words [c][h][w]; neighbour planes of word w of half h
+__device__ __forceinline__ void load_planes1(const uint32_t* lat, const Shape1& g, int c, int h, int w, Planes& p) {
+  const uint32_t* own = lat + (size_t)c * 2 * g.Wh;
+  const uint32_t* oth = lat + (size_t)(1 - c) * 2 * g.Wh;
+  const uint32_t X = oth[h * g.Wh + w];
+  const bool last = w == g.Wh - 1;
+  uint32_t Xs;
+  if (c == 0) {   // odd site p = 2 j + 1: neighbours are the even sites j and j + 1
+    const uint32_t NX = last ? oth[(1 - h) * g.Wh] : oth[h * g.Wh + w + 1];
+    Xs = (last && g.tail) ? ((X >> 1) | ((NX & 1u) << (g.tail - 1))) : __funnelshift_r(X, NX, 1);
+  } else {        // even site p = 2 j: neighbours are the odd sites j and j - 1
+    const uint32_t prev = w > 0 ? oth[h * g.Wh + w - 1] >> 31
+                                : (oth[(1 - h) * g.Wh + g.Wh - 1] >> ((g.tail ? g.tail : 32) - 1)) & 1u;
+    Xs = (X << 1) | prev;
+  }
+  p.S = own[h * g.Wh + w];
+  p.C0 = X ^ Xs;
+  p.C1 = X & Xs;
+  p.C2 = 0u;
+}
+
+// per-class popcounts over the valid bits, 3 neighbour counts per spin value: h[k] spin down, h[3 + k] spin up
+__device__ __forceinline__ void histogram3(const Planes& p, uint32_t F, uint32_t valid, int (&hA)[6], int (&hF)[6]) {
+  const uint32_t E[3] = {~p.C1 & ~p.C0 & valid, p.C0 & valid, p.C1 & valid};   // C1 and C0 are never both set
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const uint32_t up = E[k] & p.S, down = E[k] & ~p.S;
+    hA[k] += __popc(down);
+    hA[3 + k] += __popc(up);
+    hF[k] += __popc(down & F);
+    hF[3 + k] += __popc(up & F);
+  }
+}
+
+// word w of both halves of colour c: 32 threefry blocks, up to 64 site updates
+__device__ __forceinline__ void update_unit1(uint32_t* lat, const Shape1& g, const uint32_t* spread, const uint2* thr2,
+                                             const KeySchedule& ks, uint32_t one, int c, int w, int (&hA)[6],
+                                             int (&hF)[6]) {
+  Planes pa, pb;
+  load_planes1(lat, g, c, 0, w, pa);
+  load_planes1(lat, g, c, 1, w, pb);
+  const uint32_t valid = (w == g.Wh - 1 && g.tail) ? ((1u << g.tail) - 1u) : 0xffffffffu;
+  const uint32_t cbase = 2u * (32u * w) + (c == 0 ? 1u : 0u);   // site of bit 0 of the half-0 word
+  const uint32_t half = 4u * (uint32_t)g.Ph / 2u;              // N / 2
+  uint32_t Fa = 0, Fb = 0;
+#pragma unroll 1
+  for (int q = 3; q >= 0; --q) {
+    const uint32_t Na = class_nibbles(spread, pa, q), Nb = class_nibbles(spread, pb, q);
+#pragma unroll
+    for (int jj = 3; jj >= 0; --jj) {
+      const uint2 ta = thr_pair(thr2, Na, jj), tb = thr_pair(thr2, Nb, jj);
+#pragma unroll
+      for (int e = 1; e >= 0; --e) {
+        const uint32_t ctr = cbase + 2u * (8u * q + 2u * jj + e);
+        uint32_t y0, y1;
+        threefry2x32_allmad(ks, ctr, ctr + half, y0, y1, one);
+        const uint32_t da = (y0 >> 9) - (e ? ta.y : ta.x);
+        const uint32_t db = (y1 >> 9) - (e ? tb.y : tb.x);
+        Fa = __funnelshift_l(da, Fa, 1);
+        Fb = __funnelshift_l(db, Fb, 1);
+      }
+    }
+  }
+  Fa &= valid;   // the padding bits of a half's last word are not sites
+  Fb &= valid;
+  uint32_t* own = lat + (size_t)c * 2 * g.Wh;
+  own[w] = pa.S ^ Fa;
+  own[g.Wh + w] = pb.S ^ Fb;
+  histogram3(pa, Fa, valid, hA, hF);
+  histogram3(pb, Fb, valid, hA, hF);
+}
+
+// (plane word, bit) of site p
+__device__ __forceinline__ void locate1(const Shape1& g, int p, int& word, int& bit) {
+  const int c = (p & 1) ? 0 : 1, j = p >> 1, h = j >= g.Ph ? 1 : 0, k = j - h * g.Ph;
+  word = (c * 2 + h) * g.Wh + (k >> 5);
+  bit = k & 31;
+}
+// colour planes -> 32 consecutive sites starting at 32 W (row-major external layout)
+__device__ __forceinline__ uint32_t gather_word1(const uint32_t* lat, const Shape1& g, int W, int N) {
+  uint32_t out = 0;
+  for (int b = 0; b < 32 && 32 * W + b < N; ++b) {
+    int word, bit;
+    locate1(g, 32 * W + b, word, bit);
+    out |= ((lat[word] >> bit) & 1u) << b;
+  }
+  return out;
+}
+
+// Shared memory: spread[4][256] | lattice[2][2][Wh] | pair thresholds[2][256] (uint2) | hist[2][2][2][16] | 2 ints
+__global__ void __launch_bounds__(1024, 1) ising_fast1d_kernel(const IsingShape sh, const IsingIO io) {
+  extern __shared__ uint32_t smem[];
+  const int N = sh.N, T = sh.T;
+  const Shape1 g{N / 4, (N / 4 + 31) / 32, (N / 4) % 32};
+  const int plane_words = 2 * g.Wh;
+  uint32_t* spread = smem;
+  uint32_t* lat = smem + 4 * 256;
+  uint2* thr_s = reinterpret_cast<uint2*>(lat + 2 * plane_words);
+  int* hist_s = reinterpret_cast<int*>(lat + 2 * plane_words + 2 * 256 * 2);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x, tsize = blockDim.x;
+  const long long rep = blockIdx.x;
+  const int ext_words = (N + 31) / 32;
+
+  for (int v = tid; v < 4 * 256; v += tsize) spread[v] = spread8_to_nibbles(v & 255) << (v >> 8);
+  for (int v = tid; v < 2 * 2 * 2 * kIsingClasses + 2; v += tsize) hist_s[v] = 0;
+  // ---- load the chain (row-major bits -> halved colour planes, zero padding)
+  const uint32_t* ext0 = io.spins0 + (sh.broadcast0 ? 0 : rep * (size_t)ext_words);
+  for (int u = tid; u < 2 * plane_words; u += tsize) {
+    const int c = u / plane_words, hw = u - c * plane_words, h = hw / g.Wh, w = hw - h * g.Wh;
+    uint32_t word = 0;
+    for (int b = 0; b < 32; ++b) {
+      const int k = 32 * w + b;
+      if (k >= g.Ph) break;
+      const int p = 2 * (h * g.Ph + k) + (c == 0 ? 1 : 0);
+      word |= ((ext0[p >> 5] >> (p & 31)) & 1u) << b;
+    }
+    lat[u] = word;
+  }
+  if (T > 1) build_pair_table(thr_s + 256, io.thr, tid, tsize);   // sweep t = 1 -> parity buffer 1
+  __syncthreads();
+
+  // ---- initial spin sum M and bond sum B (each bond joins an odd and an even site)
+  long long M, B;
+  {
+    int hA[6], hF[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) hA[k] = hF[k] = 0;
+    int up = 0;
+    for (int u = tid; u < plane_words; u += tsize) {
+      const int h = u / g.Wh, w = u - h * g.Wh;
+      const uint32_t valid = (w == g.Wh - 1 && g.tail) ? ((1u << g.tail) - 1u) : 0xffffffffu;
+      Planes p;
+      load_planes1(lat, g, 0, h, w, p);
+      histogram3(p, 0u, valid, hA, hF);
+      up += __popc(lat[u]) + __popc(lat[plane_words + u]);
+    }
+    int b = 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) b += (k >= 3 ? 1 : -1) * (2 * (k % 3) - 2) * hA[k];
+    up = __reduce_add_sync(0xffffffffu, up);
+    b = __reduce_add_sync(0xffffffffu, b);
+    int* tmp = hist_s + 2 * 2 * 2 * kIsingClasses;
+    if (lane == 0) { atomicAdd(&tmp[0], up); atomicAdd(&tmp[1], b); }
+    __syncthreads();
+    M = 2ll * tmp[0] - (long long)N;
+    B = tmp[1];
+  }
+
+  const KeySchedule ks_rep = key_schedule(io.seeds[2 * rep], io.seeds[2 * rep + 1]);
+  for (int t = 1; t < T; ++t) {
+    KeySchedule kh[2];
+    sweep_keys(ks_rep, t, T, sh.direct_keys != 0, kh[0], kh[1]);
+    const uint2* thr_cur = thr_s + (t & 1) * 256;
+    if (t + 1 < T) build_pair_table(thr_s + ((t + 1) & 1) * 256, io.thr + (size_t)t * kIsingClasses, tid, tsize);
+    for (int c = 0; c < 2; ++c) {
+      int hA[6], hF[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) hA[k] = hF[k] = 0;
+      for (int w = tid; w < g.Wh; w += tsize) update_unit1(lat, g, spread, thr_cur, kh[c], sh.one, c, w, hA, hF);
+      int* hs = hist_s + ((t & 1) * 2 + c) * 2 * kIsingClasses;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const int a = __reduce_add_sync(0xffffffffu, hA[k]), f = __reduce_add_sync(0xffffffffu, hF[k]);
+        if (lane == 0) {
+          if (a) atomicAdd(&hs[k], a);
+          if (f) atomicAdd(&hs[kIsingClasses + k], f);
+        }
+      }
+      __syncthreads();
+    }
+    if (io.states) {  // return_states=True: the chain after this sweep, row-major bits
+      uint32_t* dst = io.states + ((size_t)rep * (T - 1) + (t - 1)) * ext_words;
+      for (int W = tid; W < ext_words; W += tsize) dst[W] = gather_word1(lat, g, W, N);
+    }
+    if (warp == 0) {
+      int a2[2], f2[2];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        int* hs = hist_s + ((t & 1) * 2 + c) * 2 * kIsingClasses;
+        a2[c] = lane < 6 ? hs[lane] : 0;
+        f2[c] = lane < 6 ? hs[kIsingClasses + lane] : 0;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        int* hs = hist_s + ((t & 1) * 2 + c) * 2 * kIsingClasses;
+        if (lane < 6) { hs[lane] = 0; hs[kIsingClasses + lane] = 0; }
+      }
+      emit_summary(a2, f2, io, sh, rep, t, M, B, lane);
+    }
+    __syncthreads();   // (states written, histograms of this parity cleared before they are used again)
+  }
+  if (io.spins_out) {
+    uint32_t* dst = io.spins_out + (size_t)rep * ext_words;
+    for (int W = tid; W < ext_words; W += tsize) dst[W] = gather_word1(lat, g, W, N);
+  }
+}
+
+static size_t fast1d_smem_bytes(long long N) {
+  const size_t Wh = (size_t)((N / 4 + 31) / 32);
+  return (4 * 256 + 4 * Wh + 2 * 256 * 2 + 2 * 2 * 2 * kIsingClasses + 2) * 4;
+}
+static bool fast1d_ok(int ndim, const int* dims) {
+  return ndim == 1 && dims[0] % 4 == 0 && dims[0] >= 8 && fast1d_smem_bytes(dims[0]) <= 227 * 1024 &&
+         getenv("NQ_ISING_NO_FAST1D") == nullptr;
+}
+
 // ------------------------------------------------------------------------------ generic kernel
 // Any even-sided 1-D / 2-D / 3-D periodic lattice (the reference's tests use 10000, 256x256 and
 // 64^3): one CTA per replica, one spin per byte in shared memory (or in a global scratch when the
@@ -1295,6 +1516,7 @@ extern "C" size_t nq_ising_workspace_bytes(const NqIsingDesc* desc) {
     return (size_t)desc->R * 2 * dims[0] * (dims[0] / 64) * 4;   // colour planes in global memory
   }
   if (fast3d_ok(ndim, dims)) return 0;   // bit-packed 3-D kernel: lattice in shared memory
+  if (fast1d_ok(ndim, dims)) return 0;   // bit-packed 1-D kernel: chain in shared memory
   if (generic_smem_bytes(N) <= 200 * 1024) return 0;
   return (size_t)desc->R * N;
 }
@@ -1377,6 +1599,12 @@ extern "C" int nq_ising_run(const NqIsingDesc* desc, const uint32_t* thr, const 
     const int threads = units >= 1024 ? 1024 : ((units + 31) / 32) * 32;
     NQ_CUDA(cudaFuncSetAttribute(ising_fast3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ising_fast3d_kernel<<<(unsigned)desc->R, threads, smem, st>>>(sh, io);
+  } else if (fast1d_ok(ndim, dims)) {
+    const size_t smem = fast1d_smem_bytes(N);
+    const int units = (int)((N / 4 + 31) / 32);
+    const int threads = units >= 1024 ? 1024 : ((units + 31) / 32) * 32;
+    NQ_CUDA(cudaFuncSetAttribute(ising_fast1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ising_fast1d_kernel<<<(unsigned)desc->R, threads, smem, st>>>(sh, io);
   } else {
     size_t smem = generic_smem_bytes(N);
     if (smem > 200 * 1024) {   // spins live in the caller's workspace (L2-resident), tables stay in shared memory

@@ -2,6 +2,7 @@
 // (float32, reference operation order), argument checks, kernel dispatch, deterministic final
 // reduction.  Kernels: langevin_impl.cuh.
 #include <cstring>
+#include <mutex>
 #include <stdlib.h>
 
 #include "langevin_impl.cuh"
@@ -151,8 +152,8 @@ static long long chunk_steps(bool fast) {
 }
 static long long persistent_ctas_per_sm(bool fast, long long n) {
   const char* env = getenv("NQ_PERSISTENT_PER_SM");
-  // STRICT: 8 CTAs of 64 per SM up to ~880 trajectories per SM (config 2 is 676), 10 beyond; FAST: 6
-  return env ? atoll(env) : kCtaScale * (fast ? 6 : (n <= 880ll * sm_count() ? 8 : 10));
+  // 8 CTAs of 64 per SM (FAST: always; r02w: 1.03e11 against 1.00e11 at 6); STRICT beyond ~880 trajectories per SM: 10
+  return env ? atoll(env) : kCtaScale * ((fast || n <= 880ll * sm_count()) ? 8 : 10);
 }
 static bool use_persistent(long long n, long long S, bool record, bool fast) {
   if (record || S < 2 * chunk_steps(fast)) return false;
@@ -183,6 +184,8 @@ static size_t persistent_bytes(long long n, int D) {
   (void)n_chunks_max;
   return align256((size_t)state_words(kernel_D(D)) * groups * kThreads * 4) + align256((size_t)(groups + 4) * 4);
 }
+
+static int normal_table(cudaStream_t st, const float** out);
 
 static int run(const NqLangevinDesc* desc, const LangevinIO& io_in, double* moments, double* grad_sums,
                void* workspace, size_t workspace_bytes, cudaStream_t st) {
@@ -224,6 +227,10 @@ static int run(const NqLangevinDesc* desc, const LangevinIO& io_in, double* mome
     return NQ_ERR_WORKSPACE;
   }
   io.partials = (double*)workspace;
+  if (fast ? kNormalTableFast : kNormalTable) {
+    rc = normal_table(st, &io.ztable);
+    if (rc != NQ_OK) return rc;
+  }
   const unsigned int* status = nullptr;
   if (record) NQ_CHECK_ARG(io.D == 0, "per-step recording is only available on the forward entry points");
   if (io.positions) NQ_CHECK_ARG(io.pos_stride >= 1, "pos_stride must be >= 1");
@@ -276,6 +283,46 @@ static int run(const NqLangevinDesc* desc, const LangevinIO& io_in, double* mome
   return NQ_OK;
 }
 
+// ---- the normal-draw table of the STRICT hot loops
+// z[p] = normal_from_bits<false>(p << 9) for the 2^23 patterns jax.random.normal distinguishes: 32 MB, built once per
+// device by the same device function the kernels used to call per step, so a lookup returns the same bits.  The table
+// lives for the life of the process (like a cuBLAS workspace); it is the one allocation the library makes.
+constexpr long long kNormalTableSize = 1ll << 23;
+__global__ void __launch_bounds__(256) normal_table_kernel(float* table) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < kNormalTableSize) table[p] = normal_from_bits<false>((uint32_t)p << 9);
+}
+static int normal_table(cudaStream_t st, const float** out) {
+  static std::mutex mu;
+  static float* tables[64] = {};
+  int dev = 0;
+  NQ_CUDA(cudaGetDevice(&dev));
+  NQ_CHECK_ARG(dev >= 0 && dev < 64, "device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lock(mu);
+  if (tables[dev] == nullptr) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    NQ_CUDA(cudaStreamIsCapturing(st, &cap));
+    if (cap != cudaStreamCaptureStatusNone) {
+      set_error("the normal-draw table of this device does not exist yet and cannot be built during stream capture: "
+                "call nq_langevin_prepare() (or run one STRICT Langevin call) before capturing");
+      return NQ_ERR_UNSUPPORTED;
+    }
+    float* t = nullptr;
+    NQ_CUDA(cudaMalloc(&t, kNormalTableSize * sizeof(float)));
+    normal_table_kernel<<<(unsigned)(kNormalTableSize / 256), 256, 0, st>>>(t);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // complete before any other stream can use it
+    if (e != cudaSuccess) {
+      cudaFree(t);
+      return cuda_fail(e, "normal table build");
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    tables[dev] = t;
+  }
+  *out = tables[dev];
+  return NQ_OK;
+}
+
 __global__ void zero_doubles_kernel(double* p, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = 0.0;
@@ -284,6 +331,12 @@ __global__ void zero_doubles_kernel(double* p, long long n) {
 }  // namespace nq
 
 using namespace nq;
+
+extern "C" int nq_langevin_prepare(void* stream) {
+  NQ_RANGE();
+  const float* t = nullptr;
+  return kNormalTable ? normal_table((cudaStream_t)stream, &t) : NQ_OK;
+}
 
 extern "C" size_t nq_langevin_workspace_bytes(int64_t n, int32_t D) {
   if (n < 1) n = 1;

@@ -31,8 +31,8 @@
 #ifndef NQ_FAST_RCP
 #define NQ_FAST_RCP 0
 #endif
-#ifndef NQ_FAST_NORMAL
-#define NQ_FAST_NORMAL 0
+#ifndef NQ_FAST_NORMAL   // 1: FAST draws are the exact jax.random.normal values (the hot loops read them from the table,
+#define NQ_FAST_NORMAL 1  // the other kernels compute them), 0: the MUFU approximation of round 1 outside the hot loops
 #endif
 
 #include "nq_common.cuh"
@@ -65,6 +65,14 @@ constexpr bool kAlgWork = NQ_STRICT_ALG_WORK != 0;
 #define NQ_PACKED_GRAD 1
 #endif
 constexpr bool kPackedGrad = NQ_PACKED_GRAD != 0;
+#ifndef NQ_NORMAL_TABLE   // STRICT hot loops: the normal draw as one load from the device-wide 2^23-entry table
+#define NQ_NORMAL_TABLE 1
+#endif
+constexpr bool kNormalTable = NQ_NORMAL_TABLE != 0;
+#ifndef NQ_NORMAL_TABLE_FAST   // FAST hot loops too: the table holds the exact draw, so FAST keeps only its landscape approximations
+#define NQ_NORMAL_TABLE_FAST 1
+#endif
+constexpr bool kNormalTableFast = kNormalTable && NQ_NORMAL_TABLE_FAST != 0;
 #ifndef NQ_PACKED_LAND   // STRICT landscape: the two wells' squares, exponentials and force terms as f32x2 pairs
 #define NQ_PACKED_LAND 1
 #endif
@@ -446,6 +454,7 @@ __device__ __forceinline__ float fast_step(const LangevinConsts& c, float& x, ui
 // ------------------------------------------------------------------------------ main kernel
 struct LangevinIO {
   const float* r_table;  // [S+1]
+  const float* ztable;   // [2^23] normal draw of every 23-bit pattern (library-owned, see normal_table()); STRICT only
   const float* phi;      // [S-1][D] or null
   const float* x0;       // [n]
   const uint32_t* seeds; // [n][2]
@@ -533,7 +542,12 @@ __device__ __forceinline__ void tile_steps(StepCtx<POT, FAST, D>& s, long long t
     if (FAST) {
       const float4 tab = lds_f32x4(tab_addr);
       dW = fmaf(tab.y, x, tab.z);
-      dR = fast_step<POT, PERIODIC ? 1 : 0>(c, x, s.rng.next(), tab.x, z);
+      if (kNormalTableFast) {   // the exact jax draw from the table instead of the MUFU approximation of it
+        z = __ldg(io.ztable + (s.rng.next() >> 9));
+        dR = fast_step_z<POT, PERIODIC ? 1 : 0>(c, x, z, tab.x);
+      } else {
+        dR = fast_step<POT, PERIODIC ? 1 : 0>(c, x, s.rng.next(), tab.x, z);
+      }
       if (RECORD) lp = fmaf(-0.5f * z, z, -c.log_norm);
     } else {
       // One straight-line block: key chain, central-range normal draw, landscape on the main paths, work
@@ -548,18 +562,29 @@ __device__ __forceinline__ void tile_steps(StepCtx<POT, FAST, D>& s, long long t
         r_prev = lds_f32(r_addr);
         r_cur = lds_f32(r_addr + 4);
       }
-      const float u = uniform_pm1_from_bits(s.rng.next());
-      const float w = erfinv_w<false>(u, c.l1p_c9);
-      z = __fmul_rn(1.41421356237309504880f, __fmul_rn(erfinv_poly_central<false>(w), u));
-      asm volatile("" : "+f"(z));   // keep the central polynomial in the straight-line block (the compiler would sink it into the w < 5 arm)
+      float u = 0.f, w = 0.f;
+      if (kNormalTable) {
+        // jax.random.normal reads only the top 23 bits of the word (Appendix A.5), so the whole draw -- uniform,
+        // log1p, both erf_inv ranges, sqrt(2) -- is a function of 2^23 patterns: one load from the 32 MB table the
+        // library builds once per device with normal_from_bits<false> itself (L2-resident on B200).
+        // Same bits as computing it; ~36 issue slots and the tail-range branch fewer per step.
+        z = __ldg(io.ztable + (s.rng.next() >> 9));
+      } else {
+        u = uniform_pm1_from_bits(s.rng.next());
+        w = erfinv_w<false>(u, c.l1p_c9);
+        z = __fmul_rn(1.41421356237309504880f, __fmul_rn(erfinv_poly_central<false>(w), u));
+        asm volatile("" : "+f"(z));   // keep the central polynomial in the straight-line block (the compiler would sink it into the w < 5 arm)
+      }
       s.land.template eval<false>(c, x);
       dW = kAlgWork ? __fmaf_rn(wa, x, wb) : work_increment<POT, FAST>(c, s.land, x, r_prev, r_cur);
       float m2 = half_mean<POT, FAST>(c, s.land, x, r_cur);
-      // ONE predicate for both rare cases: A + B <= 2 always (two exponentials of non-positive arguments), so only
+      // ONE predicate for the rare cases: A + B <= 2 always (two exponentials of non-positive arguments), so only
       // the lower edge of the main-path window can be missed and a float compare tests it (NaN -> patched)
-      if (!(w < 5.0f && s.land.in_window_low(c))) {
-        if (!(w < 5.0f)) z = __fmul_rn(1.41421356237309504880f, __fmul_rn(erfinv_poly_tail<false>(w), u));
-        if (!s.land.in_window(c)) {
+      if (!((kNormalTable || w < 5.0f) && s.land.in_window_low(c))) {
+        if (!kNormalTable && !(w < 5.0f)) z = __fmul_rn(1.41421356237309504880f, __fmul_rn(erfinv_poly_tail<false>(w), u));
+        // with the table the predicate is the window test itself: no second test (where guard_lo is +inf every
+        // step comes here, and the library division / logarithm are right everywhere)
+        if (kNormalTable || !s.land.in_window(c)) {
           s.land.fix_range(c);
           if (!kAlgWork) dW = work_increment<POT, FAST>(c, s.land, x, r_prev, r_cur);
           m2 = half_mean<POT, FAST>(c, s.land, x, r_cur);
@@ -925,11 +950,11 @@ __global__ void __launch_bounds__(kPairThreads) langevin_pair_kernel(const Lange
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           threefry2x32(key_schedule(key_ring_s[h][i + j][0][lane], key_ring_s[h][i + j][1][lane]), 0u, 0u, bits[j], unused);
-        if (FAST) {
+        if (FAST && NQ_FAST_NORMAL != 1) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) z[j] = fast_normal(bits[j]);
         } else {
-          normal4_strict(bits, z);
+          normal4_strict(bits, z);   // both math modes draw the exact jax.random.normal values
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) ring_s[h][i + j][lane] = z[j];

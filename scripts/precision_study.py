@@ -31,3 +31,14 @@ print(f'[{mode} n={n}] x_final: {q(xerr)}')
 print(f'[{mode} n={n}] work   : {q(werr)}   mean-ratio-1 {abs(w.astype(np.float64).mean() / o["work"].astype(np.float64).mean() - 1):.2e}')
 print(f'[{mode} n={n}] logp   : {q(lerr)}')
 print(f'[{mode} n={n}] grads  : logP {rel(gs[0], o["grad_sums"][0]):.2e} reparam {rel(gs[1], o["grad_sums"][1]):.2e}')
+
+# work against the EXACT work along the oracle's own binary32 trajectory (binary64 over the recorded positions): how far
+# the reference-order evaluation (difference of two O(100) energies per step) and the kernel's closed form sit from it
+same = xf == o['positions'][:, -1]
+pos = o['positions'].astype(np.float64)
+rr = np.asarray(r, np.float64)
+exact = (0.75 * ((pos[:, :-1] - rr[None, 1:]) ** 2 - (pos[:, :-1] - rr[None, :-1]) ** 2)).sum(1)
+ek = np.abs(w - exact)[same] / np.abs(exact).max()
+eo = np.abs(o['work'] - exact)[same] / np.abs(exact).max()
+print(f'[{mode} n={n}] {same.mean() * 100:.2f} % of the trajectories end on the oracle\'s bits; on those, work vs exact: '
+      f'kernel med {np.median(ek):.2e} max {ek.max():.2e} | reference-order oracle med {np.median(eo):.2e} max {eo.max():.2e}')

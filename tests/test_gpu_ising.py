@@ -558,3 +558,56 @@ def test_bit_packed_3d_kernel_gradients(cuda):
     for r in range(2):
       o = I.closed_form_gradient(loss, np.asarray(params.log_temp), np.asarray(params.field), Jlt, Jlt, s0, seeds[r])
       assert rel(got[r], np.concatenate(o['grad'])) < 1e-4
+
+
+@pytest.mark.parametrize('n,R,T', [(10000, 2, 5), (8, 3, 6), (12, 2, 6), (128, 2, 5), (256, 2, 4), (2052, 2, 4), (4224, 2, 3)])
+def test_bit_packed_1d_kernel_is_bit_exact(cuda, n, R, T, monkeypatch):
+  """ising_fast1d_kernel: periodic chains with N % 4 == 0 (10 000 is the reference's own 1-D test shape,
+  tests/ising_test.py:71) run bit-packed in shared memory -- each colour plane stored as two halves of N/4 sites so
+  that jax's counter partner p + N/2 is the same bit one half further, 2 x 3 site classes, one threefry block per TWO
+  spin-updates.  The sizes cover a partly filled last word (10 000: 2500 = 78 words + 4 bits; 2052: one bit), one-word
+  halves (8, 12, 128) and whole words (256, 4224).  Spin histories bit-exact against the oracle, summaries within the
+  ulp bounds, and everything equal to the byte-per-spin generic kernel (NQ_ISING_NO_FAST1D=1)."""
+  from noneq_opt_b200 import ising
+  lt = np.log(np.linspace(1.6, 0.9, T).astype(np.float32))
+  h = np.linspace(-0.3, 0.6, T).astype(np.float32)
+  params = ising.IsingParameters(lt, h)
+  s0 = I.random_spins((n,), .55, J.PRNGKey(21))
+  seeds = J.split(J.PRNGKey(4), R)
+
+  def run():
+    final, (summary, states) = ising.simulate_ising(params, s0, seeds, return_states=True)
+    torch.cuda.synchronize()
+    return final.spins.clone(), [getattr(summary, f).clone() for f in FIELDS], states.spins.clone()
+  fin, summ, states = run()
+  assert tuple(fin.shape) == (R, n) and tuple(states.shape) == (R, T - 1, n)
+  for r in range(R):
+    fin_o, summ_o, states_o = I.simulate_ising(lt, h, s0, seeds[r], return_states=True)
+    np.testing.assert_array_equal(fin[r].cpu().numpy(), fin_o)
+    np.testing.assert_array_equal(states[r].cpu().numpy(), states_o)
+    check_summary(np.stack([s[r].cpu().numpy() for s in summ]), np.stack([getattr(summ_o, f) for f in FIELDS]), n)
+  monkeypatch.setenv('NQ_ISING_NO_FAST1D', '1')
+  fin_g, summ_g, states_g = run()
+  assert torch.equal(fin_g, fin) and torch.equal(states_g, states)
+  for a, b in zip(summ_g, summ):
+    assert torch.equal(a, b)
+
+
+def test_bit_packed_1d_kernel_gradients_and_ensemble(cuda):
+  """REINFORCE gradients of both losses on the reference's 1-D shape through the bit-packed path, against the
+  oracle's closed-form gradient; and an ensemble of chains starting from one shared lattice."""
+  from noneq_opt_b200 import ising, parameterization as p10n
+  n, T = 10000, 9
+  w = (0.2 * np.random.RandomState(9).normal(size=(2, 4))).astype(np.float32)
+  sched = ising.IsingSchedule(p10n.Chebyshev(w[0] + np.float32([0.4, 0, 0, 0])), p10n.Chebyshev(w[1]))
+  times = np.linspace(0, 1, T, dtype=np.float32)
+  params = sched(times)
+  s0 = I.random_spins((n,), .5, J.PRNGKey(2))
+  seeds = J.split(J.PRNGKey(12), 3)
+  Jlt = P.Chebyshev(np.zeros(4), np.float64).jacobian(times.astype(np.float64))
+  for loss in ('total_work', 'total_entropy_production'):
+    g, _ = ising.estimate_gradient_rev(getattr(ising, loss))(sched, times, s0, seeds)
+    got = np.concatenate([g.log_temp.weights.cpu().numpy(), g.field.weights.cpu().numpy()], -1)
+    for r in range(3):
+      o = I.closed_form_gradient(loss, np.asarray(params.log_temp), np.asarray(params.field), Jlt, Jlt, s0, seeds[r])
+      assert rel(got[r], np.concatenate(o['grad'])) < 1e-4
