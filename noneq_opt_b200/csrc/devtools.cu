@@ -8,7 +8,7 @@
 // Each thread runs 8 independent dependency chains; one loop iteration issues kOps instructions
 // of the mix per chain-slot.  The host divides (threads * iters * ops_per_iter) by the elapsed SM
 // cycles to get thread-instructions / clk / SM for that mix.
-#include "nq_common.cuh"
+#include "langevin_impl.cuh"   // (brings nq_common.cuh; for the landscape check)
 
 namespace nq {
 // self-contained: the dev library does not link core.cu
@@ -162,7 +162,8 @@ __device__ float normal_literal(uint32_t bits) {
 
 // which: 0 logf_main(x) vs logf(x); 1 log1pf_main(-x) vs log1pf(-x); 2 div_main(c, x) vs c / x (IEEE);
 //        3 normal_from_bits<false>(p << 9) vs normal_literal(p << 9), p = the bit pattern itself;
-//        4 expf_main(x) vs expf(x); 5 expf_main2({x, -x}) vs {expf(x), expf(-x)}.
+//        4 expf_main(x) vs expf(x); 5 expf_main2({x, -x}) vs {expf(x), expf(-x)};
+//        6 the packed landscape's A, B, A + B vs the scalar reference order (c = beta dE).
 // x = the float with bit pattern p, p in [first, first + count).  out[0] = mismatches, out[1] = first mismatching p.
 __global__ void math_check_kernel(int which, unsigned long long first, unsigned long long count, float c,
                                   unsigned long long* out) {
@@ -177,6 +178,27 @@ __global__ void math_check_kernel(int which, unsigned long long first, unsigned 
     else if (which == 2) { a = div_main(c, x); b = __fdiv_rn(c, x); }
     else if (which == 3) { a = normal_from_bits<false>(p << 9); b = normal_literal(p << 9); }
     else if (which == 4) { const StrictRegs sr; a = expf_main(x, sr.exp_k1, sr.exp_k252); b = expf(x); }
+    else if (which == 6) {
+      // the packed landscape (Landscape::eval: both wells as f32x2 pairs) against the scalar reference order
+      // A = exp(cl ul^2), B = exp(-(cr ur^2 + bde)) with the library expf, every operation rounded separately; x is
+      // the pattern's float folded into [-64, 64), c = beta dE (a non-zero value catches a contracted multiply-add)
+      LangevinConsts k{};
+      const StrictRegs sr;
+      k.cl = -0.0543f; k.cr = 0.0571f; k.bde = c; k.two_xm = 28.0f; k.inv_beta = 4.183f;
+      k.exp_k1 = sr.exp_k1; k.exp_k252 = sr.exp_k252;
+      k.well_c2 = f2_pack(k.cl, -k.cr);
+      k.guard_span = 0x3e000000u; k.guard_lo = 0x1p-62f;
+      const float xx = fmodf(x, 64.0f);
+      Landscape<NQ_POT_BIOMOLECULE_SHIFTED, false> land;
+      land.template eval<false>(k, xx);
+      const float ur = __fsub_rn(xx, k.two_xm);
+      const float A = expf(__fmul_rn(k.cl, __fmul_rn(xx, xx)));
+      const float B = expf(-__fadd_rn(__fmul_rn(k.cr, __fmul_rn(ur, ur)), k.bde));
+      a = land.A; b = A;
+      if (__float_as_uint(land.B) != __float_as_uint(B) || __float_as_uint(land.sAB) != __float_as_uint(__fadd_rn(A, B)))
+        a = __uint_as_float(~__float_as_uint(b));
+      if (!(fabsf(x) < 1e30f)) a = b;   // NaN / inf patterns: fmodf is not the subject
+    }
     else {   // both halves of the packed form: lo = exp(x), hi = exp(-x)
       const StrictRegs sr;
       float hi;
@@ -199,7 +221,7 @@ __global__ void math_check_kernel(int which, unsigned long long first, unsigned 
 
 extern "C" int nqdev_math_check(int32_t which, uint64_t first, uint64_t count, float c, uint64_t* out /*device [2]*/,
                                 void* stream) {
-  if (which < 0 || which > 5 || !out) return NQ_ERR_INVALID_ARGUMENT;
+  if (which < 0 || which > 6 || !out) return NQ_ERR_INVALID_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned long long init[2] = {0ull, ~0ull};
   if (cudaMemcpyAsync(out, init, sizeof(init), cudaMemcpyHostToDevice, st) != cudaSuccess) return NQ_ERR_CUDA;

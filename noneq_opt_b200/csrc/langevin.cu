@@ -69,9 +69,8 @@ int make_langevin_consts(const NqLangevinDesc* d, LangevinConsts* c) {
   {
     const StrictRegs sr;
     c->exp_k1 = sr.exp_k1; c->exp_k252 = sr.exp_k252; c->l1p_c9 = sr.l1p_c9;
-    const float pc[2] = {c->cl, -c->cr}, pb[2] = {0.f, -c->bde};   // f32x2: low half first
+    const float pc[2] = {c->cl, -c->cr};   // f32x2: low half first
     memcpy(&c->well_c2, pc, 8);
-    memcpy(&c->well_b2, pb, 8);
   }
   c->one = 1u;
   c->S = d->steps;

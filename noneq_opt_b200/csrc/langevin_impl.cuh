@@ -110,7 +110,7 @@ struct LangevinConsts {
   // STRICT: width of the operand window [2^-62, 2^62) in which the division / logarithm of A + B take their
   // main paths (div_main, logf_main); 0 sends every step through the library functions (extreme 1 / beta)
   uint32_t guard_span;
-  f32x2 well_c2, well_b2;           // {cl, -cr} and {0, -bde}: the packed landscape's constant pairs (kPackedLand)
+  f32x2 well_c2;                    // {cl, -cr}: the packed landscape's constant pair (kPackedLand)
   float exp_k1, exp_k252, l1p_c9;   // StrictRegs: register-held multiplicands of expf_main / log1pf_main
   float guard_lo;   // 2^-62 when A + B is bounded above by construction (in_window_low), else +inf
   uint32_t one;   // = 1: multiplicand of the IMAD-form additions of the key chain (threefry2x32_inj)
@@ -156,7 +156,11 @@ struct Landscape {
       // both wells side by side in FFMA2 / FMUL2 / FADD2 pairs {left, right}: every half is the scalar operation with
       // the scalar rounding (the right well carries -cr and -bde: negation commutes with every rounding, so the pair
       // holds a and -v bit for bit)
-      const f32x2 arg2 = f2_add(f2_mul(c.well_c2, f2_sq(f2_pack(ul, ur))), c.well_b2);
+      // (the right well's "+ beta dE" stays a scalar add: ptxas contracts a packed multiply and a packed add into
+      // one FFMA2 even when both carry .rn, which would skip the rounding of cr ur^2 the reference performs)
+      float a0, ncv;
+      f2_unpack(f2_mul(c.well_c2, f2_sq(f2_pack(ul, ur))), a0, ncv);
+      const f32x2 arg2 = f2_pack(a0, __fsub_rn(ncv, c.bde));
       const f32x2 AB2 = expf_main2(arg2, c.exp_k1, c.exp_k252);
       f2_unpack(AB2, A, B);
       sAB = __fadd_rn(A, B);
@@ -674,13 +678,12 @@ __device__ __forceinline__ void pin_constants(LangevinConsts& c) {
   const uint32_t base = (uint32_t)__cvta_generic_to_shared(pin_s);
 #pragma unroll
   for (int i = 0; i < N; ++i) *f[i] = lds_f32(base + 4 * i);
-  // the constant pairs, re-read as 64-bit words so that they arrive in (and keep) aligned register pairs
-  __shared__ __align__(8) f32x2 pin2_s[2];
-  if (threadIdx.x == 0) { pin2_s[0] = c.well_c2; pin2_s[1] = c.well_b2; }
+  // the constant pair, re-read as a 64-bit word so that it arrives in (and keeps) an aligned register pair
+  __shared__ __align__(8) f32x2 pin2_s[1];
+  if (threadIdx.x == 0) pin2_s[0] = c.well_c2;
   __syncthreads();
   const uint32_t base2 = (uint32_t)__cvta_generic_to_shared(pin2_s);
   asm volatile("ld.shared.b64 %0, [%1];" : "=l"(c.well_c2) : "r"(base2));
-  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(c.well_b2) : "r"(base2 + 8));
 }
 
 template <int POT, bool FAST, int D, bool RECORD, bool PIN = false>

@@ -60,3 +60,12 @@ def test_packed_expf_pair_is_expf_in_both_halves(cuda):
   # expf_main2 (FFMA2 / FADD2 / FMUL2 on a register pair): {exp(x), exp(-x)} for every float x
   bad, where = _check(5, 0, 1 << 32)
   assert bad == 0, f'{bad} mismatches, first at pattern {where:#x}'
+
+
+@pytest.mark.parametrize('bde', [0.0, 0.7, -1.3])
+def test_packed_landscape_is_the_scalar_reference_order(cuda, bde):
+  # Landscape::eval evaluates both wells as f32x2 pairs; ptxas contracts packed multiply + packed add into FFMA2 even
+  # with .rn on both, so the right well's "+ beta dE" is a scalar add -- A, B and A + B must carry the bits of the
+  # one-rounding-per-operation scalar form for every float x (folded into [-64, 64))
+  bad, where = _check(6, 0, 1 << 32, bde)
+  assert bad == 0, f'{bad} mismatches, first at pattern {where:#x}'
