@@ -354,14 +354,26 @@ def run_native(args):
     per_gpu = value / ws
     peaks = measured_peaks()
     hbm_peak = peaks['hbm_gbs'] if peaks else 6650.0
-    alg_bytes = 24.0 * C2_B + 4.0 * (C2_S + 1) + 4.0 * 13 * (C2_S - 1)
+    # per-trajectory I/O + trap table + protocol Jacobian + the 2^23-entry normal-draw table (read once per launch when
+    # cold -- the bench flushes L2 between timed iterations -- and L2-resident from then on)
+    alg_bytes = 24.0 * C2_B + 4.0 * (C2_S + 1) + 4.0 * 13 * (C2_S - 1) + 4.0 * (1 << 23)
     traffic, traffic_src = profiled_dram_traffic(args.math)
+    measured = langevin_instr_per_step().get(args.math, {})
+    alu_peak = 148 * 64 * 1.965e9   # the ALU pipe (LOP3 / SHF / IADD3: the threefry rotates and xors) is half rate
     roofline = dict(
         bound='issue', kernel='langevin_persistent_kernel<BIOMOLECULE_SHIFTED, D=13> (FIFO-scheduled form of langevin_kernel)',
         achieved=per_gpu * INSTR_PER_TRAJ_STEP / 1e12, peak=ISSUE_PEAK / 1e12, unit='Tinstr/s (thread-instructions)',
         frac=per_gpu * INSTR_PER_TRAJ_STEP / ISSUE_PEAK,
         note='instruction-issue bound (3 threefry2x32-20 blocks per step): 326 thread-instr/traj-step (SURVEY 8d) x '
-             'measured traj-steps/s per GPU / (148 SM x 128 lanes x 1.965 GHz); not HBM- or tensor-bound',
+             'measured traj-steps/s per GPU / (148 SM x 128 lanes x 1.965 GHz); not HBM- or tensor-bound.  The kernel '
+             'EXECUTES fewer than the 326 algorithmic instructions (packed f32x2 pairs, the normal draw as a table load): '
+             'executed_* are from the committed ncu capture, alu_pipe is the binding half-rate pipe',
+        executed_instr_per_step=measured.get('instr_per_step'),
+        executed_alu_instr_per_step=measured.get('alu_instr_per_step'),
+        alu_pipe=(dict(achieved=per_gpu * measured['alu_instr_per_step'] / 1e12, peak=alu_peak / 1e12,
+                       unit='Tinstr/s on the half-rate ALU pipe', frac=per_gpu * measured['alu_instr_per_step'] / alu_peak)
+                  if measured.get('alu_instr_per_step') else None),
+        executed_source=measured.get('source'),
         traffic=traffic, traffic_source=traffic_src,
         hbm=dict(bound='hbm', achieved=alg_bytes / (ms * 1e-3) / 1e9, peak=hbm_peak, unit='GB/s',
                  frac=alg_bytes / (ms * 1e-3) / 1e9 / hbm_peak,
@@ -379,8 +391,9 @@ def run_native(args):
                 config5=c5,
                 other_math_mode={'math_mode': other, 'value': units / (ms_other * 1e-3), 'ms_per_step': ms_other,
                                  'mean_work': float(mom_other[1] / mom_other[0]), 'grad0': float(grad_other[0]),
-                                 'note': 'strict = reference operation order (parity-certified, default); fast = MUFU/FMA '
-                                         'refactored step, parity statistical (DESIGN.md 5)'})
+                                 'note': 'strict = reference operation order for positions, closed-form work increment '
+                                         '(parity-certified, default); fast = MUFU/FMA landscape, same exact normal '
+                                         'draws, parity statistical (DESIGN.md 4.1, 5)'})
 
   # ---- secondary: Ising spin-updates/s (rank-local replicas; no collective on the data path)
   ising_res = None if args.no_ising else bench_ising(args, dev, rank, ws)
@@ -443,6 +456,16 @@ def bench_config1_training(dev):
               graph_replay_device_ms_per_step=e0.elapsed_time(e1) / n, launches_per_step=tr.launches_per_step,
               traj_steps_per_s=B * (S + Neq) / (wall_ms * 1e-3),
               note='latency-bound: 32 CTAs of one producer + one consumer warp (DESIGN.md 4.1, 4.5)')
+
+
+def langevin_instr_per_step():
+  """Executed thread-instructions per trajectory-step of the headline Langevin kernel per math mode, from the committed
+  `ncu --set full --import-source on` captures (profiles/langevin_instr_per_step.json, written from the opcode tables
+  scripts/summarize_ncu.py produces)."""
+  try:
+    return json.load(open(os.path.join(ROOT, 'profiles', 'langevin_instr_per_step.json')))
+  except Exception:
+    return {}
 
 
 def ising_instr_per_update():

@@ -77,6 +77,10 @@ constexpr bool kNormalTableFast = kNormalTable && NQ_NORMAL_TABLE_FAST != 0;
 #define NQ_PACKED_LAND 1
 #endif
 constexpr bool kPackedLand = NQ_PACKED_LAND != 0;
+#ifndef NQ_TAB_IN_PHI   // D = 13: (r_k, a_k, b_k) ride in the three padding slots of the 16-float phi row (one LDS.128 fewer per step)
+#define NQ_TAB_IN_PHI 1
+#endif
+constexpr bool tab_in_phi(int D) { return NQ_TAB_IN_PHI != 0 && D > 0 && (D + 3) / 4 * 4 - D == 3; }
 // resident CTAs per SM the register budget is held to, so that config 2 (1563 CTAs of 64) is one wave
 // Resident CTAs per SM the kernels are compiled for (the register budget).  Measured at the config-5 shard size
 // (1.25e6 trajectories, static launch; gpurun_out/variants_r02m.log, 1e10 traj-steps/s STRICT / FAST):
@@ -517,6 +521,7 @@ __device__ __forceinline__ void tile_steps(StepCtx<POT, FAST, D>& s, long long t
                                            uint32_t phi_addr, uint32_t tab_addr) {
   constexpr bool GRAD = D > 0;
   constexpr int DPS = GRAD ? pad4(D) : 4;
+  constexpr bool TIP = tab_in_phi(D) && (FAST || kAlgWork);
   const LangevinConsts& c = s.c;
   const LangevinIO& io = s.io;
   float x = s.x, z = s.z, lp = s.lp, Wt = s.Wt, LPt = s.LPt;
@@ -543,8 +548,10 @@ __device__ __forceinline__ void tile_steps(StepCtx<POT, FAST, D>& s, long long t
     }
     float dW, dR;
     const float x_before = x;
+    float4 lastq = make_float4(0.f, 0.f, 0.f, 0.f);   // TIP: the row's last quad = (phi_{D-1}, r_k, a_k, b_k)
+    if (TIP) lastq = lds_f32x4(phi_addr + 4 * (DPS - 4));
     if (FAST) {
-      const float4 tab = lds_f32x4(tab_addr);
+      const float4 tab = TIP ? make_float4(lastq.y, lastq.z, lastq.w, 0.f) : lds_f32x4(tab_addr);
       dW = fmaf(tab.y, x, tab.z);
       if (kNormalTableFast) {   // the exact jax draw from the table instead of the MUFU approximation of it
         z = __ldg(io.ztable + (s.rng.next() >> 9));
@@ -560,7 +567,7 @@ __device__ __forceinline__ void tile_steps(StepCtx<POT, FAST, D>& s, long long t
       // A + B outside the main-path window (never, for physical parameters) -- are patched afterwards.
       float r_prev, r_cur, wa, wb;
       if (kAlgWork) {
-        const float4 tab = lds_f32x4(tab_addr);
+        const float4 tab = TIP ? make_float4(lastq.y, lastq.z, lastq.w, 0.f) : lds_f32x4(tab_addr);
         r_cur = tab.x; wa = tab.y; wb = tab.z;
       } else {
         r_prev = lds_f32(r_addr);
@@ -584,6 +591,7 @@ __device__ __forceinline__ void tile_steps(StepCtx<POT, FAST, D>& s, long long t
       float m2 = half_mean<POT, FAST>(c, s.land, x, r_cur);
       // ONE predicate for the rare cases: A + B <= 2 always (two exponentials of non-positive arguments), so only
       // the lower edge of the main-path window can be missed and a float compare tests it (NaN -> patched)
+      // (a warp vote in front of this branch does not remove its reconvergence barrier pair: tried, two instructions more)
       if (!((kNormalTable || w < 5.0f) && s.land.in_window_low(c))) {
         if (!kNormalTable && !(w < 5.0f)) z = __fmul_rn(1.41421356237309504880f, __fmul_rn(erfinv_poly_tail<false>(w), u));
         // with the table the predicate is the window test itself: no second test (where guard_lo is +inf every
@@ -611,7 +619,7 @@ __device__ __forceinline__ void tile_steps(StepCtx<POT, FAST, D>& s, long long t
         const f32x2 a2 = f2_pack(a, a), b2 = f2_pack(b, b);
 #pragma unroll
         for (int q = 0; q < DPS / 4; ++q) {
-          const float4 p = lds_f32x4(phi_addr + 16 * q);
+          const float4 p = (TIP && q == DPS / 4 - 1) ? lastq : lds_f32x4(phi_addr + 16 * q);
           if (4 * q < D) {
             const f32x2 p01 = f2_pack(p.x, p.y);
             gA2[2 * q] = f2_fma(a2, p01, gA2[2 * q]);
@@ -626,7 +634,7 @@ __device__ __forceinline__ void tile_steps(StepCtx<POT, FAST, D>& s, long long t
       } else {
 #pragma unroll
         for (int q = 0; q < DPS / 4; ++q) {
-          const float4 p = lds_f32x4(phi_addr + 16 * q);
+          const float4 p = (TIP && q == DPS / 4 - 1) ? lastq : lds_f32x4(phi_addr + 16 * q);
           const float pv[4] = {p.x, p.y, p.z, p.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -752,20 +760,25 @@ __device__ __forceinline__ void langevin_chunk(const LangevinConsts& c_in, const
     __syncthreads();
     NQ_DBG_ASSERT(t0 >= 1 && t0 - 1 + len <= c.S && len >= 1 && len <= kTile);
     for (int i = threadIdx.x; i <= len; i += kThreads) r_s[i] = io.r_table[t0 - 1 + i];
-    if (FAST || kAlgWork) {
-      // dW_k = (k_s/2)[(x-r_k)^2 - (x-r_{k-1})^2] = a_k x + b_k,  a_k = k_s (r_{k-1} - r_k),  b_k = -a_k (r_{k-1} + r_k)/2
-      for (int i = threadIdx.x; i < len; i += kThreads) {
-        const float r0 = io.r_table[t0 - 1 + i], r1 = io.r_table[t0 + i];
-        const float a = 2.0f * c.hk * (r0 - r1);
-        tab_s[i] = make_float4(r1, a, -0.5f * a * (r0 + r1), 0.f);
-      }
-    }
     if (GRAD) {
       // phi row for step k is k-1 (k = 1..S-1); step S (fixed end point) contributes nothing
       for (int i = threadIdx.x; i < len * DPS; i += kThreads) {
         const int row = i / DPS, col = i - row * DPS;
         const long long k = t0 + row;
         phi_s[i] = (col < io.D && k <= c.S - 1) ? io.phi[(k - 1) * io.D + col] : 0.f;  // io.D <= D (template)
+      }
+    }
+    if (FAST || kAlgWork) {
+      // dW_k = (k_s/2)[(x-r_k)^2 - (x-r_{k-1})^2] = a_k x + b_k,  a_k = k_s (r_{k-1} - r_k),  b_k = -a_k (r_{k-1} + r_k)/2
+      if (tab_in_phi(D)) __syncthreads();   // the padding slots of the rows written above
+      for (int i = threadIdx.x; i < len; i += kThreads) {
+        const float r0 = io.r_table[t0 - 1 + i], r1 = io.r_table[t0 + i];
+        const float a = 2.0f * c.hk * (r0 - r1), b = -0.5f * a * (r0 + r1);
+        if (tab_in_phi(D)) {
+          phi_s[i * DPS + DPS - 3] = r1; phi_s[i * DPS + DPS - 2] = a; phi_s[i * DPS + DPS - 1] = b;
+        } else {
+          tab_s[i] = make_float4(r1, a, b, 0.f);
+        }
       }
     }
     __syncthreads();

@@ -75,7 +75,7 @@ def full(src, dst):
 ALU_OPS = {'SHF', 'LOP3', 'IADD3', 'VIADD', 'ISETP', 'FSETP', 'LEA', 'I2FP', 'FSEL', 'FMNMX', 'PRMT', 'PLOP3', 'SEL', 'VIMNMX',
            'POPC', 'FLO', 'BREV', 'IABS', 'FCHK', 'I2F', 'F2I', 'F2F', 'FRND', 'MOV', 'SHL', 'SHR', 'P2R', 'R2P', 'BMSK', 'SGXT',
            'IMNMX', 'VABSDIFF', 'LOP', 'VOTE', 'REDUX'}
-FMA_OPS = {'FFMA', 'FMUL', 'FADD', 'IMAD', 'HFMA2', 'DFMA', 'DADD', 'DMUL'}
+FMA_OPS = {'FFMA', 'FMUL', 'FADD', 'IMAD', 'HFMA2', 'DFMA', 'DADD', 'DMUL', 'FFMA2', 'FMUL2', 'FADD2'}   # *2: sm_100a packed f32x2
 
 
 def _role(op):
@@ -84,7 +84,7 @@ def _role(op):
     return 'integer (threefry hash, bit-sliced lattice, addresses)'
   if base == 'MUFU':
     return 'transcendental (MUFU)'
-  if base in ('FFMA', 'FMUL', 'FADD', 'FSETP', 'FSEL', 'FMNMX', 'I2FP', 'F2F', 'FCHK', 'HFMA2', 'FRND', 'DFMA', 'DADD', 'DMUL', 'F2I', 'I2F'):
+  if base in ('FFMA', 'FMUL', 'FADD', 'FFMA2', 'FMUL2', 'FADD2', 'FSETP', 'FSEL', 'FMNMX', 'I2FP', 'F2F', 'FCHK', 'HFMA2', 'FRND', 'DFMA', 'DADD', 'DMUL', 'F2I', 'I2F'):
     return 'floating point'
   if base in ('LDS', 'STS', 'LDG', 'STG', 'LDC', 'LDCU', 'LDL', 'STL', 'ATOMS', 'ATOMG', 'RED', 'ATOM', 'LDSM', 'MEMBAR', 'ERRBAR', 'CGAERRBAR', 'CCTL'):
     return 'memory'
