@@ -366,6 +366,15 @@ __device__ __forceinline__ void sweep_keys(const KeySchedule& ks_rep, int t, int
 // Shared memory: spread[4][256] | per team: lattice[2][L][NW], thr[2][16] | (CTA team) hist[2][2][2][16]
 // GLOBAL_LAT: the colour planes of a replica live in global memory (L2-resident) instead of shared
 // memory -- same code, for lattices whose 2 x L x L/64 words exceed 227 KB (L >= 2048).
+// Warp teams derive the per-sweep half keys (two words of split(seed, T-1) and their split: four threefry blocks,
+// ~280 warp-instructions, 8 % of a 64^2 sweep when every lane repeats them) for kKeyBatch sweeps at a time, lane j
+// taking sweep t + j, and read them back from shared memory: ~9 instructions per sweep instead of 280.
+#ifndef NQ_ISING_KEY_BATCH
+#define NQ_ISING_KEY_BATCH 32
+#endif
+constexpr int kKeyBatch = NQ_ISING_KEY_BATCH;   // 0: every sweep derives its own keys (the CTA-team form)
+static_assert(kKeyBatch == 0 || kKeyBatch == 32, "one lane per batched sweep");
+
 template <bool WARP_TEAM, bool GLOBAL_LAT = false, bool SEG = false>
 __global__ void __launch_bounds__(WARP_TEAM ? 32 * NQ_ISING_TEAMS : 1024, WARP_TEAM ? NQ_ISING_MINB : 1) ising_fast_kernel(const IsingShape sh, const IsingIO io) {
   static_assert(!SEG || !GLOBAL_LAT, "segments are scheduled per CTA with the lattice in shared memory");
@@ -375,7 +384,8 @@ __global__ void __launch_bounds__(WARP_TEAM ? 32 * NQ_ISING_TEAMS : 1024, WARP_T
   const int lat_words = 2 * L * NW;
   constexpr int kThrWords = 2 * 256 * 2;  // two parity buffers of the 256-entry pair table
   const int smem_lat_words = GLOBAL_LAT ? 0 : lat_words;
-  const int team_words = smem_lat_words + kThrWords + (WARP_TEAM ? 2 * 2 * 2 * kIsingClasses : 0);
+  // warp teams also keep the half-sweep keys of the next kKeyBatch sweeps (kKeyBatch x 4 words): see the sweep loop
+  const int team_words = smem_lat_words + kThrWords + (WARP_TEAM ? 2 * 2 * 2 * kIsingClasses + 4 * kKeyBatch : 0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int team = WARP_TEAM ? warp : 0;
   const int tid = WARP_TEAM ? lane : threadIdx.x;          // index within the team
@@ -521,7 +531,23 @@ __global__ void __launch_bounds__(WARP_TEAM ? 32 * NQ_ISING_TEAMS : 1024, WARP_T
     // shared threshold table of this sweep is complete / the one of the previous sweep is free
     if (WARP_TEAM) __syncthreads();
     KeySchedule kh[2];
-    sweep_keys(ks_rep, t, T, sh.direct_keys != 0, kh[0], kh[1]);
+    if (WARP_TEAM && kKeyBatch > 0) {
+      uint32_t* kc = reinterpret_cast<uint32_t*>(hist_s + 2 * 2 * 2 * kIsingClasses);   // [kKeyBatch][4]
+      const int j = (t - t_first) % kKeyBatch;
+      if (j == 0) {
+        __syncwarp();   // the previous batch has been read by every lane
+        if (t + lane < t_end) {
+          KeySchedule a, b;
+          sweep_keys(ks_rep, t + lane, T, sh.direct_keys != 0, a, b);
+          kc[4 * lane + 0] = a.ks0; kc[4 * lane + 1] = a.ks1; kc[4 * lane + 2] = b.ks0; kc[4 * lane + 3] = b.ks1;
+        }
+        __syncwarp();
+      }
+      kh[0] = key_schedule(kc[4 * j + 0], kc[4 * j + 1]);
+      kh[1] = key_schedule(kc[4 * j + 2], kc[4 * j + 3]);
+    } else {
+      sweep_keys(ks_rep, t, T, sh.direct_keys != 0, kh[0], kh[1]);
+    }
     const uint2* thr_cur = thr_s + (t & 1) * 256;
     if (t + 1 < t_end) build_pair_table(thr_s + ((t + 1) & 1) * 256, io.thr + (size_t)t * kIsingClasses, btid, bsize);
     // warp teams share ONE copy of the half-sweep code between the colours (their phases differ, so the
@@ -1402,7 +1428,7 @@ __global__ void __launch_bounds__(128) ising_grad_kernel(const IsingGradArgs a_i
 static bool fast_path(int L) { return L % 64 == 0; }
 static size_t fast_smem_bytes(int L, bool warp_team, int nteams, bool global_lat = false) {
   const size_t lat_words = global_lat ? 0 : 2 * (size_t)L * (L / 64);
-  size_t words = 4 * 256 + nteams * (lat_words + 2 * 256 * 2 + (warp_team ? 2 * 2 * 2 * kIsingClasses : 0));
+  size_t words = 4 * 256 + nteams * (lat_words + 2 * 256 * 2 + (warp_team ? 2 * 2 * 2 * kIsingClasses + 4 * kKeyBatch : 0));
   if (!warp_team) words += 2 * 2 * 2 * kIsingClasses + 2;
   return words * 4;
 }
