@@ -32,7 +32,7 @@ c2 = np.array([20., 19.95996] + [0.] * 11, np.float32)
 for name, B in (('c2', 100_000), ('c5_one_gpu', 10_000_000), ('c5_shard_of_8', 1_250_000)):
   seeds = nqr.split(nqr.PRNGKey(0), B)
   x0 = torch.zeros(B, device='cuda')
-  ms, g = timed(lambda: bc.gradient_terms(pot, c2, x0, seeds, 0., 40., 0, shift, 10_000, 1e-8, KT, 1.0, KT / 1e7), reps=4 if B == 100_000 else 2)
+  ms, g = timed(lambda: bc.gradient_terms(pot, c2, x0, seeds, 0., 40., 0, shift, 10_000, 1e-8, KT, 1.0, KT / 1e7), reps=4 if B == 100_000 else 3)
   m = g['moments'].cpu().numpy()
   res[name] = dict(ms=ms, traj_steps_per_s=B * 1e4 / ms * 1e3, mean_work=m[1] / m[0],
                    work_std_err=float(np.sqrt((m[2] / m[0] - (m[1] / m[0]) ** 2) / m[0])),
