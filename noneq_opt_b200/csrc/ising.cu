@@ -193,6 +193,14 @@ __device__ __forceinline__ void histogram(const Planes& p, uint32_t F, int (&hA)
 // 1: the 23 uniform bits jax keeps of a word (bits >> 9) as the high half of bits * 2^23 (IMAD.HI, FMA pipe, fused
 // with the subtraction of the threshold) instead of a shift on the binding ALU pipe; the 2^23 comes from the
 // run-time 1 so that ptxas cannot turn the multiply back into a shift
+// 1: blocks enter the hash after the first round's addition (threefry2x32_pre): the counter words of a unit advance
+// by constants, so x1 and x0 + x1 are per-unit bases plus constants -- one addition fewer per block
+#ifndef NQ_ISING_PRESUM
+#define NQ_ISING_PRESUM 1
+#endif
+constexpr bool kPreSumOn = NQ_ISING_PRESUM != 0;   // warp teams only (measured, r02z: 64^2 5.31e11 -> 5.52e11, 128^2 4.96e11 ->
+// 5.17e11; the CTA team, whose adds are all IMADs, loses 3 %: 1024^2 5.97e11 -> 5.80e11 -- ptxas hoists the products and
+// adds the constants on the ALU pipe)
 #ifndef NQ_ISING_MULHI
 #define NQ_ISING_MULHI 0
 #endif
@@ -201,8 +209,9 @@ __device__ __forceinline__ void update_unit(uint32_t* lat, const IsingShape& sh,
                                             const uint2* thr2, const KeySchedule& ks, int c, int i, int w,
                                             int (&hA)[10], int (&hF)[10]) {
   constexpr bool ALLMAD = MODE == 1;
+  constexpr bool kPreSum = kPreSumOn && !ALLMAD;
   KeyInject kinj;
-  if (MODE == 2) kinj = key_inject(ks.ks0, ks.ks1, sh.one);
+  if (MODE == 2 || kPreSum) kinj = key_inject(ks.ks0, ks.ks1, sh.one);
   const int L = sh.L, NW = sh.NW, i2 = i + L / 2;
   Planes pa, pb;
   load_planes(lat, sh, c, i, w, pa);
@@ -210,12 +219,13 @@ __device__ __forceinline__ void update_unit(uint32_t* lat, const IsingShape& sh,
   const int off = c == 0 ? 1 - (i & 1) : (i & 1);
   const uint32_t cbase = (uint32_t)i * L + 2u * (32u * w) + off;
   const uint32_t half = (uint32_t)L * L / 2;
+  const uint32_t b1 = cbase + half + ks.ks1, b01 = 2u * cbase + half + ks.ks0 + ks.ks1;   // kPreSum bases
   // Sites are visited from 31 down to 0 so that the acceptance bits can be shifted in from the
   // right: accept <=> (bits >> 9) - thr < 0, and one funnel shift moves that sign bit into the mask
   // (the subtraction can issue on the FMA pipe; the ALU pipe, which bounds this kernel, sees one
   // shift instead of compare + select + or).
   uint32_t Fa = 0, Fb = 0, Na = 0, Nb = 0;
-  const uint32_t two23 = sh.one << 23;
+  const uint32_t two23 = sh.one << 23, sixteen = sh.one << 4;
 #if NQ_ISING_BLOCKS_PER_ITER == 8
 #pragma unroll 1
   for (int q = 3; q >= 0; --q) {
@@ -242,7 +252,16 @@ __device__ __forceinline__ void update_unit(uint32_t* lat, const IsingShape& sh,
       for (int e = 1; e >= 0; --e) {
         const uint32_t ctr = cbase + 2u * (8u * q + 2u * j + e);
         uint32_t y0, y1;
-        if (ALLMAD) threefry2x32_allmad(ks, ctr, ctr + half, y0, y1, sh.one);
+        if (kPreSum) {
+          // x1 = ctr + half + ks1 and x0 + x1 = 2 ctr + half + ks0 + ks1: both are (a per-unit base) + (16 q resp. 32 q)
+          // + a compile-time constant, so a block enters the hash after its first addition with two adds, not three
+          const uint32_t o = 2u * (2u * j + e);
+          const uint32_t bq1 = ALLMAD ? mad1((uint32_t)q, sixteen, b1) : b1 + 16u * q;      // once per q
+          const uint32_t bq01 = ALLMAD ? mad1((uint32_t)q, 2u * sixteen, b01) : b01 + 32u * q;
+          const uint32_t x1 = ALLMAD ? mad1(bq1, sh.one, o) : bq1 + o;
+          const uint32_t s01 = ALLMAD ? mad1(bq01, sh.one, 2u * o) : bq01 + 2u * o;
+          threefry2x32_pre<MODE>(kinj, s01, x1, sh.one, y0, y1);
+        } else if (ALLMAD) threefry2x32_allmad(ks, ctr, ctr + half, y0, y1, sh.one);
         else if (MODE == 2) threefry2x32_inj<false>(kinj, ctr + ks.ks0, ctr + half + ks.ks1, sh.one, y0, y1);
         else threefry2x32(ks, ctr, ctr + half, y0, y1);
         const uint32_t da = (NQ_ISING_MULHI ? __umulhi(y0, two23) : (y0 >> 9)) - (e ? ta.y : ta.x);
