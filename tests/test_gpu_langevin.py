@@ -636,3 +636,39 @@ def test_closed_form_work_is_nearer_the_exact_work_than_the_reference_order(cuda
   assert np.median(err_kernel) < 0.2 * np.median(err_oracle)
   assert np.quantile(err_kernel, 0.9) < 0.5 * np.quantile(err_oracle, 0.9)
   assert (np.abs(w - o['work']) / np.abs(o['work']).max()).max() < POS_RTOL
+
+
+@pytest.mark.parametrize('case', ['far_start', 'inverted_left_well', 'deep_right_well'])
+def test_landscape_main_path_window_and_its_patch_block(cuda, case):
+  """The STRICT step evaluates the division and (literal work order) logarithm of A + B on their main paths inside
+  [2^-62, 2^62) and patches steps outside that window with the library functions (one float compare per step, valid
+  where A + B is bounded above; otherwise every step takes the patch block).  far_start: trajectories that begin 32
+  well-widths out, A + B ~ 1e-25, and fall back into the window; inverted_left_well / deep_right_well: parameters for
+  which the bound does not hold (kappa_l < 0; beta dE < -40), so the whole run goes through the patch block."""
+  from noneq_opt_b200 import barrier_crossing as bc, random as nqr, space
+  from oracle import c_oracle
+  _, shift = space.free()
+  n, S = 96, 160
+  coeffs = np.array([2.0e+01, 1.99599600e+01] + [0.] * 11, np.float32)
+  kl, kr, dE, x0v = KAPPA, KAPPA, 0., 0.
+  if case == 'far_start':
+    x0v = 60.0
+  elif case == 'inverted_left_well':
+    kl = -0.02 * KAPPA
+  else:
+    dE = -45.0 * KT
+  pot_o = L.V_biomolecule_shifted(kl, kr, XM, dE, 1.5, BETA)
+  pot_g = bc.V_biomolecule_shifted(kl, kr, XM, dE, 1.5, BETA)
+  r, phi = L.make_schedule_chebyshev(S, coeffs, 0., 40.)
+  seeds_np = J.split(J.PRNGKey(5), n)
+  x0 = np.full(n, x0v, np.float32)
+  o = c_oracle.langevin(pot_o, r, phi, x0, seeds_np, S, 0, 1e-8, KT, KT / 1e7, 1.0, record=True)
+  seeds = nqr.split(J.PRNGKey(5), n)
+  g = bc.gradient_terms(pot_g, coeffs, x0, seeds, 0., 40., 0, shift, S, 1e-8, KT, 1.0, KT / 1e7)
+  xf, w = g['x_final'].cpu().numpy(), g['work'].cpu().numpy()
+  assert np.isfinite(o['positions']).all() and np.isfinite(xf).all() and np.isfinite(w).all()
+  assert rel(xf, o['positions'][:, -1]) < POS_RTOL
+  assert rel(w, o['work']) < POS_RTOL
+  assert rel(g['logp'].cpu().numpy(), o['logp']) < POS_RTOL
+  gs = g['grad_sums'].cpu().numpy()
+  assert rel(gs[0], o['grad_sums'][0]) < GRAD_RTOL and rel(gs[1], o['grad_sums'][1]) < GRAD_RTOL
