@@ -638,15 +638,20 @@ def test_closed_form_work_is_nearer_the_exact_work_than_the_reference_order(cuda
   assert (np.abs(w - o['work']) / np.abs(o['work']).max()).max() < POS_RTOL
 
 
+@pytest.mark.parametrize('launch', ['pipeline', 'one_warp'])
 @pytest.mark.parametrize('case', ['far_start', 'inverted_left_well', 'deep_right_well'])
-def test_landscape_main_path_window_and_its_patch_block(cuda, case):
+def test_landscape_main_path_window_and_its_patch_block(cuda, case, launch, monkeypatch):
   """The STRICT step evaluates the division and (literal work order) logarithm of A + B on their main paths inside
   [2^-62, 2^62) and patches steps outside that window with the library functions (one float compare per step, valid
   where A + B is bounded above; otherwise every step takes the patch block).  far_start: trajectories that begin 32
   well-widths out, A + B ~ 1e-25, and fall back into the window; inverted_left_well / deep_right_well: parameters for
-  which the bound does not hold (kappa_l < 0; beta dE < -40), so the whole run goes through the patch block."""
+  which the bound does not hold (kappa_l < 0; beta dE < -40), so the whole run goes through the patch block.  Both
+  launch forms: the three-warp pipeline small ensembles take, and the one-warp kernel's straight-line step loop
+  (NQ_PAIR_MAX=0), whose rare-case predicate is the float compare."""
   from noneq_opt_b200 import barrier_crossing as bc, random as nqr, space
   from oracle import c_oracle
+  if launch == 'one_warp':
+    monkeypatch.setenv('NQ_PAIR_MAX', '0')
   _, shift = space.free()
   n, S = 96, 160
   coeffs = np.array([2.0e+01, 1.99599600e+01] + [0.] * 11, np.float32)
