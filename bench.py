@@ -98,19 +98,33 @@ class ClockSampler:
       phys = int(visible.split(',')[self.index]) if visible and visible.split(',')[self.index].isdigit() else self.index
       return pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
 
-  def _poll_nvml(self, nv, h):
+  def _sample_nvml(self, nv, h, mx):
     masks = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
              nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap]
+    try:
+      bits = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+      self.rows.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx),
+                        str(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)] +
+                       ['Active' if bits & m else 'Not Active' for m in masks])
+    except Exception:
+      pass
+
+  def _poll_nvml(self, nv, h):
     mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
     while not self.stop_flag.is_set():
+      self._sample_nvml(nv, h, mx)
+      time.sleep(0.005)
+
+  def sample_now(self):
+    """One synchronous sample from the calling thread: called while a timed step's kernel is in flight, so that every
+    step contributes at least one under-load sample even where the polling thread is slow (a box whose NVML queries
+    take ~100 ms gave ONE sample for the whole timed region).  Host-side only: the step is timed by CUDA events."""
+    if self.source == 'nvml' and getattr(self, '_nvml', None):
+      nv, h = self._nvml
       try:
-        bits = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-        self.rows.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx),
-                          str(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)] +
-                         ['Active' if bits & m else 'Not Active' for m in masks])
+        self._sample_nvml(nv, h, nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
       except Exception:
         pass
-      time.sleep(0.005)
 
   def prepare(self):
     """NVML initialisation and a first query, done BEFORE the warm-up so that starting the sampler at
@@ -296,6 +310,8 @@ def run_native(args):
       e0.record()
       result = fn()
       e1.record()
+      if sampler:
+        sampler.sample_now()
       torch.cuda.synchronize()
       total_ms += e0.elapsed_time(e1)
       if os.environ.get('NQ_BENCH_DEBUG'):
