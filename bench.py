@@ -233,7 +233,11 @@ def workload_config(n_gpus):
                        f'{C2_B} trajectories/GPU x {C2_S} steps, forward + REINFORCE work gradient wrt 13 Chebyshev coeffs',
               trajectories_per_gpu=C2_B, steps_per_trajectory=C2_S, coefficients=13, kT=KT, dt=DT,
               parallelism=f'ensemble-sharded x{n_gpus} + 1 allreduce', l2='flushed between timed iterations '
-              f'({L2_FLUSH_BYTES >> 20} MiB write); working set is registers + 24 B/trajectory')
+              f'({L2_FLUSH_BYTES >> 20} MiB write); working set is registers + 24 B/trajectory + the 32 MB normal-draw '
+              'table, which every timed iteration therefore reads cold',
+              normal_draws='every step hashes its own threefry key and maps the 23 bits jax.random.normal keeps through a '
+                           'table of that function over all 2^23 patterns (32 MB per device, written once by the kernels\' '
+                           'own device function before the warm-up): a tabulated function, not cached results')
 
 
 # =============================================================================== native arm
