@@ -237,7 +237,7 @@ def workload_config(n_gpus):
               'table, which every timed iteration therefore reads cold',
               normal_draws='every step hashes its own threefry key and maps the 23 bits jax.random.normal keeps through a '
                            'table of that function over all 2^23 patterns (32 MB per device, written once by the kernels\' '
-                           'own device function before the warm-up): a tabulated function, not cached results')
+                           'own device function on the first call, i.e. during the warm-up): a tabulated function, not cached results')
 
 
 # =============================================================================== native arm
