@@ -547,7 +547,7 @@ def bench_ising(args, dev, rank, ws):
   spins0 = -torch.ones((L, L), dtype=torch.float32, device=dev)
   seeds = nqr.split(nqr.PRNGKey(0), R * ws, first=rank * R, count=R)
   est = ising.estimate_gradient_rev(ising.total_entropy_production)
-  ms = timed(lambda: est(sched, times, spins0, seeds), 5, 2)
+  ms = timed(lambda: est(sched, times, spins0, seeds), 10, 3)   # (5 + 2 let one slow host iteration move the mean by 10 %)
   upd = float(R * ws) * (T - 1) * L * L
   # end to end: host lattice + host keys in, host gradient + per-replica loss terms out
   spins0_h = -np.ones((L, L), np.float32)
@@ -561,9 +561,9 @@ def bench_ising(args, dev, rank, ws):
     return g, summ.entropy_production.sum(-1).cpu().numpy()
   g3, ep3 = c3_e2e()
   d2h = g3.nbytes + ep3.nbytes
-  ms_e = timed(c3_e2e, 5, 1)
+  ms_e = timed(c3_e2e, 10, 2)
   out['c3_64x64_4096rep_1000sweeps_grad'] = dict(
-      spin_updates_per_s=upd / (ms * 1e-3), ms_per_step=ms, per_gpu=upd / ws / (ms * 1e-3), steps=5, warmup=2,
+      spin_updates_per_s=upd / (ms * 1e-3), ms_per_step=ms, per_gpu=upd / ws / (ms * 1e-3), steps=10, warmup=3,
       e2e=dict(value=upd / (ms_e * 1e-3), unit='spin-updates/s', ms_per_step=ms_e, h2d_bytes_per_step=h2d,
                d2h_bytes_per_step=d2h, api='noneq_opt_b200.ising.estimate_gradient_rev(total_entropy_production) with numpy '
                'lattice and keys in, per-replica gradients and entropy production back on the host'),
