@@ -421,6 +421,7 @@ def run_native(args):
     line['ising'] = ising_res
     if ws == 1 and not args.no_ising:
       line['config1_training'] = bench_config1_training(dev)
+      line['ising_training'] = bench_ising_training(dev)
     if ws == 1 and not args.no_cpu:
       line['cpu_baseline'] = cpu_baseline()
       if not args.no_ising:
@@ -476,6 +477,49 @@ def bench_config1_training(dev):
               graph_replay_device_ms_per_step=e0.elapsed_time(e1) / n, launches_per_step=tr.launches_per_step,
               traj_steps_per_s=B * (S + Neq) / (wall_ms * 1e-3),
               note='latency-bound: 32 CTAs of one producer + one consumer warp (DESIGN.md 4.1, 4.5)')
+
+
+def bench_ising_training(dev):
+  """One Ising training step (`run_ising_opt.py:77-102` around `get_train_step`, `ising.py:263-290`) through the host
+  `get_train_step` and as one CUDA-graph replay of `training.IsingTrainer` (zero host synchronisations per step), at
+  the reference driver's own shape (its argv comments: size 32, 51 time steps, degree 32, batch 256; a 32 x 32 lattice
+  takes the byte-per-spin generic kernel) and at configs[2]'s shape (64^2, 4096 replicas, 1001 time steps, degree 16)."""
+  import torch
+  from noneq_opt_b200 import ising, optimizers, parameterization as p10n, training
+  out = {}
+  for name, (L, T, deg, B, n) in dict(reference_driver_32x32_T51_deg32_batch256=(32, 51, 32, 256, 50),
+                                      config3_64x64_T1001_deg16_batch4096=(64, 1001, 16, 4096, 5)).items():
+    sched = ising.IsingSchedule(
+        p10n.AddBaseline(p10n.ConstrainEndpoints(p10n.Chebyshev(np.zeros(deg, np.float32)), 0., 0.), ising.log_temp_baseline(0.65)),
+        p10n.AddBaseline(p10n.ConstrainEndpoints(p10n.Chebyshev(np.zeros(deg, np.float32)), 0., 0.), ising.field_baseline()))
+    spins0 = -np.ones((L, L), np.float32)
+    opt = optimizers.adam(optimizers.exponential_decay(0.1, n, 0.01))
+    step_fn = ising.get_train_step(opt, spins0, B, T, ising.total_entropy_production, 'fwd', max_grad=1.0)
+    state, stream = opt.init_fn(sched), ising.seed_stream(0)
+    for j in range(2):
+      state, _ = step_fn(state, j, next(stream))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for j in range(n):
+      state, _ = step_fn(state, j, next(stream))
+    torch.cuda.synchronize()
+    host_ms = 1e3 * (time.perf_counter() - t0) / n
+    tr = training.IsingTrainer(sched, spins0, B, T, np.array([0, 0], np.uint32), loss_function=ising.total_entropy_production,
+                               max_grad=1.0, step_size=0.1, decay_steps=n, decay_rate=0.01)
+    for _ in range(3):
+      tr.step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+      tr.step()
+    e1.record()
+    torch.cuda.synchronize()
+    dev_ms = e0.elapsed_time(e1) / n
+    out[name] = dict(host_get_train_step_ms_per_step=host_ms, graph_replay_ms_per_step=dev_ms,
+                     launches_per_step=int(tr.launches_per_step), spin_updates_per_s=float(B) * (T - 1) * L * L / (dev_ms * 1e-3),
+                     mean_loss=float(tr.loss.mean().item()))
+  return out
 
 
 def langevin_instr_per_step():
