@@ -307,16 +307,23 @@ def run_native(args):
     if sampler:
       sampler.start()
     launches0 = lib.nq_launch_count()
-    total_ms, result = 0.0, None
+    total_ms, result, events = 0.0, None, []
+    # Every step is bracketed by its own pair of CUDA events; the host does NOT wait for a step before enqueueing the
+    # next (one synchronise after the last), so that a late host thread on one rank -- Python jitter -- is absorbed by
+    # the stream queue instead of stalling the other ranks inside that step's all-reduce (with 8 ranks and a host
+    # synchronise per step, two such stalls in ten steps cost 5 % of the max-over-ranks time).  An end-to-end step
+    # (step_e2e) reads its results on the host and therefore synchronises by itself.
     for _ in range(steps):
       flush.fill_(1)                       # L2 flush between timed iterations (not timed)
       e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
       e0.record()
       result = fn()
       e1.record()
+      events.append((e0, e1))
       if sampler:
         sampler.sample_now()
-      torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    for e0, e1 in events:
       total_ms += e0.elapsed_time(e1)
       if os.environ.get('NQ_BENCH_DEBUG'):
         print(f'[bench rank {rank}] {fn.__name__}: {e0.elapsed_time(e1):.3f} ms', file=sys.stderr)
