@@ -677,3 +677,36 @@ def test_landscape_main_path_window_and_its_patch_block(cuda, case, launch, monk
   assert rel(g['logp'].cpu().numpy(), o['logp']) < POS_RTOL
   gs = g['grad_sums'].cpu().numpy()
   assert rel(gs[0], o['grad_sums'][0]) < GRAD_RTOL and rel(gs[1], o['grad_sums'][1]) < GRAD_RTOL
+
+
+def test_normal_table_prepare_is_idempotent_and_refuses_to_build_during_capture(cuda):
+  """The trajectory kernels read their normal draws from a per-device table the library builds on first use
+  (include/noneq_b200.h: nq_langevin_prepare).  The build allocates and synchronises, which stream capture forbids:
+  in a FRESH process a build requested on a capturing stream must be refused with NQ_ERR_UNSUPPORTED and the
+  documented message (leaving the capture intact), and succeed outside capture; repeated prepares are no-ops."""
+  import subprocess
+  import sys
+  from noneq_opt_b200 import _lib
+  assert _lib.lib().nq_langevin_prepare(None) == 0 and _lib.lib().nq_langevin_prepare(None) == 0
+  child = r'''
+import sys
+import torch
+sys.path.insert(0, %r)
+from noneq_opt_b200 import _lib
+lib = _lib.lib()
+buf = torch.zeros(16, device='cuda')
+side = torch.cuda.Stream()
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g, stream=side):
+  buf.add_(1.0)
+  rc = lib.nq_langevin_prepare(_lib.stream_arg())
+  msg = lib.nq_last_error().decode()
+  buf.add_(1.0)
+print('RC', rc, 'MSG', 'nq_langevin_prepare' in msg and 'capture' in msg)
+g.replay(); torch.cuda.synchronize()
+print('GRAPH', float(buf[0]))
+print('AFTER', lib.nq_langevin_prepare(None), lib.nq_langevin_prepare(None))
+''' % ROOT
+  r = subprocess.run([sys.executable, '-c', child], capture_output=True, text=True, timeout=300)
+  assert 'RC %d MSG True' % _lib.NQ_ERR_UNSUPPORTED in r.stdout, r.stdout + r.stderr
+  assert 'GRAPH 2.0' in r.stdout and 'AFTER 0 0' in r.stdout, r.stdout + r.stderr
