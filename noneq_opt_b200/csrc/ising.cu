@@ -668,6 +668,30 @@ __global__ void ising_status_kernel(const unsigned* status, float* summary, size
     summary[i] = __int_as_float(0x7fc00000);
 }
 
+// CTA-per-replica kernels: the half-sweep keys of the next kKeyBatch sweeps, derived by warp 0 (lane j takes sweep
+// t + j) into a CTA-shared cache kc[kKeyBatch][4]; every thread then reads its sweep's four words (the warp-team
+// kernel does the same per warp, see ising_fast_kernel).  Called by ALL threads of the CTA at every sweep.
+__device__ __forceinline__ void cta_sweep_keys(uint32_t* kc, const KeySchedule& ks_rep, int t, int T, bool direct,
+                                               KeySchedule& k_first, KeySchedule& k_second) {
+  if (kKeyBatch == 0) {
+    sweep_keys(ks_rep, t, T, direct, k_first, k_second);
+    return;
+  }
+  const int j = (t - 1) % kKeyBatch;
+  if (j == 0) {
+    __syncthreads();   // every thread has read the previous batch
+    if (threadIdx.x < 32 && t + (int)threadIdx.x < T) {
+      KeySchedule a, b;
+      sweep_keys(ks_rep, t + (int)threadIdx.x, T, direct, a, b);
+      kc[4 * threadIdx.x + 0] = a.ks0; kc[4 * threadIdx.x + 1] = a.ks1;
+      kc[4 * threadIdx.x + 2] = b.ks0; kc[4 * threadIdx.x + 3] = b.ks1;
+    }
+    __syncthreads();
+  }
+  k_first = key_schedule(kc[4 * j + 0], kc[4 * j + 1]);
+  k_second = key_schedule(kc[4 * j + 2], kc[4 * j + 3]);
+}
+
 // ------------------------------------------------------------------------------ bit-packed 3-D kernel
 // The fast path for cubic / cuboid lattices d0 x d1 x d2 (the reference's own 3-D test shape is 64^3,
 // tests/ising_test.py:71; sum_neighbors / even_odd_masks are rank-generic, ising.py:75-106).  Same design as the 2-D
@@ -774,6 +798,7 @@ __global__ void __launch_bounds__(1024, 1) ising_fast3d_kernel(const IsingShape 
   uint32_t* lat = smem + 4 * 256;
   uint2* thr_s = reinterpret_cast<uint2*>(lat + 2 * plane_words);
   int* hist_s = reinterpret_cast<int*>(lat + 2 * plane_words + 2 * 256 * 2);
+  uint32_t* kc = reinterpret_cast<uint32_t*>(hist_s + 2 * 2 * 2 * kIsingClasses + 2);   // [kKeyBatch][4] sweep keys
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x, tsize = blockDim.x;
   const long long rep = blockIdx.x;
   const size_t ext_words = (size_t)sh.N / 32;
@@ -823,7 +848,7 @@ __global__ void __launch_bounds__(1024, 1) ising_fast3d_kernel(const IsingShape 
   const int units = (g.d0 / 2) * g.d1 * NW;
   for (int t = 1; t < T; ++t) {
     KeySchedule kh[2];
-    sweep_keys(ks_rep, t, T, sh.direct_keys != 0, kh[0], kh[1]);
+    cta_sweep_keys(kc, ks_rep, t, T, sh.direct_keys != 0, kh[0], kh[1]);
     const uint2* thr_cur = thr_s + (t & 1) * 256;
     if (t + 1 < T) build_pair_table(thr_s + ((t + 1) & 1) * 256, io.thr + (size_t)t * kIsingClasses, tid, tsize);
     for (int c = 0; c < 2; ++c) {
@@ -887,7 +912,7 @@ __global__ void __launch_bounds__(1024, 1) ising_fast3d_kernel(const IsingShape 
 
 static size_t fast3d_smem_bytes(const int* dims) {
   const size_t plane_words = (size_t)dims[0] * dims[1] * (dims[2] / 64);
-  return (4 * 256 + 2 * plane_words + 2 * 256 * 2 + 2 * 2 * 2 * kIsingClasses + 2) * 4;
+  return (4 * 256 + 2 * plane_words + 2 * 256 * 2 + 2 * 2 * 2 * kIsingClasses + 2 + 4 * kKeyBatch) * 4;
 }
 static bool fast3d_ok(int ndim, const int* dims) {
   return ndim == 3 && dims[2] % 64 == 0 && dims[1] % 2 == 0 && dims[0] % 4 == 0 && fast3d_smem_bytes(dims) <= 227 * 1024 &&
@@ -1007,6 +1032,7 @@ __global__ void __launch_bounds__(1024, 1) ising_fast1d_kernel(const IsingShape 
   uint32_t* lat = smem + 4 * 256;
   uint2* thr_s = reinterpret_cast<uint2*>(lat + 2 * plane_words);
   int* hist_s = reinterpret_cast<int*>(lat + 2 * plane_words + 2 * 256 * 2);
+  uint32_t* kc = reinterpret_cast<uint32_t*>(hist_s + 2 * 2 * 2 * kIsingClasses + 2);   // [kKeyBatch][4] sweep keys
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x, tsize = blockDim.x;
   const long long rep = blockIdx.x;
   const int ext_words = (N + 31) / 32;
@@ -1059,7 +1085,7 @@ __global__ void __launch_bounds__(1024, 1) ising_fast1d_kernel(const IsingShape 
   const KeySchedule ks_rep = key_schedule(io.seeds[2 * rep], io.seeds[2 * rep + 1]);
   for (int t = 1; t < T; ++t) {
     KeySchedule kh[2];
-    sweep_keys(ks_rep, t, T, sh.direct_keys != 0, kh[0], kh[1]);
+    cta_sweep_keys(kc, ks_rep, t, T, sh.direct_keys != 0, kh[0], kh[1]);
     const uint2* thr_cur = thr_s + (t & 1) * 256;
     if (t + 1 < T) build_pair_table(thr_s + ((t + 1) & 1) * 256, io.thr + (size_t)t * kIsingClasses, tid, tsize);
     for (int c = 0; c < 2; ++c) {
@@ -1108,7 +1134,7 @@ __global__ void __launch_bounds__(1024, 1) ising_fast1d_kernel(const IsingShape 
 
 static size_t fast1d_smem_bytes(long long N) {
   const size_t Wh = (size_t)((N / 4 + 31) / 32);
-  return (4 * 256 + 4 * Wh + 2 * 256 * 2 + 2 * 2 * 2 * kIsingClasses + 2) * 4;
+  return (4 * 256 + 4 * Wh + 2 * 256 * 2 + 2 * 2 * 2 * kIsingClasses + 2 + 4 * kKeyBatch) * 4;
 }
 static bool fast1d_ok(int ndim, const int* dims) {
   return ndim == 1 && dims[0] % 4 == 0 && dims[0] >= 8 && fast1d_smem_bytes(dims[0]) <= 227 * 1024 &&
