@@ -394,6 +394,31 @@ __device__ __forceinline__ void sweep_keys(const KeySchedule& ks_rep, int t, int
 constexpr int kKeyBatch = NQ_ISING_KEY_BATCH;   // 0: every sweep derives its own keys (the CTA-team form)
 static_assert(kKeyBatch == 0 || kKeyBatch == 32, "one lane per batched sweep");
 
+// CTA-per-replica kernels: the half-sweep keys of the next kKeyBatch sweeps, derived by warp 0 (lane j takes sweep
+// t + j) into a CTA-shared cache kc[kKeyBatch][4]; every thread then reads its sweep's four words (the warp-team
+// kernel does the same per warp, see ising_fast_kernel).  Called by ALL threads of the CTA at every sweep.
+__device__ __forceinline__ void cta_sweep_keys(uint32_t* kc, const KeySchedule& ks_rep, int t, int T, bool direct,
+                                               KeySchedule& k_first, KeySchedule& k_second, int t_first = 1, int t_end = -1) {
+  if (kKeyBatch == 0) {
+    sweep_keys(ks_rep, t, T, direct, k_first, k_second);
+    return;
+  }
+  if (t_end < 0) t_end = T;
+  const int j = (t - t_first) % kKeyBatch;   // (t_first, t_end): the sweeps of this pass (a segment, or the whole run)
+  if (j == 0) {
+    __syncthreads();   // every thread has read the previous batch
+    if (threadIdx.x < 32 && t + (int)threadIdx.x < t_end) {
+      KeySchedule a, b;
+      sweep_keys(ks_rep, t + (int)threadIdx.x, T, direct, a, b);
+      kc[4 * threadIdx.x + 0] = a.ks0; kc[4 * threadIdx.x + 1] = a.ks1;
+      kc[4 * threadIdx.x + 2] = b.ks0; kc[4 * threadIdx.x + 3] = b.ks1;
+    }
+    __syncthreads();
+  }
+  k_first = key_schedule(kc[4 * j + 0], kc[4 * j + 1]);
+  k_second = key_schedule(kc[4 * j + 2], kc[4 * j + 3]);
+}
+
 template <bool WARP_TEAM, bool GLOBAL_LAT = false, bool SEG = false>
 __global__ void __launch_bounds__(WARP_TEAM ? 32 * NQ_ISING_TEAMS : 1024, WARP_TEAM ? NQ_ISING_MINB : 1) ising_fast_kernel(const IsingShape sh, const IsingIO io) {
   static_assert(!SEG || !GLOBAL_LAT, "segments are scheduled per CTA with the lattice in shared memory");
@@ -564,6 +589,9 @@ __global__ void __launch_bounds__(WARP_TEAM ? 32 * NQ_ISING_TEAMS : 1024, WARP_T
       }
       kh[0] = key_schedule(kc[4 * j + 0], kc[4 * j + 1]);
       kh[1] = key_schedule(kc[4 * j + 2], kc[4 * j + 3]);
+    } else if (!WARP_TEAM) {
+      cta_sweep_keys(reinterpret_cast<uint32_t*>(hist_s + 2 * 2 * 2 * kIsingClasses + 2), ks_rep, t, T, sh.direct_keys != 0,
+                     kh[0], kh[1], t_first, t_end);
     } else {
       sweep_keys(ks_rep, t, T, sh.direct_keys != 0, kh[0], kh[1]);
     }
@@ -666,30 +694,6 @@ __global__ void ising_status_kernel(const unsigned* status, float* summary, size
   if (*status == 0u) return;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     summary[i] = __int_as_float(0x7fc00000);
-}
-
-// CTA-per-replica kernels: the half-sweep keys of the next kKeyBatch sweeps, derived by warp 0 (lane j takes sweep
-// t + j) into a CTA-shared cache kc[kKeyBatch][4]; every thread then reads its sweep's four words (the warp-team
-// kernel does the same per warp, see ising_fast_kernel).  Called by ALL threads of the CTA at every sweep.
-__device__ __forceinline__ void cta_sweep_keys(uint32_t* kc, const KeySchedule& ks_rep, int t, int T, bool direct,
-                                               KeySchedule& k_first, KeySchedule& k_second) {
-  if (kKeyBatch == 0) {
-    sweep_keys(ks_rep, t, T, direct, k_first, k_second);
-    return;
-  }
-  const int j = (t - 1) % kKeyBatch;
-  if (j == 0) {
-    __syncthreads();   // every thread has read the previous batch
-    if (threadIdx.x < 32 && t + (int)threadIdx.x < T) {
-      KeySchedule a, b;
-      sweep_keys(ks_rep, t + (int)threadIdx.x, T, direct, a, b);
-      kc[4 * threadIdx.x + 0] = a.ks0; kc[4 * threadIdx.x + 1] = a.ks1;
-      kc[4 * threadIdx.x + 2] = b.ks0; kc[4 * threadIdx.x + 3] = b.ks1;
-    }
-    __syncthreads();
-  }
-  k_first = key_schedule(kc[4 * j + 0], kc[4 * j + 1]);
-  k_second = key_schedule(kc[4 * j + 2], kc[4 * j + 3]);
 }
 
 // ------------------------------------------------------------------------------ bit-packed 3-D kernel
@@ -1486,7 +1490,7 @@ static bool fast_path(int L) { return L % 64 == 0; }
 static size_t fast_smem_bytes(int L, bool warp_team, int nteams, bool global_lat = false) {
   const size_t lat_words = global_lat ? 0 : 2 * (size_t)L * (L / 64);
   size_t words = 4 * 256 + nteams * (lat_words + 2 * 256 * 2 + (warp_team ? 2 * 2 * 2 * kIsingClasses + 4 * kKeyBatch : 0));
-  if (!warp_team) words += 2 * 2 * 2 * kIsingClasses + 2;
+  if (!warp_team) words += 2 * 2 * 2 * kIsingClasses + 2 + 4 * kKeyBatch;   // histograms, 2 scratch ints, sweep-key cache
   return words * 4;
 }
 
