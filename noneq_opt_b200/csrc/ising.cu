@@ -1155,9 +1155,10 @@ __global__ void __launch_bounds__(256) ising_generic_kernel(const IsingShape sh,
   int* hist_s = reinterpret_cast<int*>(smem);               // [2][2][16]
   int* scratch = hist_s + 2 * 2 * kIsingClasses;            // [2]
   uint32_t* thr_s = reinterpret_cast<uint32_t*>(scratch + 2);  // [16]
+  uint32_t* kc = thr_s + kIsingClasses;                        // [kKeyBatch][4] sweep keys (cta_sweep_keys)
   const int T = sh.T, N = sh.N, d0 = sh.d0, d1 = sh.d1, d2 = sh.d2, ndim = sh.ndim;
   const long long rep = blockIdx.x;
-  signed char* sp = sh.scratch ? sh.scratch + (size_t)rep * N : reinterpret_cast<signed char*>(thr_s + kIsingClasses);
+  signed char* sp = sh.scratch ? sh.scratch + (size_t)rep * N : reinterpret_cast<signed char*>(kc + 4 * kKeyBatch);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ncls = 2 * ndim + 1;
   const size_t ext_words = ((size_t)N + 31) / 32;
@@ -1192,7 +1193,7 @@ __global__ void __launch_bounds__(256) ising_generic_kernel(const IsingShape sh,
   const KeySchedule ks_rep = key_schedule(io.seeds[2 * rep], io.seeds[2 * rep + 1]);
   for (int t = 1; t < T; ++t) {
     KeySchedule kh[2];
-    sweep_keys(ks_rep, t, T, sh.direct_keys != 0, kh[0], kh[1]);
+    cta_sweep_keys(kc, ks_rep, t, T, sh.direct_keys != 0, kh[0], kh[1]);
     if (threadIdx.x < kIsingClasses) thr_s[threadIdx.x] = io.thr[(size_t)(t - 1) * kIsingClasses + threadIdx.x];
     for (int v = threadIdx.x; v < 2 * 2 * kIsingClasses; v += blockDim.x) hist_s[v] = 0;
     __syncthreads();
@@ -1566,10 +1567,10 @@ static SegPlan plan_segments(int L, long long R, int T) {
   p.lat_bytes = (size_t)R * 2 * L * (L / 64) * 4;
   return p;
 }
+static const size_t kGenericSmemHeader = (2 * 2 * kIsingClasses + 2 + kIsingClasses + 4 * kKeyBatch) * 4;
 static size_t generic_smem_bytes(long long N) {
-  return (2 * 2 * kIsingClasses + 2 + kIsingClasses) * 4 + (((size_t)N + 3) / 4) * 4;
+  return kGenericSmemHeader + (((size_t)N + 3) / 4) * 4;
 }
-static const size_t kGenericSmemHeader = (2 * 2 * kIsingClasses + 2 + kIsingClasses) * 4;
 
 // lattice geometry of a descriptor: ndim == 0 means the 2-D square L x L
 static int lattice_dims(const NqIsingDesc* d, int dims[3]) {
